@@ -1,0 +1,218 @@
+"""oracle/pyoracle.py -- ctypes wrapper of the CPU oracle.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+kind="port"      -> oracle/liboracle.so (our restatement; travels to the GPU box)
+kind="reference" -> oracle/_ref/libsedi_ref.so (the reference's own plug-in sources, stub-compiled)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBS = {}
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def build(quiet=True):
+    """(Re)build the checker with oracle/Makefile.  _ref is only built where /root/reference exists."""
+    subprocess.run(["make", "-C", _HERE], check=True, stdout=subprocess.DEVNULL if quiet else None)
+
+
+def _load(kind):
+    if kind in _LIBS:
+        return _LIBS[kind]
+    path = os.path.join(_HERE, "liboracle.so" if kind == "port" else os.path.join("_ref", "libsedi_ref.so"))
+    if not os.path.exists(path):
+        if kind == "port":
+            build()
+        else:
+            raise FileNotFoundError(path)
+    lib = C.CDLL(path)
+    lib.ora_create.restype = C.c_void_p
+    lib.ora_create.argtypes = [C.c_int]
+    lib.ora_destroy.argtypes = [C.c_void_p]
+    lib.ora_command.argtypes = [C.c_void_p, C.c_char_p]
+    lib.ora_set_box.argtypes = [C.c_void_p, _dp, _dp, C.c_int]
+    lib.ora_add_atoms.argtypes = [C.c_void_p, C.c_int, _ip, _ip, _dp, _dp, _dp, C.c_void_p]
+    lib.ora_set_omega.argtypes = [C.c_void_p, _dp]
+    lib.ora_nlocal.argtypes = [C.c_void_p]
+    lib.ora_nghost.argtypes = [C.c_void_p]
+    lib.ora_get_atoms.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+    lib.ora_get_radius_mass.argtypes = [C.c_void_p, _dp, _dp]
+    lib.ora_put_fdrag.argtypes = [C.c_void_p, C.c_int, _dp, C.c_void_p, _ip]
+    lib.ora_set_timestep.argtypes = [C.c_void_p, C.c_double]
+    lib.ora_run.argtypes = [C.c_void_p, C.c_longlong]
+    lib.ora_setup.argtypes = [C.c_void_p]
+    lib.ora_reneighbor.argtypes = [C.c_void_p]
+    lib.ora_stat.restype = C.c_longlong
+    lib.ora_stat.argtypes = [C.c_void_p, C.c_int]
+    lib.ora_get_pairs.restype = C.c_longlong
+    lib.ora_get_pairs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]
+    lib.ora_get_wall_shear.argtypes = [C.c_void_p, C.c_int, _dp]
+    lib.ora_foam_jd_ergun_wenyu.argtypes = [C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp]
+    lib.ora_foam_jd_syamlal_obrien.argtypes = [C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp]
+    lib.ora_foam_particle_force.argtypes = [C.c_int, _ip, _dp, _dp, _dp, _dp, _dp, _dp, C.c_void_p, C.c_void_p,
+                                            C.c_int, C.c_int, C.c_double, C.c_double, _dp, C.c_double,
+                                            _dp, _dp, _dp, _dp, _dp, _dp]
+    lib.ora_foam_cell_owner.argtypes = [C.c_int, _dp, _dp, _dp, _ip, _ip]
+    lib.ora_foam_particle_to_eulerian.argtypes = [C.c_int, _ip, _dp, _dp, C.c_int, _dp, _dp, _dp]
+    lib.ora_foam_calc_tc.argtypes = [C.c_int, _ip, _dp, _dp, _dp, _dp, C.c_int, _dp, C.c_int, C.c_double, C.c_double, _dp, _dp]
+    _LIBS[kind] = lib
+    return lib
+
+
+def have_reference():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libsedi_ref.so"))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """CPU DEM time loop driven by LAMMPS script lines -- the checker for the CUDA engine."""
+
+    def __init__(self, kind="port"):
+        self.kind = kind
+        self.lib = _load(kind)
+        self.h = self.lib.ora_create(1 if kind == "reference" else 0)
+        if not self.h:
+            raise RuntimeError("oracle backend %r unavailable" % kind)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.ora_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def command(self, line):
+        self.lib.ora_command(self.h, line.encode())
+
+    def commands(self, text):
+        for ln in text.strip().splitlines():
+            self.command(ln)
+
+    def set_box(self, lo, hi, ntypes=1):
+        self.lib.ora_set_box(self.h, np.ascontiguousarray(lo, np.float64), np.ascontiguousarray(hi, np.float64), ntypes)
+
+    def add_atoms(self, tag, typ, diam, rho, x, v=None):
+        n = len(tag)
+        x = np.ascontiguousarray(x, np.float64).reshape(n, 3)
+        v = None if v is None else np.ascontiguousarray(v, np.float64).reshape(n, 3)
+        self.lib.ora_add_atoms(self.h, n, np.ascontiguousarray(tag, np.int32), np.ascontiguousarray(typ, np.int32),
+                               np.ascontiguousarray(diam, np.float64), np.ascontiguousarray(rho, np.float64), x, _ptr(v))
+
+    def set_omega(self, omega):
+        self.lib.ora_set_omega(self.h, np.ascontiguousarray(omega, np.float64))
+
+    @property
+    def nlocal(self):
+        return self.lib.ora_nlocal(self.h)
+
+    def setup(self):
+        self.lib.ora_setup(self.h)
+
+    def run(self, n):
+        self.lib.ora_run(self.h, int(n))
+
+    def reneighbor(self):
+        self.lib.ora_reneighbor(self.h)
+
+    def set_timestep(self, dt):
+        self.lib.ora_set_timestep(self.h, float(dt))
+
+    def put_fdrag(self, fdrag, tags, foam_cpu=None):
+        n = len(tags)
+        fc = None if foam_cpu is None else np.ascontiguousarray(foam_cpu, np.int32)
+        self.lib.ora_put_fdrag(self.h, n, np.ascontiguousarray(fdrag, np.float64).reshape(n, 3), _ptr(fc),
+                               np.ascontiguousarray(tags, np.int32))
+
+    def atoms(self):
+        """dict of owned-atom arrays, sorted by tag (identity across the boundary is the tag)."""
+        n = self.nlocal
+        out = {k: np.zeros((n, 3)) for k in ("x", "v", "omega", "f", "torque")}
+        tag = np.zeros(n, np.int32)
+        self.lib.ora_get_atoms(self.h, _ptr(out["x"]), _ptr(out["v"]), _ptr(out["omega"]), _ptr(out["f"]),
+                               _ptr(out["torque"]), _ptr(tag))
+        o = np.argsort(tag, kind="stable")
+        res = {k: a[o] for k, a in out.items()}
+        res["tag"] = tag[o]
+        return res
+
+    def stat(self, name):
+        return int(self.lib.ora_stat(self.h, {"nbuilds": 0, "pair_evals": 1, "steps": 2, "gran_pairs": 3,
+                                              "half_pairs": 4, "full_pairs": 5}[name]))
+
+    def pairs(self, which="gran", history=False):
+        w = {"gran": 0, "half": 1, "full": 2}[which]
+        m = int(self.lib.ora_get_pairs(self.h, w, None, None, None, None, 0))
+        ti = np.zeros(m, np.int32); tj = np.zeros(m, np.int32)
+        touch = np.zeros(m, np.int32) if history else None
+        shear = np.zeros((m, 3)) if history else None
+        self.lib.ora_get_pairs(self.h, w, _ptr(ti), _ptr(tj), _ptr(touch), _ptr(shear), m)
+        return (ti, tj, touch, shear) if history else (ti, tj)
+
+    def wall_shear(self, wall):
+        out = np.zeros((self.nlocal, 3))
+        self.lib.ora_get_wall_shear(self.h, wall, out)
+        return out
+
+
+# ---- OpenFOAM-side coupling restatement -------------------------------------------------------------
+FORCE_DRAG, FORCE_PGRAD, FORCE_BUOY, FORCE_ADDEDMASS, FORCE_LIFT = 1, 2, 4, 8, 16
+DRAG_ERGUN_WENYU, DRAG_SYAMLAL_OBRIEN = 0, 1
+
+
+def jd(model, Ur, alpha, pd, nuf, rhof, kind="port"):
+    lib = _load(kind)
+    Ur = np.ascontiguousarray(Ur, np.float64)
+    out = np.zeros_like(Ur)
+    fn = lib.ora_foam_jd_ergun_wenyu if model == DRAG_ERGUN_WENYU else lib.ora_foam_jd_syamlal_obrien
+    fn(len(Ur), Ur, np.ascontiguousarray(alpha, np.float64), np.ascontiguousarray(pd, np.float64), nuf, rhof, out)
+    return out
+
+
+def particle_force(cell, d, U, UOld, Uf, gamma, gradp, DDtU, curlU, model, flags, nub, rhob, g, deltaT, kind="port"):
+    lib = _load(kind)
+    n = len(cell)
+    c = lambda a: np.ascontiguousarray(a, np.float64)
+    Uri = np.zeros((n, 3)); mag = np.zeros(n); al = np.zeros(n); Jd = np.zeros(n); F = np.zeros((n, 3)); DuDt = np.zeros((n, 3))
+    DDtU = None if DDtU is None else c(DDtU)
+    curlU = None if curlU is None else c(curlU)
+    lib.ora_foam_particle_force(n, np.ascontiguousarray(cell, np.int32), c(d), c(U), c(UOld), c(Uf), c(gamma), c(gradp),
+                                _ptr(DDtU), _ptr(curlU), model, flags, nub, rhob, c(g), deltaT, Uri, mag, al, Jd, F, DuDt)
+    return dict(Uri=Uri, magUri=mag, alpha=al, Jd=Jd, F=F, DuDt=DuDt)
+
+
+def cell_owner(x, lo, hi, ncell, kind="port"):
+    lib = _load(kind)
+    x = np.ascontiguousarray(x, np.float64)
+    out = np.zeros(len(x), np.int32)
+    lib.ora_foam_cell_owner(len(x), x, np.ascontiguousarray(lo, np.float64), np.ascontiguousarray(hi, np.float64),
+                            np.ascontiguousarray(ncell, np.int32), out)
+    return out
+
+
+def particle_to_eulerian(cell, d, U, cellV, kind="port"):
+    lib = _load(kind)
+    Cn = len(cellV)
+    gamma = np.zeros(Cn); Ue = np.zeros((Cn, 3))
+    lib.ora_foam_particle_to_eulerian(len(cell), np.ascontiguousarray(cell, np.int32), np.ascontiguousarray(d, np.float64),
+                                      np.ascontiguousarray(U, np.float64), Cn, np.ascontiguousarray(cellV, np.float64), gamma, Ue)
+    return gamma, Ue
+
+
+def calc_tc(cell, d, U, Uf, gamma, cellV, model, nub, rhob, kind="port"):
+    lib = _load(kind)
+    Cn = len(cellV)
+    Asrc = np.zeros((Cn, 3)); Omega = np.zeros(Cn)
+    c = lambda a: np.ascontiguousarray(a, np.float64)
+    lib.ora_foam_calc_tc(len(cell), np.ascontiguousarray(cell, np.int32), c(d), c(U), c(Uf), c(gamma), Cn, c(cellV), model,
+                         nub, rhob, Asrc, Omega)
+    return Asrc, Omega

@@ -1,0 +1,1 @@
+// oracle/stubs: intentionally empty (included but unused by pair_lubricate_poly.cpp).
