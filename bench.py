@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200: M particle-contact-updates / s at 1e6 particles.
+
+One "step" = one coupling step of the particle hot path on a 1e6-particle bed (BASELINE.json configs[2]):
+    fluid force (gather Uf / gamma / grad p at the owner cell, ErgunWenYu drag)  ->  `substeps` DEM sub-steps
+    (neighbour rebuilds as needed, Hertz-Mindlin contact sweep with shear history, wall/granFix, gravity, fdrag,
+    nve/sphere)  ->  cell-owner location  ->  scatter of void fraction / solid velocity / momentum source.
+Unit of work: one neighbour-list pair evaluated by the contact sweep in one DEM sub-step, counted once
+per undirected pair.
+
+value : device-resident throughput (cell fields and particle state already in HBM), CUDA events on the engine stream.
+e2e   : the same metric through the reference's own boundary (interfaceToLammps/library.h): host fluid-force array ->
+        lammps_put_local_info -> lammps_step(substeps) -> lammps_get_local_info -> host x, v ; copies inside the timing.
+roofline : dominant kernel k_step (one fused DEM sub-step), algorithmic bytes 188 N + 56 P per launch over its
+        CUDA-event duration, against MEASURED_PEAKS.json.
+cpu_baseline / --impl reference : the reference's own plug-in sources (oracle/_ref, compiled from /root/reference by
+        oracle/Makefile) driven by the oracle's restated LAMMPS loop on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "M particle-contact-updates/sec at 1e6 particles"
+UNIT = "M pair-updates/s"
+BED_DIMS = (100, 100, 100)   # 1e6 particles per GPU
+SUBSTEPS = 100               # DEM sub-steps per coupling step (shipped cases: dt_fluid / dt_DEM = 100)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# CPU side: the reference's own objects (kind "reference") or the port, on the host cores
+# --------------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    dims, nsteps, kind, seed = args
+    from oracle import pyoracle
+    from sedifoam_b200 import cases
+    case = cases.fluidized_bed(dims=dims, seed=seed)
+    o = pyoracle.Oracle(kind)
+    cases.apply(case, o)
+    o.setup()
+    n = len(case["tag"])
+    m = case["rho"] * np.pi / 6.0 * case["diam"] ** 3
+    o.put_fdrag(np.tile([0.0, 9.8 * 0.3, 0.0], (n, 1)) * m[:, None], case["tag"])
+    e0 = o.stat("pair_evals")
+    t0 = time.perf_counter()
+    o.run(nsteps)
+    dt = time.perf_counter() - t0
+    return o.stat("pair_evals") - e0, dt, n
+
+
+def cpu_throughput(nsteps, cores, dims_total=BED_DIMS):
+    """`cores` independent sub-domain replicas of the bed (1/cores of the particles each, no halo exchange): an upper
+    bound for a `cores`-rank MPI run of the reference, which has no threading of its own."""
+    import multiprocessing as mp
+    from oracle import pyoracle
+    kind = "reference" if pyoracle.have_reference() else "port"
+    if cores == 1:
+        dims = dims_total
+    else:
+        f = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[cores]
+        dims = tuple(max(2, dims_total[k] // f[k]) for k in range(3))
+    jobs = [(dims, nsteps, kind, 20261017 + r) for r in range(cores)]
+    if cores == 1:
+        res = [_cpu_worker(jobs[0])]
+    else:
+        with mp.get_context("spawn").Pool(cores) as pool:
+            res = pool.map(_cpu_worker, jobs)
+    evals = sum(r[0] for r in res)
+    tmax = max(r[1] for r in res)
+    npart = sum(r[2] for r in res)
+    return dict(value=evals / tmax / 1e6, unit=UNIT, cores=cores, kind=kind,
+                sample="%d particles (%d sub-domain replicas of %s, no halo), %d DEM sub-steps, %.1f s" %
+                       (npart, cores, "x".join(map(str, dims)), nsteps, tmax),
+                seconds=tmax, pair_evals=evals)
+
+
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.max_mhz = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def load_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--dims", default=None, help="override the bed lattice, e.g. 50x50x50 (testing only)")
+    ap.add_argument("--substeps", type=int, default=SUBSTEPS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dims = tuple(int(v) for v in args.dims.split("x")) if args.dims else BED_DIMS
+    K, W, S = args.steps, max(args.warmup, 0), args.substeps
+    config = {"workload": "configs[2]: %d-particle fluidized bed per GPU, gran/hertzFix/history + wall/granFix + fdrag(ErgunWenYu), "
+                          "%d DEM sub-steps per coupling step" % (int(np.prod(dims)), S),
+              "particles_per_gpu": int(np.prod(dims)), "substeps_per_step": S, "dt_dem": 2e-6, "skin_over_d": 0.25,
+              "decomposition": "1 GPU" if world == 1 else "%d bricks" % world}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cores = os.cpu_count() or 1
+        cores = 8 if cores >= 8 else (4 if cores >= 4 else (2 if cores >= 2 else 1))
+        nsteps = 10
+        # each "step" of the reference arm is a bounded sample: `nsteps` DEM sub-steps of the same bed on all host cores
+        vals = []
+        t_all = time.perf_counter()
+        for it in range(W + K):
+            r = cpu_throughput(nsteps, cores, dims)
+            if it >= W:
+                vals.append(r)
+            if time.perf_counter() - t_all > 240 and len(vals) >= 1:
+                break
+        v = float(np.mean([r["value"] for r in vals]))
+        ms = float(np.mean([r["seconds"] for r in vals])) * 1e3
+        line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": W, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "impl": "reference", "config": config,
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": vals[-1]["cores"], "kind": vals[-1]["kind"], "sample": vals[-1]["sample"]},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import sedifoam_b200 as sb
+    from sedifoam_b200 import cases
+    if not torch.cuda.is_available():
+        print("bench.py: no CUDA device; the particle hot path has no CPU fallback", file=sys.stderr)
+        return 2
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    case = cases.fluidized_bed(dims=dims, seed=cases.SEED + rank)
+    n = len(case["tag"])
+    eng = sb.Lammps(device=local_rank)
+    cases.apply(case, eng)
+    eng.mesh_box(case["mesh_lo"], case["mesh_hi"], case["mesh_n"])
+    eng.coupling_config(sb.DRAG_ERGUN_WENYU, sb.FORCE_DRAG | sb.FORCE_PGRAD, case["nub"], case["rhob"], case["g"], S * case["dt"])
+    Uf, gamma, gradp = cases.uniform_fields(case)
+    eng.put_cell_fields(Uf, gamma, gradp)
+    eng.setup()
+    eng.scatter_alpha_u(device_only=True)
+
+    def device_step():
+        eng.compute_fluid_force()
+        eng.sedi_step(S)
+        eng.scatter_alpha_u(device_only=True)
+        eng.calc_tc(device_only=True)
+
+    for _ in range(W):
+        device_step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    eng.reset_stats()
+    eng.profile(True)
+    barrier(); eng.synchronize()
+    t0 = time.perf_counter()
+    eng.timer_start()
+    for _ in range(K):
+        device_step()
+    ms_dev = eng.timer_stop_ms()
+    eng.synchronize(); barrier()
+    wall = time.perf_counter() - t0
+    ms = allmax(max(ms_dev, 0.0))
+    evals = eng.stat("pair_evals"); launches = eng.stat("launches"); nbuilds = eng.stat("nbuilds")
+    ksteps, kms = eng.get_profile()
+    eng.profile(False)
+    pairs_now = eng.stat("gran_pairs")
+    tot_evals = allsum(float(evals))
+    value = tot_evals / (ms * 1e-3) / 1e6
+
+    # ---- e2e through the reference boundary with host buffers
+    fd = np.zeros((n, 3)); tags = case["tag"].copy()
+    xh = np.zeros((n, 3)); vh = np.zeros((n, 3)); foam = np.zeros(n, np.int32); lmp = np.zeros(n, np.int32); tg = np.zeros(n, np.int32)
+    m = case["rho"] * np.pi / 6.0 * case["diam"] ** 3
+    fd[:, 1] = 0.3 * 9.8 * m
+
+    def e2e_step():
+        eng.put_local_info(fd, tags, foam_cpu=foam)
+        eng.step(S)
+        eng.get_local_info(xh, vh, foam, lmp, tg)
+
+    e2e_step()
+    eng.reset_stats()
+    barrier(); eng.synchronize()
+    t1 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    eng.synchronize()
+    e2e_s = allmax(time.perf_counter() - t1)
+    barrier()
+    e2e_evals = allsum(float(eng.stat("pair_evals")))
+    e2e_value = e2e_evals / e2e_s / 1e6
+    h2d = n * (24 + 4 + 4)
+    d2h = n * (24 + 24 + 4 + 4)
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    # ---- roofline of the dominant kernel (fused DEM sub-step): 188 B / particle + 56 B / undirected pair per launch
+    peak, peak_src = load_peak()
+    P_avg = evals / max(1, eng_steps(K, S))
+    alg_bytes = 188.0 * n + 56.0 * P_avg
+    k_avg_ms = kms / max(1, ksteps)
+    achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9 if k_avg_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "k_step_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "k_step<gran/hertzFix/history>", "avg_launch_us": k_avg_ms * 1e3, "launches_timed": ksteps,
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "kernel_share_of_step": kms / ms_dev if ms_dev > 0 else None}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            cores = 8 if (os.cpu_count() or 1) >= 8 else 1
+            cpu = cpu_throughput(10, cores, dims)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as ex:  # the checker is test infrastructure; its absence must not break the GPU number
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
+
+    if rank == 0:
+        config.update({"pairs_per_particle": pairs_now / n, "neighbor_rebuilds_in_timed_region": nbuilds,
+                       "l2": "per-step working set (2x96 B state + list + history > 300 MB at 1e6 particles) exceeds the 126 MB L2; no flush needed",
+                       "solid_fraction": float(np.pi / 6 / (1 - 2e-3) ** 3)})
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
+                "particle_steps_per_s": world * n * K * S / (ms * 1e-3), "wall_s_timed_region": wall}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def eng_steps(K, S):
+    return K * S
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,128 @@
+/* sedi_b200.h -- C-ABI of libsedi_b200.so, the B200-native particle hot path of sediFoam.
+ *
+ * Two groups of entry points, all `extern "C"`, plain pointers and sizes only:
+ *
+ * (1) The drop-in boundary: the 17 `lammps_*` functions of the reference's own C interface between the OpenFOAM
+ *     side and LAMMPS (/root/reference/interfaceToLammps/library.h:29-63).  Same names, same argument meaning,
+ *     caller-allocated arrays, identity across the boundary = atom tag.  `softParticleCloud`
+ *     (lammpsFoam/softParticleCloud.C:119-163, :838-922) links against these unchanged.  MPI_Comm is an `int`
+ *     here when no MPI is present (define SEDI_HAVE_MPI before including to use <mpi.h>).
+ *
+ * (2) `sedi_*`: the device-resident API used by the host-side mirror of `enhancedCloud` (host/) so that per-particle
+ *     data never crosses PCIe: fluid cell fields in, Eulerian cell fields out.
+ *
+ * Errors follow the reference convention (library.cpp:380-383): print to stderr and abort().  There is no CPU
+ * fallback: every compute entry point requires a CUDA device and aborts without one.
+ */
+#ifndef SEDI_B200_H
+#define SEDI_B200_H
+
+#ifdef SEDI_HAVE_MPI
+#include <mpi.h>
+#else
+typedef int MPI_Comm; /* single-process stand-in; reference: library.h:19 includes mpi.h */
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- (1) drop-in boundary: interfaceToLammps/library.h ------------------------------------------------ */
+void lammps_open(int argc, char **argv, MPI_Comm comm, void **ptr);            /* library.h:29, library.cpp:44-49  */
+void lammps_close(void *ptr);                                                  /* library.h:30, library.cpp:55-59  */
+void lammps_file(void *ptr, char *path);                                       /* library.h:31, library.cpp:65-69  */
+char *lammps_command(void *ptr, char *line);                                   /* library.h:32, library.cpp:75-79  */
+void lammps_sync(void *ptr);                                                   /* library.h:34, library.cpp:82-87  */
+int lammps_get_global_n(void *ptr);                                            /* library.h:35, library.cpp:96-101 */
+void lammps_get_initial_np(void *ptr, int *np);                                /* library.h:38, library.cpp:109-135 */
+void lammps_get_initial_info(void *ptr, double *coords, double *velos, double *diam, double *rho, int *tag,
+                             int *lmpCpuId, int *type);                        /* library.h:40-42, library.cpp:142-206 */
+int lammps_get_local_n(void *ptr);                                             /* library.h:45, library.cpp:210-217 */
+void lammps_get_local_domain(void *ptr, double *domain);                       /* library.h:48, library.cpp:222-240 */
+void lammps_get_local_info(void *ptr, double *coords, double *velos, int *foamCpuId, int *lmpCpuId,
+                           int *tag);                                          /* library.h:51-52, library.cpp:246-308 */
+void lammps_put_local_info(void *ptr, int nLocalIn, double *fdrag, double *DuDt, int *foamCpuIdIn,
+                           int *tagIn);                                        /* library.h:55-56, library.cpp:314-367 */
+void lammps_step(void *ptr, int n);                                            /* library.h:58, library.cpp:372-386 */
+void lammps_set_timestep(void *ptr, double dt);                                /* library.h:59, library.cpp:398-402 */
+double lammps_get_timestep(void *ptr);                                         /* library.h:60, library.cpp:390-394 */
+void lammps_create_particle(void *ptr, int npAdd, double *position, double *tag, double diameter, double rho,
+                            int type, double *vel);                            /* library.h:61-62, library.cpp:406-503 */
+void lammps_delete_particle(void *ptr, int *deleteList, int nDelete);          /* library.h:63, library.cpp:507-621 */
+
+/* ---- (2) device-resident engine API -------------------------------------------------------------------- */
+int sedi_abi_version(void);
+int sedi_device_count(void); /* number of CUDA devices visible (0 on a CPU-only box; never aborts) */
+void sedi_set_device(void *ptr, int dev); /* before the first compute call; default: $SEDI_DEVICE, $LOCAL_RANK, 0 */
+
+/* programmatic equivalents of `read_data` (box header + Atoms section: id type diameter density x y z) */
+void sedi_set_box(void *ptr, const double *lo, const double *hi, int ntypes);
+void sedi_add_atoms(void *ptr, int n, const int *tag, const int *type, const double *diameter, const double *density,
+                    const double *x, const double *v /* may be NULL */);
+void sedi_set_omega(void *ptr, int n, const int *tag, const double *omega);
+
+/* full state download for tests / checkpoints, rows in device order; any pointer may be NULL */
+void sedi_get_state(void *ptr, double *x, double *v, double *omega, double *f, double *torque, double *radius,
+                    double *rmass, int *tag, int *type, int *mask);
+/* directed neighbour list as (tag_i, tag_j, meta) rows; returns the row count; call with cap = 0 to size.
+ * meta: bit30 granular list, bit31 type-cutoff list, bits 25..29 periodic image code (13 = none). */
+long long sedi_get_pairs(void *ptr, int *tag_i, int *tag_j, unsigned *meta, int *touch, double *shear, long long cap);
+void sedi_get_wall_shear(void *ptr, int wall, double *shear /* [n][3], device order */);
+void sedi_force_rebuild(void *ptr);
+/* which: 0 neighbour rebuilds, 1 undirected granular pair evaluations, 2 DEM steps, 3 directed granular entries,
+ *        4 directed type-list entries, 5 ELL row capacity, 6 kernel launches issued, 7 local particle count */
+long long sedi_get_stat(void *ptr, int which);
+void sedi_reset_stats(void *ptr);
+void sedi_synchronize(void *ptr);
+void *sedi_stream(void *ptr); /* the cudaStream_t every kernel of this engine is launched on */
+/* last event-timed DEM kernel time of lammps_step / sedi_step in milliseconds (CUDA events on the engine stream) */
+double sedi_last_step_ms(void *ptr);
+/* CUDA-event stopwatch on the engine stream (bench.py's timed region) */
+void sedi_timer_start(void *ptr);
+double sedi_timer_stop_ms(void *ptr);
+/* per-kernel timing of the fused DEM sub-step kernel: CUDA events bracket each back-to-back group of k_step
+ * launches; sedi_get_profile returns the number of executed launches and their summed duration */
+void sedi_profile(void *ptr, int on);
+long long sedi_get_profile(void *ptr, double *kernel_ms);
+
+/* --- coupling (mirror of enhancedCloud, device resident).  Mesh = single-block uniform blockMesh. */
+void sedi_mesh_box(void *ptr, const double *lo, const double *hi, const int *ncell);
+int sedi_mesh_ncells(void *ptr);
+/* drag model / force switches: names of constant/cloudProperties (enhancedCloud.C:586-598) */
+#define SEDI_DRAG_ERGUN_WENYU_ID 0
+#define SEDI_DRAG_SYAMLAL_OBRIEN_ID 1
+#define SEDI_FORCE_DRAG_BIT 1
+#define SEDI_FORCE_PGRAD_BIT 2
+#define SEDI_FORCE_BUOY_BIT 4
+#define SEDI_FORCE_ADDEDMASS_BIT 8
+#define SEDI_FORCE_LIFT_BIT 16
+void sedi_coupling_config(void *ptr, int drag_model, int force_flags, double nub, double rhob, const double *g,
+                          double deltaT);
+/* host cell fields -> device (Uf, gradp, DDtU, curlU are [C][3]; gamma is [C]); NULL = leave unchanged / absent */
+void sedi_put_cell_fields(void *ptr, const double *Uf, const double *gamma, const double *gradp, const double *DDtU,
+                          const double *curlU);
+/* locate particles in cells (cell owner index, int32, -1 = outside) */
+void sedi_locate(void *ptr);
+/* updateParticleUr + updateParticleAlpha + Jd + updateDragOnParticles: writes fix fdrag's per-atom force on device */
+void sedi_compute_fluid_force(void *ptr);
+/* particleToEulerianField: gamma[C], Ue[C][3] (host pointers, may be NULL to keep results on the device) */
+void sedi_scatter_alpha_u(void *ptr, double *gamma, double *Ue);
+/* calcTcFields: Asrc[C][3] ; Omega[C] is identically zero in the reference (enhancedCloud.C:391) */
+void sedi_calc_tc(void *ptr, double *Asrc, double *Omega);
+void sedi_enable_diag(void *ptr, int on); /* keep Uri/|Uri|/alpha/Jd per particle at the next sedi_compute_fluid_force */
+/* diagnostics of the last sedi_compute_fluid_force, device order: cell[n], Uri[n][3], magUri[n], alpha[n], Jd[n],
+ * F[n][3]; any pointer may be NULL */
+void sedi_get_coupling_diag(void *ptr, int *cell, double *Uri, double *magUri, double *alphap, double *Jd, double *F);
+/* same as lammps_step but never touches host particle arrays */
+void sedi_step(void *ptr, int n);
+
+/* --- multi-GPU: one process per GPU, brick decomposition of the particle box (LAMMPS `processors Px Py Pz`).
+ * The NCCL unique id is produced by rank 0 (sedi_comm_unique_id) and distributed by the host (MPI_Bcast in a real
+ * lammpsFoam run, torch.distributed in bench.py); procgrid may be NULL (taken from the script / factorised). */
+int sedi_comm_unique_id(void *out, int cap); /* returns the id size in bytes, 0 when NCCL is unavailable */
+int sedi_comm_init(void *ptr, int rank, int nranks, const void *nccl_unique_id, int id_bytes, const int *procgrid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEDI_B200_H */

@@ -51,7 +51,7 @@ def _load(kind):
     lib.ora_stat.restype = C.c_longlong
     lib.ora_stat.argtypes = [C.c_void_p, C.c_int]
     lib.ora_get_pairs.restype = C.c_longlong
-    lib.ora_get_pairs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]
+    lib.ora_get_pairs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]
     lib.ora_get_wall_shear.argtypes = [C.c_void_p, C.c_int, _dp]
     lib.ora_foam_jd_ergun_wenyu.argtypes = [C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp]
     lib.ora_foam_jd_syamlal_obrien.argtypes = [C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp]
@@ -151,11 +151,13 @@ class Oracle:
 
     def pairs(self, which="gran", history=False):
         w = {"gran": 0, "half": 1, "full": 2}[which]
-        m = int(self.lib.ora_get_pairs(self.h, w, None, None, None, None, 0))
+        m = int(self.lib.ora_get_pairs(self.h, w, None, None, None, None, 0, None))
         ti = np.zeros(m, np.int32); tj = np.zeros(m, np.int32)
         touch = np.zeros(m, np.int32) if history else None
         shear = np.zeros((m, 3)) if history else None
-        self.lib.ora_get_pairs(self.h, w, _ptr(ti), _ptr(tj), _ptr(touch), _ptr(shear), m)
+        ghost = np.zeros(m, np.int32)
+        self.lib.ora_get_pairs(self.h, w, _ptr(ti), _ptr(tj), _ptr(touch), _ptr(shear), m, _ptr(ghost))
+        self.last_ghost = ghost
         return (ti, tj, touch, shear) if history else (ti, tj)
 
     def wall_shear(self, wall):

@@ -110,7 +110,7 @@ long long ora_stat(void *p, int which) {
 
 // Neighbour-list export as (tag_i, tag_j) rows (ghost partners report the tag of their source atom).
 // which: 0 granular half list, 1 type-cutoff half list (fix cohesive), 2 full list (lubricate/poly).
-long long ora_get_pairs(void *p, int which, int *ti, int *tj, int *touch, double *shear, long long cap) {
+long long ora_get_pairs(void *p, int which, int *ti, int *tj, int *touch, double *shear, long long cap, int *ghost) {
   Sim *s = (Sim *)p;
   CSRList &l = which == 0 ? s->gran : which == 1 ? s->half : s->full;
   long long m = 0;
@@ -119,6 +119,7 @@ long long ora_get_pairs(void *p, int which, int *ti, int *tj, int *touch, double
       const int k = l.offset[i] + jj;
       if (m < cap) {
         ti[m] = s->tag[i]; tj[m] = s->tag[l.neigh[k]];
+        if (ghost) ghost[m] = (l.neigh[k] >= s->nlocal) ? 1 : 0;
         if (touch) touch[m] = (l.history ? l.touch[k] : 0);
         if (shear) for (int d = 0; d < 3; d++) shear[3 * m + d] = l.history ? l.shear[3 * (size_t)k + d] : 0.0;
       }

@@ -1,0 +1,197 @@
+"""Synthetic particle cases (seeded) shared by tests/ and bench.py -- the configurations of BASELINE.json / SURVEY.md 8(d).
+
+A case is a plain dict: box, atoms (tag, type, diam, rho, x, v), a LAMMPS script (the plug-in API of the reference:
+`pair_style gran/hertzFix/history`, `fix fdrag`, `fix cohesive`, `fix wall/granFix`, `pair_style lubricate/poly` ...),
+and the fluid-side description (uniform blockMesh box, cell fields, cloudProperties switches).  `apply(case, sim)`
+feeds it to either the CUDA engine (sedifoam_b200.Lammps) or the CPU oracle (oracle.pyoracle.Oracle): both expose
+set_box / add_atoms / commands.  SI numbers pass through LAMMPS `lj` units as in every shipped in.lammps.
+"""
+import numpy as np
+
+SEED = 20261017
+
+
+def lattice(dims, spacing, origin, jitter, rng):
+    nx, ny, nz = dims
+    ix, iy, iz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    x = np.stack([ix.ravel(), iy.ravel(), iz.ravel()], axis=1).astype(np.float64)
+    x = np.asarray(origin, np.float64) + (x + 0.5) * np.asarray(spacing, np.float64)
+    if jitter:
+        x += rng.uniform(-jitter, jitter, size=x.shape)
+    return x
+
+
+def _base(x, d, rho, box_lo, box_hi, periodic, script, mesh_cell, typ=None, v=None, ntypes=1, extra=None):
+    n = len(x)
+    d = np.full(n, d, np.float64) if np.isscalar(d) else np.asarray(d, np.float64)
+    case = dict(
+        box_lo=np.asarray(box_lo, np.float64), box_hi=np.asarray(box_hi, np.float64), periodic=periodic, ntypes=ntypes,
+        tag=np.arange(1, n + 1, dtype=np.int32), type=np.ones(n, np.int32) if typ is None else np.asarray(typ, np.int32),
+        diam=d, rho=np.full(n, rho, np.float64), x=np.ascontiguousarray(x), v=np.zeros((n, 3)) if v is None else v,
+        script=script,
+    )
+    lo, hi = case["box_lo"], case["box_hi"]
+    nc = np.maximum(1, np.round((hi - lo) / mesh_cell)).astype(np.int32)
+    case["mesh_lo"], case["mesh_hi"], case["mesh_n"] = lo.copy(), hi.copy(), nc
+    case["nub"], case["rhob"] = 1.0e-6, 1000.0
+    if extra:
+        case.update(extra)
+    return case
+
+
+def apply(case, sim):
+    """Feed a case to an engine/oracle object exposing set_box, add_atoms, commands."""
+    sim.command("atom_style sphere")
+    sim.command("boundary " + " ".join(case["periodic"]))
+    sim.command("newton off")
+    sim.command("communicate single vel yes")
+    sim.set_box(case["box_lo"], case["box_hi"], case["ntypes"])
+    sim.add_atoms(case["tag"], case["type"], case["diam"], case["rho"], case["x"], case["v"])
+    sim.commands(case["script"])
+
+
+def fluidized_bed(dims=(100, 100, 100), d=5.0e-4, rho=2650.0, overlap=2.0e-3, skin_frac=0.25, dt=2.0e-6, kn=1.0e7, e=0.9,
+                  mu=0.4, head=0.5, seed=SEED, jitter_frac=1.0e-3, vjit=1.0e-3):
+    """configs[2]: dense bed -- jittered simple-cubic lattice with every particle in (slightly pre-compressed,
+    overlap*d) contact with its 6 lattice neighbours and the walls, solid fraction pi/6/(1-overlap)^3 = 0.527 -- in a
+    box with granular walls on all sides and free head-room on top; Hertz-Mindlin pair + wall/granFix + gravity +
+    fdrag.  The bed relaxes/expands during the run, which exercises history carry-over across neighbour rebuilds."""
+    rng = np.random.default_rng(seed)
+    a = d * (1.0 - overlap)
+    ext = np.array(dims, np.float64) * a
+    lo = np.zeros(3)
+    hi = ext.copy()
+    hi[1] = ext[1] * (1.0 + head)
+    x = lattice(dims, (a, a, a), lo, jitter_frac * d, rng)
+    v = rng.uniform(-vjit, vjit, size=x.shape)
+    script = f"""
+neighbor {skin_frac * d:.9g} bin
+neigh_modify delay 0
+pair_style gran/hertzFix/history {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1
+pair_coeff * *
+timestep {dt:.9g}
+fix 1 all nve/sphere
+fix 2 all gravity 9.8 vector 0 -1 0
+fix 3 all fdrag
+fix xw all wall/granFix {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 xplane {lo[0]:.17g} {hi[0]:.17g}
+fix yw all wall/granFix {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 yplane {lo[1]:.17g} {hi[1]:.17g}
+fix zw all wall/granFix {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 zplane {lo[2]:.17g} {hi[2]:.17g}
+"""
+    return _base(x, d, rho, lo, hi, ("f", "f", "f"), script, 4.0 * d, v=v,
+                 extra=dict(name="fluidized_bed", Uf=(0.0, 0.02, 0.0), g=(0.0, -9.8, 0.0), dt=dt, substeps=100))
+
+
+def sediment_column(dims=(36, 103, 27), d=5.0e-4, rho=2650.0, phi=0.30, skin_frac=0.25, dt=2.0e-6, kn=1.0e7, e=0.9, mu=0.4,
+                    seed=SEED, jitter_frac=0.05):
+    """configs[1]: monodisperse spheres sedimenting in a column periodic in x and z with a granular floor at y=0."""
+    rng = np.random.default_rng(seed)
+    a = d * (np.pi / 6.0 / phi) ** (1.0 / 3.0)
+    ext = np.array(dims, np.float64) * a
+    lo = np.zeros(3)
+    hi = ext.copy()
+    x = lattice(dims, (a, a, a), lo, jitter_frac * d, rng)
+    script = f"""
+neighbor {skin_frac * d:.9g} bin
+neigh_modify delay 0
+pair_style gran/hertzFix/history {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1
+pair_coeff * *
+timestep {dt:.9g}
+fix 1 all nve/sphere
+fix 2 all gravity 9.8 vector 0 -1 0
+fix 3 all fdrag
+fix yw all wall/granFix {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 yplane 0.0 NULL
+"""
+    return _base(x, d, rho, lo, hi, ("p", "f", "p"), script, 4.0 * d,
+                 extra=dict(name="sediment_column", Uf=(0.0, 0.0, 0.0), g=(0.0, -9.8, 0.0), dt=dt, substeps=100))
+
+
+def cohesive_shear_bed(dims=(40, 20, 40), d=5.0e-5, rho=2650.0, phi=0.55, dt=2.0e-8, kn=1.0e7, e=0.9, mu=0.4, opt=1,
+                       vshear=0.01, seed=SEED, jitter_frac=1.0e-3):
+    """configs[3]: cohesive silt bed, periodic in x/z, wall/granFix floor and a sheared wall/granFix lid, fix cohesive."""
+    rng = np.random.default_rng(seed)
+    a = d * (np.pi / 6.0 / phi) ** (1.0 / 3.0)
+    ext = np.array(dims, np.float64) * a
+    lo = np.zeros(3)
+    hi = ext.copy()
+    x = lattice(dims, (a, a, a), lo, jitter_frac * d, rng)
+    smax = 1.0e-6
+    skin = max(0.25 * d, 2.0 * smax)
+    script = f"""
+neighbor {skin:.9g} bin
+neigh_modify delay 0
+pair_style gran/hertzFix/history {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1
+pair_coeff * *
+timestep {dt:.9g}
+fix 1 all nve/sphere
+fix 2 all gravity 9.8 vector 0 -1 0
+fix 3 all fdrag
+fix 4 all cohesive 1e-20 1e-7 4e-10 {smax:.9g} {opt}
+fix yb all wall/granFix {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 yplane 0.0 NULL
+fix yt all wall/granFix {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 yplane NULL {hi[1]:.17g} shear x {vshear:.9g}
+"""
+    return _base(x, d, rho, lo, hi, ("p", "f", "p"), script, 4.0 * d,
+                 extra=dict(name="cohesive_shear_bed", Uf=(0.05, 0.0, 0.0), g=(0.0, -9.8, 0.0), dt=dt, substeps=100))
+
+
+def poly_lubricated(dims=(20, 20, 20), dmin=3.0e-4, dmax=7.0e-4, rho=2650.0, phi=0.45, dt=2.0e-6, kn=1.0e7, e=0.9, mu=0.4,
+                    visc=1.0e-3, seed=SEED, vjit=0.01):
+    """configs[4]: polydisperse periodic packing with hybrid/overlay gran/hertzFix/history + lubricate/poly (full list).
+    cut_inner is 1.001*dmax: the reference switches lubrication off inside cut_inner (pair_lubricate_poly.cpp:294-297)
+    and takes log(1/h) of the gap outside it (:308), so any overlapping pair must lie inside cut_inner (ri+rj <= dmax)
+    or the reference itself produces NaN."""
+    rng = np.random.default_rng(seed)
+    n = int(np.prod(dims))
+    diam = rng.uniform(dmin, dmax, size=n)
+    vol = np.pi / 6.0 * np.sum(diam ** 3)
+    a = (vol / phi / n) ** (1.0 / 3.0)
+    ext = np.array(dims, np.float64) * a
+    lo = np.zeros(3)
+    hi = ext.copy()
+    x = lattice(dims, (a, a, a), lo, 0.02 * dmin, rng)
+    v = rng.uniform(-vjit, vjit, size=x.shape)
+    skin = 0.1 * dmin
+    script = f"""
+neighbor {skin:.9g} bin
+neigh_modify delay 0
+pair_style hybrid/overlay gran/hertzFix/history {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 lubricate/poly {visc:.9g} 1 1 {1.001 * dmax:.9g} {1.5 * dmax:.9g}
+pair_coeff * *
+timestep {dt:.9g}
+fix 1 all nve/sphere
+fix 3 all fdrag
+"""
+    return _base(x, diam, rho, lo, hi, ("p", "p", "p"), script, 4.0 * dmax, v=v,
+                 extra=dict(name="poly_lubricated", Uf=(0.0, 0.0, 0.0), g=(0.0, 0.0, 0.0), dt=dt, substeps=100))
+
+
+def single_sphere():
+    """configs[0]: the shipped install check cases/auto-testing/test-cases/xiaocase3 (1 sphere, d = 83 um, rho = 2000,
+    uniform 0.05 m/s water flow, g = 0, stock gran/hooke/history + wall/gran, SyamlalOBrien drag, 100 DEM steps of
+    2e-7 s per fluid step of 2e-5 s; in.lammps:3-32, IC_uniform.in, constant/transportProperties)."""
+    x = np.array([[0.002, 0.0019, 0.00025]])
+    script = """
+neighbor 5.0e-4 bin
+neigh_modify delay 0
+pair_style gran/hooke/history 5000.0 NULL 11200 NULL 0.1 0
+pair_coeff * *
+timestep 2e-7
+velocity all set 0.0 0.0 0.0 units box
+fix 1 all nve/sphere
+fix 2 all gravity 0.0 vector 0 -1 0
+fix 3 all fdrag
+fix xwall all wall/gran 5000.0 NULL 11200 NULL 0.1 0 xplane 0.00 0.004
+fix ywall all wall/gran 5000.0 NULL 11200 NULL 0.1 0 yplane 0.00 0.004
+fix zwall all wall/gran 5000.0 NULL 11200 NULL 0.1 0 zplane 0.00 0.0005
+"""
+    c = _base(x, 8.3e-5, 2000.0, (0, 0, 0), (0.004, 0.004, 0.0005), ("f", "f", "f"), script, 4.0e-4,
+              extra=dict(name="single_sphere", Uf=(0.0, 0.05, 0.0), g=(0.0, 0.0, 0.0), dt=2e-7, substeps=100))
+    c["mesh_n"] = np.array([10, 10, 1], np.int32)
+    return c
+
+
+def uniform_fields(case, gamma=None):
+    """prescribed cell fields standing in for the OpenFOAM solver: uniform Uf, hydrostatic grad p, given gamma."""
+    C = int(np.prod(case["mesh_n"]))
+    Uf = np.tile(np.asarray(case["Uf"], np.float64), (C, 1))
+    gradp = np.tile(case["rhob"] * np.asarray(case["g"], np.float64), (C, 1))
+    gam = np.zeros(C) if gamma is None else gamma
+    return Uf, gam, gradp

@@ -1,0 +1,193 @@
+// sedi_couple.cuh -- two-way fluid<->particle coupling kernels (the OpenFOAM-side half of the hot path).
+//
+// Reference arithmetic followed:
+//   cell owner            softParticleCloud::setPositionVeloCpuId + Cloud::move on an axis-aligned blockMesh
+//                         (lammpsFoam/softParticleCloud.C:547-578, softParticle.C:102-151)
+//   gather + fluid force  enhancedCloud::updateParticleUr/Alpha/updateDragOnParticles (enhancedCloud.C:56-257)
+//   drag closures         ErgunWenYu::Jd (dragModels/ErgunWenYu/ErgunWenYu.C:104-132),
+//                         SyamlalOBrien::Jd (dragModels/SyamlalOBrien/SyamlalOBrien.C:106-143)
+//   scatter 1             enhancedCloud::particleToEulerianField (enhancedCloud.C:911-962)
+//   scatter 2             enhancedCloud::calcTcFields (enhancedCloud.C:316-416)
+// Cell fields keep OpenFOAM's memory layout (Field<vector> = interleaved xyz doubles, Field<scalar> = doubles) so the
+// host solver's internalField() storage can be passed straight through the C-ABI.
+#pragma once
+#include "sedi_device.cuh"
+
+namespace sedi {
+
+static __device__ __constant__ double kROOTVSMALL = 1.0e-150;
+
+struct MeshBox {  // single-block uniform hex mesh: cell = i + nx (j + ny k)
+  double lo[3], hi[3], dx[3];
+  int nc[3];
+};
+
+enum { SEDI_DRAG_ERGUN_WENYU = 0, SEDI_DRAG_SYAMLAL_OBRIEN = 1 };
+enum { SEDI_FORCE_DRAG = 1, SEDI_FORCE_PGRAD = 2, SEDI_FORCE_BUOY = 4, SEDI_FORCE_ADDEDMASS = 8, SEDI_FORCE_LIFT = 16 };
+
+__device__ __forceinline__ double jd_closure(int model, double Ur, double alpha, double pd, double nuf, double rhof) {
+  const double beta = fmax(1.0 - alpha, kROOTVSMALL);
+  if (model == SEDI_DRAG_ERGUN_WENYU) {
+    const double bp = pow(beta, -2.65);
+    const double Re = fmax(beta * Ur * pd / nuf, kROOTVSMALL);
+    double Cds = 24.0 * (1.0 + 0.15 * pow(Re, 0.687)) / Re;
+    if (Re > 1000.0) Cds = 0.44;
+    double K = 0.75 * Cds * rhof * Ur * bp / pd;
+    if (beta <= 0.8) K = 150.0 * alpha * nuf * rhof / ((beta * pd) * (beta * pd)) + 1.75 * rhof * Ur / (beta * pd);
+    return K;
+  }
+  const double Ai = pow(beta, 4.14);
+  double Bi = 0.8 * pow(beta, 1.28);
+  if (beta > 0.85) Bi = pow(beta, 2.65);
+  const double Re = fmax(Ur * pd / nuf, kROOTVSMALL);
+  const double Vr = 0.5 * (Ai - 0.06 * Re + sqrt((0.06 * Re) * (0.06 * Re) + 0.12 * Re * (2.0 * Bi - Ai) + Ai * Ai));
+  const double sq = 0.63 + 4.8 * sqrt(Vr / Re);
+  return 0.75 * (sq * sq) * rhof * Ur / (pd * (Vr * Vr));
+}
+
+__global__ void k_locate_cells(const D4 *posr, int n, MeshBox M, int *cell) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const D4 x = posr[p];
+  const double t0 = (x.x - M.lo[0]) / M.dx[0], t1 = (x.y - M.lo[1]) / M.dx[1], t2 = (x.z - M.lo[2]) / M.dx[2];
+  const int i0 = (int)floor(t0), i1 = (int)floor(t1), i2 = (int)floor(t2);
+  const bool in = !(t0 < 0.0) && !(t1 < 0.0) && !(t2 < 0.0) && i0 < M.nc[0] && i1 < M.nc[1] && i2 < M.nc[2];
+  cell[p] = in ? i0 + M.nc[0] * (i1 + M.nc[1] * i2) : -1;
+}
+
+struct ForceParams {
+  int n, model, flags;
+  const D4 *posr, *velm;
+  const int *cell;
+  const double *Uf, *gamma, *gradp, *DDtU, *curlU;  // cell fields (interleaved vectors)
+  double *uold[3];                                   // particle velocity at the previous coupling step
+  double *fdrag[3], *dudt[3];                        // outputs: fix fdrag's per-atom arrays
+  double *Uri, *magUri, *alphap, *Jd;                // optional diagnostics (interleaved / scalar), may be null
+  double nub, rhob, g[3], deltaT;
+};
+
+__global__ void __launch_bounds__(256) k_particle_force(const __grid_constant__ ForceParams P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  const int c = P.cell[i];
+  const D4 x = P.posr[i], v = P.velm[i];
+  double F0 = 0.0, F1 = 0.0, F2 = 0.0, u0 = 0.0, u1 = 0.0, u2 = 0.0, mag = 0.0, al = 0.0, jd = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  const double d = x.w * 2.0;  // library.cpp:194
+  if (c >= 0) {
+    u0 = P.Uf[3 * (size_t)c] - v.x; u1 = P.Uf[3 * (size_t)c + 1] - v.y; u2 = P.Uf[3 * (size_t)c + 2] - v.z;
+    mag = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
+    al = P.gamma[c];
+  }
+  // the closure is evaluated for every particle (unlocated ones with Ur = 0, alpha = 0), as Jd_ = drag_->Jd(magUri_) does
+  jd = jd_closure(P.model, mag, al, d, P.nub, P.rhob);
+  if (c >= 0) {
+    const double Vol = 3.14159265358979323846 * d * d * d / 6.0;
+    if (P.DDtU) { a0 = P.DDtU[3 * (size_t)c]; a1 = P.DDtU[3 * (size_t)c + 1]; a2 = P.DDtU[3 * (size_t)c + 2]; }
+    if (P.flags & SEDI_FORCE_DRAG) { F0 += jd * (1.0 - al) * Vol * u0; F1 += jd * (1.0 - al) * Vol * u1; F2 += jd * (1.0 - al) * Vol * u2; }
+    if (P.flags & SEDI_FORCE_PGRAD) { F0 += -P.gradp[3 * (size_t)c] * Vol; F1 += -P.gradp[3 * (size_t)c + 1] * Vol; F2 += -P.gradp[3 * (size_t)c + 2] * Vol; }
+    if (P.flags & SEDI_FORCE_BUOY) { F0 += -P.g[0] * P.rhob * Vol; F1 += -P.g[1] * P.rhob * Vol; F2 += -P.g[2] * P.rhob * Vol; }
+    if (P.flags & SEDI_FORCE_ADDEDMASS) {
+      double c0 = a0 - (v.x - P.uold[0][i]) / P.deltaT, c1 = a1 - (v.y - P.uold[1][i]) / P.deltaT, c2 = a2 - (v.z - P.uold[2][i]) / P.deltaT;
+      const double m = sqrt(c0 * c0 + c1 * c1 + c2 * c2);
+      if (m > 10) { c0 = c0 / (m + kROOTVSMALL) * 10; c1 = c1 / (m + kROOTVSMALL) * 10; c2 = c2 / (m + kROOTVSMALL) * 10; }
+      F0 += 0.5 * P.rhob * Vol * c0; F1 += 0.5 * P.rhob * Vol * c1; F2 += 0.5 * P.rhob * Vol * c2;
+    }
+    if (P.flags & SEDI_FORCE_LIFT) {
+      const double w0 = P.curlU[3 * (size_t)c], w1 = P.curlU[3 * (size_t)c + 1], w2 = P.curlU[3 * (size_t)c + 2];
+      const double magw = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+      const double coef = 1.6 * P.rhob * sqrt(P.nub) * (d * d);
+      const double s = sqrt(magw + kROOTVSMALL);
+      F0 += coef * (u1 * w2 - u2 * w1) / s; F1 += coef * (u2 * w0 - u0 * w2) / s; F2 += coef * (u0 * w1 - u1 * w0) / s;
+    }
+  }
+  P.fdrag[0][i] = F0; P.fdrag[1][i] = F1; P.fdrag[2][i] = F2;
+  P.dudt[0][i] = a0; P.dudt[1][i] = a1; P.dudt[2][i] = a2;
+  if (P.Uri) { P.Uri[3 * (size_t)i] = u0; P.Uri[3 * (size_t)i + 1] = u1; P.Uri[3 * (size_t)i + 2] = u2; }
+  if (P.magUri) P.magUri[i] = mag;
+  if (P.alphap) P.alphap[i] = al;
+  if (P.Jd) P.Jd[i] = jd;
+}
+
+// remember U for the next coupling step's added-mass term (softParticleCloud.C:571-572: UOld = U; U = Vnew)
+__global__ void k_save_uold(const D4 *velm, int n, double *u0, double *u1, double *u2) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const D4 v = velm[i];
+  u0[i] = v.x; u1[i] = v.y; u2[i] = v.z;
+}
+
+// Segmented warp reduction keyed by cell id: runs of equal adjacent keys are summed with shuffles, one FP64 atomic
+// per run head.  Particles are stored in DEM-bin order, so neighbouring lanes usually share a fluid cell.
+__device__ __forceinline__ void warp_cell_add4(int key, double a, double b, double c, double d, double *dsta, double *dstv) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int k2 = __shfl_down_sync(full, key, o);
+    const double a2 = __shfl_down_sync(full, a, o), b2 = __shfl_down_sync(full, b, o), c2 = __shfl_down_sync(full, c, o), d2 = __shfl_down_sync(full, d, o);
+    if (lane + o < 32 && k2 == key) { a += a2; b += b2; c += c2; d += d2; }
+  }
+  const int kprev = __shfl_up_sync(full, key, 1);
+  if (key >= 0 && (lane == 0 || kprev != key)) {
+    if (dsta) atomicAdd(&dsta[key], a);
+    atomicAdd(&dstv[3 * (size_t)key], b); atomicAdd(&dstv[3 * (size_t)key + 1], c); atomicAdd(&dstv[3 * (size_t)key + 2], d);
+  }
+}
+
+// scatter 1: gamma += Vp, Ue += Vp Up   (enhancedCloud.C:918-930)
+__global__ void __launch_bounds__(256) k_scatter_alpha_u(const D4 *posr, const D4 *velm, const int *cell, int n, double *gamma, double *Ue) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int key = -1; double vol = 0.0, m0 = 0.0, m1 = 0.0, m2 = 0.0;
+  if (i < n) {
+    key = cell[i];
+    if (key >= 0) {
+      const double d = posr[i].w * 2.0;
+      vol = 3.14159265358979323846 * d * d * d / 6.0;
+      const D4 v = velm[i];
+      m0 = vol * v.x; m1 = vol * v.y; m2 = vol * v.z;
+    }
+  }
+  warp_cell_add4(key, vol, m0, m1, m2, gamma, Ue);
+}
+// gamma /= V ; Ue /= V ; Ue /= gamma where gamma > ROOTVSMALL   (:932-962, smoothing flags off)
+__global__ void k_finalize_alpha_u(int C, const double *cellV, double *gamma, double *Ue) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double V = cellV[c];
+  const double g = gamma[c] / V;
+  gamma[c] = g;
+  double u0 = Ue[3 * (size_t)c] / V, u1 = Ue[3 * (size_t)c + 1] / V, u2 = Ue[3 * (size_t)c + 2] / V;
+  if (g > kROOTVSMALL) { u0 /= g; u1 /= g; u2 /= g; }
+  Ue[3 * (size_t)c] = u0; Ue[3 * (size_t)c + 1] = u1; Ue[3 * (size_t)c + 2] = u2;
+}
+
+// scatter 2: Asrc[c] += Vp Jd / Vc (Up - Uf[c])   (enhancedCloud.C:356-386); Omega stays 0 (:391)
+__global__ void __launch_bounds__(256) k_scatter_asrc(const D4 *posr, const D4 *velm, const int *cell, int n, const double *Uf,
+                                                      const double *gamma, const double *cellV, int model, double nub, double rhob,
+                                                      double *Asrc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int key = -1; double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  if (i < n) {
+    key = cell[i];
+    if (key >= 0) {
+      const D4 v = velm[i];
+      const double d = posr[i].w * 2.0;
+      const double f0 = Uf[3 * (size_t)key], f1 = Uf[3 * (size_t)key + 1], f2 = Uf[3 * (size_t)key + 2];
+      const double u0 = f0 - v.x, u1 = f1 - v.y, u2 = f2 - v.z;
+      const double mag = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
+      const double jd = jd_closure(model, mag, gamma[key], d, nub, rhob);
+      const double Vol = 3.14159265358979323846 * d * d * d / 6.0;
+      const double omg = Vol * jd / cellV[key];
+      s0 = omg * (v.x - f0); s1 = omg * (v.y - f1); s2 = omg * (v.z - f2);
+    }
+  }
+  warp_cell_add4(key, 0.0, s0, s1, s2, (double *)0, Asrc);
+}
+// Asrc *= (1-gamma) ; [smooth] ; Asrc /= (1-gamma)   (:407-416)
+__global__ void k_finalize_asrc(int C, const double *gamma, double *Asrc) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double w = 1 - gamma[c];
+  for (int k = 0; k < 3; k++) { double a = Asrc[3 * (size_t)c + k] * w; a /= w; Asrc[3 * (size_t)c + k] = a; }
+}
+
+}  // namespace sedi

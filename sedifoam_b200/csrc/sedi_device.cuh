@@ -1,0 +1,101 @@
+// sedi_device.cuh -- device-side data layout and kernel parameter blocks of the B200 particle engine.
+//
+// HBM layout (all FP64, see DESIGN.md "Data layout"):
+//   posr[i] = {x, y, z, radius}            32 B, one 256-bit sector  -> one LDG.E.ENL2.256 per gathered partner
+//   velm[i] = {vx, vy, vz, rmass}          32 B
+//   omgt[i] = {wx, wy, wz, bits(tag|mask|type|flags)}  32 B
+// The three quads are double-buffered (A/B): the fused step kernel reads A (own row + gathered partners) and
+// writes B, so the whole DEM sub-step is ONE launch with no race between a particle's update and its
+// partners' reads.  Streaming-only per-particle data (fluid force, vOld, xhold, f, torque, wall history) are
+// SoA planes.  Neighbour list and contact history are ELL, slot-major: entry (i, s) at [s * npad + i], so a
+// warp reading slot s of 32 consecutive particles touches contiguous memory.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sedi {
+
+struct __align__(32) D4 { double x, y, z, w; };
+
+// omgt.w bit layout
+__host__ __device__ inline unsigned long long pack_bits(int tag, int mask, int type, int flags) {
+  return ((unsigned long long)(unsigned)tag) | ((unsigned long long)(mask & 0xFFFF) << 32) |
+         ((unsigned long long)(type & 0xFF) << 48) | ((unsigned long long)(flags & 0xFF) << 56);
+}
+__host__ __device__ inline int bits_tag(unsigned long long b) { return (int)(unsigned)(b & 0xFFFFFFFFull); }
+__host__ __device__ inline int bits_mask(unsigned long long b) { return (int)((b >> 32) & 0xFFFF); }
+__host__ __device__ inline int bits_type(unsigned long long b) { return (int)((b >> 48) & 0xFF); }
+__host__ __device__ inline int bits_flags(unsigned long long b) { return (int)((b >> 56) & 0xFF); }
+enum { PFLAG_GHOST = 1 };
+
+// neighbour entry: [24:0] partner index, [29:25] periodic image code (0..26, 13 = none), [30] in the granular
+// list (rsq <= (ri+rj+skin)^2), [31] in the type-cutoff list (rsq <= cutneighsq[ti][tj]) used by fix cohesive
+// and pair lubricate/poly.
+static const unsigned NB_IDX_MASK = 0x01FFFFFFu;
+static const int NB_IMG_SHIFT = 25;
+static const unsigned NB_FLAG_GRAN = 1u << 30;
+static const unsigned NB_FLAG_TYPE = 1u << 31;
+static const int NB_IMG_NONE = 13;
+static const int MAX_SLOTS = 64;  // touch mask is one 64-bit word per particle
+static const int MAX_FIXES = 12;
+static const int MAX_WALLS = 6;
+static const int MAX_TYPES = 8;
+
+struct FixDev {
+  int kind, groupbit;
+  int i0, i1, i2, i3;        // wall: wallstyle, wiggle, wshear, axis ; cohesive: opt
+  long long time_origin;
+  int wall_index, pad;
+  double d[10];
+  // gravity: d0..2 = g * nhat ; fdrag: d0 = carrier_rho ; cohesive: d0 ah, d1 lam, d2 smin, d3 smax
+  // wall: d0 kn, d1 kt, d2 gamman, d3 gammat, d4 xmu, d5 lo, d6 hi, d7 cylradius, d8 beta, and
+  //       wiggle: d[9] = amplitude (period in aux), shear: d[9] = vshear
+  double aux;
+};
+
+struct StepParams {
+  int n;        // rows in the particle arrays (owned + ghost)
+  int npad;     // ELL leading dimension
+  int nfix;
+  int pair;     // PairKind
+  int mode;     // StepMode
+  int lub_enabled, lub_flaglog, lub_flagfld, lub_flagHI;
+  int has_cohesive;
+  int nve_groupbit;  // 0 = no integrator
+  int freeze_groupbit;
+  int periodic_any;
+  long long ntimestep;
+  const D4 *posr_in, *velm_in, *omgt_in;
+  D4 *posr_out, *velm_out, *omgt_out;
+  const int *nn;
+  const unsigned *nbr;
+  D4 *shear;                  // [slot * npad + i], .w unused
+  unsigned long long *tmask;  // touching-slot mask per particle
+  double *f[3], *tq[3];       // stored force/torque (written by SETUP/LAST, read by the initial-integrate kernel)
+  double *fdrag[3], *dudt[3], *vold[3];
+  double *xhold[3];
+  double *wshear[MAX_WALLS][3];
+  unsigned *wmask;            // per-particle wall-touch bits
+  int *ctrl;                  // [0] rebuild-needed flag, [1] steps completed, [2] error flags
+  unsigned long long *counters;  // [0] directed pair visits, [1] directed touching pairs
+  double dtv, dtf, dt_live, trigger_sq;
+  double kn, kt, gamman, gammat, xmu, beta;
+  double prd[3];
+  double lub_mu, lub_cutsq, lub_cut_inner, lub_R0, lub_RT0;
+  FixDev fix[MAX_FIXES];
+};
+
+enum StepMode {
+  MODE_SETUP = 0,  // forces only, history frozen (update->setupflag), store f/torque
+  MODE_FUSED = 1,  // forces + final_integrate(n) + initial_integrate(n+1), displacement check
+  MODE_LAST = 2    // forces + final_integrate(n), store f/torque (end of a `run`)
+};
+
+struct BinParams {
+  int n;
+  double lo[3], inv[3];  // bin = floor((x - lo) * inv)
+  int nb[3];
+  int periodic[3];
+};
+
+}  // namespace sedi

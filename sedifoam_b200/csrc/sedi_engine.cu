@@ -1,0 +1,1144 @@
+// sedi_engine.cu -- host-side engine of libsedi_b200.so: owns the device-resident particle state, drives the
+// neighbour rebuild / fused DEM sub-step / coupling kernels on one CUDA stream, and exports the C-ABI declared in
+// include/sedi_b200.h (the reference's interfaceToLammps/library.h boundary + the device-resident sedi_* API).
+//
+// What replaces what (reference file:line):
+//   Engine::command        lmp_->input->one(line)                       lammpsFoam/softParticleCloud.C:85-115
+//   Engine::run            lammps_step = "run n pre no post no"          interfaceToLammps/library.cpp:372-386
+//                          + EXTERNAL Verlet::run / Neighbor / FixShearHistory
+//   Engine::put_local      lammps_put_local_info                         interfaceToLammps/library.cpp:314-367
+//   Engine::get_local      lammps_get_local_info                         interfaceToLammps/library.cpp:246-308
+//   Engine::fluid_force... enhancedCloud::updateParticleUr/updateDragOnParticles/particleToEulerianField/calcTcFields
+//                                                                        lammpsFoam/enhancedCloud.C:83-441, 911-980
+// There is no CPU fallback: every compute entry point needs a CUDA device and aborts without one
+// (reference error convention: print + abort, library.cpp:380-383).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/sedi_b200.h"
+#include "lmp_script.hpp"
+#include "sedi_device.cuh"
+#include "sedi_neigh.cuh"
+#include "sedi_step.cuh"
+#include "sedi_couple.cuh"
+#include "sedi_comm.cuh"
+
+#define CK(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t e_ = (call);                                                                                  \
+    if (e_ != cudaSuccess) {                                                                                  \
+      fprintf(stderr, "ERROR: CUDA failure %s at %s:%d: %s\n", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      fflush(stderr);                                                                                         \
+      abort();                                                                                                \
+    }                                                                                                         \
+  } while (0)
+
+namespace sedi {
+
+static inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+template <class T>
+struct Buf {  // grow-only device array
+  T *p;
+  size_t cap;
+  Buf() : p(0), cap(0) {}
+  void ensure(size_t n) {
+    if (n <= cap) return;
+    if (p) CK(cudaFree(p));
+    size_t want = n + n / 8 + 64;
+    CK(cudaMalloc((void **)&p, want * sizeof(T)));
+    cap = want;
+  }
+  void ensure_keep(size_t n, size_t used, cudaStream_t s) {
+    if (n <= cap) return;
+    size_t want = n + n / 8 + 64;
+    T *q;
+    CK(cudaMalloc((void **)&q, want * sizeof(T)));
+    if (p && used) CK(cudaMemcpyAsync(q, p, used * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    if (p) { CK(cudaStreamSynchronize(s)); CK(cudaFree(p)); }
+    p = q; cap = want;
+  }
+  void release() { if (p) cudaFree(p); p = 0; cap = 0; }
+};
+
+template <class T>
+struct Pinned {  // grow-only pinned host staging
+  T *p;
+  size_t cap;
+  Pinned() : p(0), cap(0) {}
+  void ensure(size_t n) {
+    if (n <= cap) return;
+    if (p) CK(cudaFreeHost(p));
+    size_t want = n + n / 8 + 64;
+    CK(cudaMallocHost((void **)&p, want * sizeof(T)));
+    cap = want;
+  }
+  void release() { if (p) cudaFreeHost(p); p = 0; cap = 0; }
+};
+
+struct Plane2 {  // a per-particle plane with a permutation partner
+  Buf<double> b[2];
+  int cur;
+  Plane2() : cur(0) {}
+  double *get() { return b[cur].p; }
+  double *alt() { return b[cur ^ 1].p; }
+};
+
+struct Ell {  // directed neighbour list + contact history, slot-major
+  Buf<unsigned> nbr;
+  Buf<int> nn;
+  Buf<unsigned long long> tmask;
+  Buf<D4> shear;
+  int npad, cap;
+  bool valid;
+  Ell() : npad(0), cap(0), valid(false) {}
+};
+
+// small pack / unpack kernels of the C-ABI boundary -------------------------------------------------------
+__global__ void k_pack_local(const D4 *posr, const D4 *velm, const D4 *omgt, const int *foam, int n, double *x, double *v, int *tag,
+                             int *foamid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const D4 p = posr[i], u = velm[i];
+  x[3 * (size_t)i] = p.x; x[3 * (size_t)i + 1] = p.y; x[3 * (size_t)i + 2] = p.z;
+  v[3 * (size_t)i] = u.x; v[3 * (size_t)i + 1] = u.y; v[3 * (size_t)i + 2] = u.z;
+  tag[i] = bits_tag((unsigned long long)__double_as_longlong(omgt[i].w));
+  foamid[i] = foam[i];
+}
+
+// lammps_put_local_info: the reference pairs the k-th smallest incoming tag with the k-th smallest local tag
+// (library.cpp:343-366); for equal tag sets -- the only consistent use -- that is a lookup by tag.
+__global__ void k_put_fdrag(int n, const double *fd, const int *tagin, const int *foamin, const int *tag2idx, int maxtag, double *f0,
+                            double *f1, double *f2, int *foam, int *err) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int t = tagin[k];
+  const int i = (t >= 0 && t <= maxtag) ? tag2idx[t] : -1;
+  if (i < 0) { atomicOr(err, 1); return; }
+  f0[i] = fd[3 * (size_t)k]; f1[i] = fd[3 * (size_t)k + 1]; f2[i] = fd[3 * (size_t)k + 2];
+  if (foamin) foam[i] = foamin[k];
+}
+
+__global__ void k_unpack_state(const D4 *posr, const D4 *velm, const D4 *omgt, int n, double *x, double *v, double *w, double *radius,
+                               double *rmass, int *tag, int *type, int *mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const D4 p = posr[i], u = velm[i], o = omgt[i];
+  x[3 * (size_t)i] = p.x; x[3 * (size_t)i + 1] = p.y; x[3 * (size_t)i + 2] = p.z;
+  v[3 * (size_t)i] = u.x; v[3 * (size_t)i + 1] = u.y; v[3 * (size_t)i + 2] = u.z;
+  w[3 * (size_t)i] = o.x; w[3 * (size_t)i + 1] = o.y; w[3 * (size_t)i + 2] = o.z;
+  radius[i] = p.w; rmass[i] = u.w;
+  const unsigned long long b = (unsigned long long)__double_as_longlong(o.w);
+  tag[i] = bits_tag(b); type[i] = bits_type(b); mask[i] = bits_mask(b);
+}
+
+__global__ void k_interleave3(const double *a, const double *b, const double *c, int n, double *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[3 * (size_t)i] = a[i]; out[3 * (size_t)i + 1] = b[i]; out[3 * (size_t)i + 2] = c[i];
+}
+
+__global__ void k_set_omega(int n, const int *tagin, const double *w, const int *tag2idx, int maxtag, D4 *omgt) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int t = tagin[k];
+  if (t < 0 || t > maxtag) return;
+  const int i = tag2idx[t];
+  if (i < 0) return;
+  D4 o = omgt[i];
+  o.x = w[3 * (size_t)k]; o.y = w[3 * (size_t)k + 1]; o.z = w[3 * (size_t)k + 2];
+  omgt[i] = o;
+}
+
+__global__ void k_fill_double(double *p, size_t n, double v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+static const int NPLANES_BASE = 6;  // f, tq, fdrag, dudt, vold, uold (x3 each)
+
+class Engine {
+ public:
+  Script script;
+  int device;
+  bool dev_ready, loaded, setup_done, params_dirty, cell_valid;
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1, evk0, evk1, evt0, evt1;
+  bool prof_on;
+  double prof_ms;
+  long long prof_steps;
+  // particle rows
+  int n, nlocal, npad, maxtag;
+  Buf<D4> posr[2], velm[2], omgt[2];
+  int cur;
+  Plane2 f[3], tq[3], fdrag[3], dudt[3], vold[3], uold[3], xhold[3];
+  Plane2 wshear[MAX_WALLS][3];
+  Buf<unsigned> wmask[2];
+  Buf<int> foam[2];
+  int icur;  // which of wmask/foam is live
+  Ell ell[2];
+  int ecur;
+  // binning scratch
+  Buf<int> cellid, cellcount, cellstart, cellfill, order, blocksum, tag2idx, rowstart;
+  Buf<int> ctrl;                     // [0] rebuild flag, [1] steps executed, [2] errors, [3] max row length
+  Buf<unsigned long long> counters;  // [0..3] list sizes written by the build, [4..5] optional k_step counters
+  Pinned<int> h_ctrl;
+  Pinned<unsigned long long> h_counters;
+  BinParams bin;
+  double cutneighmax;
+  double cutneighsq[(MAX_TYPES + 1) * (MAX_TYPES + 1)];
+  double dt_init;
+  double lub_R0, lub_RT0, lub_RS0;
+  double beta_pair;
+  StepParams base;
+  // stats
+  long long nbuilds, pair_evals, steps_done, launches, list_gran_dir, list_type_dir, list_gran_img, list_type_img;
+  int chunk;
+  double last_step_ms;
+  bool count_in_kernel;
+  // boundary staging
+  Buf<double> d_stage_a, d_stage_b;
+  Buf<int> d_stage_i, d_stage_j;
+  Pinned<double> h_stage_a, h_stage_b;
+  Pinned<int> h_stage_i, h_stage_j;
+  // coupling
+  MeshBox mesh;
+  bool have_mesh;
+  int ncells;
+  Buf<int> cell;
+  Buf<double> Uf, gamma, gradp, DDtU, curlU, cellV, Ue, Asrc;
+  bool have_DDtU, have_curlU, have_gradp;
+  int drag_model, force_flags;
+  double nub, rhob, gvec[3], deltaT;
+  Buf<double> dg_Uri, dg_mag, dg_alpha, dg_Jd;
+  bool want_diag;
+  Comm comm;
+
+  Engine()
+      : device(0), dev_ready(false), loaded(false), setup_done(false), params_dirty(true), cell_valid(false), stream(0), n(0),
+        nlocal(0), npad(0), maxtag(0), cur(0), icur(0), ecur(0), cutneighmax(0), dt_init(0), lub_R0(0), lub_RT0(0), lub_RS0(0),
+        beta_pair(0), nbuilds(0), pair_evals(0), steps_done(0), launches(0), list_gran_dir(0), list_type_dir(0), list_gran_img(0),
+        list_type_img(0), chunk(16), last_step_ms(0), count_in_kernel(false), have_mesh(false), ncells(0), have_DDtU(false),
+        have_curlU(false), have_gradp(false), drag_model(0), force_flags(SEDI_FORCE_DRAG | SEDI_FORCE_PGRAD), nub(1e-6), rhob(1000.0),
+        deltaT(1.0), want_diag(false), prof_on(false), prof_ms(0), prof_steps(0) {
+    gvec[0] = gvec[1] = gvec[2] = 0.0;
+    memset(&base, 0, sizeof(base));
+    memset(&bin, 0, sizeof(bin));
+    memset(&mesh, 0, sizeof(mesh));
+    const char *e = getenv("SEDI_CHUNK");
+    if (e && atoi(e) > 0) chunk = atoi(e);
+    e = getenv("SEDI_DEVICE");
+    if (e) device = atoi(e);
+    else if ((e = getenv("LOCAL_RANK"))) device = atoi(e);
+  }
+
+  ~Engine() {
+    if (!dev_ready) return;
+    cudaSetDevice(device);
+    cudaStreamSynchronize(stream);
+    // device memory is released with the process; explicit frees keep long-lived hosts clean
+    for (int k = 0; k < 2; k++) { posr[k].release(); velm[k].release(); omgt[k].release(); wmask[k].release(); foam[k].release();
+      ell[k].nbr.release(); ell[k].nn.release(); ell[k].tmask.release(); ell[k].shear.release(); }
+    Plane2 *groups[] = {f, tq, fdrag, dudt, vold, uold, xhold};
+    for (size_t g = 0; g < sizeof(groups) / sizeof(groups[0]); g++) for (int d = 0; d < 3; d++) { groups[g][d].b[0].release(); groups[g][d].b[1].release(); }
+    for (int w = 0; w < MAX_WALLS; w++) for (int d = 0; d < 3; d++) { wshear[w][d].b[0].release(); wshear[w][d].b[1].release(); }
+    cellid.release(); cellcount.release(); cellstart.release(); cellfill.release(); order.release(); blocksum.release();
+    tag2idx.release(); rowstart.release(); ctrl.release(); counters.release(); h_ctrl.release(); h_counters.release();
+    d_stage_a.release(); d_stage_b.release(); d_stage_i.release(); d_stage_j.release();
+    h_stage_a.release(); h_stage_b.release(); h_stage_i.release(); h_stage_j.release();
+    cell.release(); Uf.release(); gamma.release(); gradp.release(); DDtU.release(); curlU.release(); cellV.release(); Ue.release(); Asrc.release();
+    dg_Uri.release(); dg_mag.release(); dg_alpha.release(); dg_Jd.release();
+    comm.destroy();
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evk0); cudaEventDestroy(evk1);
+    cudaEventDestroy(evt0); cudaEventDestroy(evt1);
+    cudaStreamDestroy(stream);
+  }
+
+  SimConfig &cfg() { return script.cfg; }
+
+  // ---- device bring-up: no CPU fallback -------------------------------------------------------------------
+  void need_device() {
+    if (dev_ready) { CK(cudaSetDevice(device)); return; }
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt <= 0)
+      fatal("libsedi_b200 needs a CUDA device (sm_100a); none is visible and there is no CPU fallback.",
+            e != cudaSuccess ? cudaGetErrorString(e) : "");
+    if (device >= cnt) device = device % cnt;
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventCreate(&evk0)); CK(cudaEventCreate(&evk1));
+    CK(cudaEventCreate(&evt0)); CK(cudaEventCreate(&evt1));
+    ctrl.ensure(8); counters.ensure(8); h_ctrl.ensure(8); h_counters.ensure(8);
+    CK(cudaMemsetAsync(ctrl.p, 0, 8 * sizeof(int), stream));
+    CK(cudaMemsetAsync(counters.p, 0, 8 * sizeof(unsigned long long), stream));
+    dev_ready = true;
+  }
+
+  // ---- script ------------------------------------------------------------------------------------------------
+  void command(const char *line) {
+    ScriptAction a = script.one(line);
+    params_dirty = true;
+    if (a.kind == ScriptAction::READ_DATA) loaded = false;
+    if (a.kind == ScriptAction::RUN) run(a.nsteps);
+  }
+
+  void file(const char *path) {
+    FILE *fp = fopen(path, "r");
+    if (!fp) fatal("Cannot open input script", path);
+    char buf[2048];
+    while (fgets(buf, sizeof(buf), fp)) command(buf);
+    fclose(fp);
+  }
+
+  // ---- upload of the script's atoms (EXTERNAL read_data / AtomVecSphere::data_atom) -----------------------------
+  void alloc_rows(int rows) {
+    npad = ((rows + 127) / 128) * 128;
+    if (npad < 128) npad = 128;
+    for (int k = 0; k < 2; k++) { posr[k].ensure(npad); velm[k].ensure(npad); omgt[k].ensure(npad); wmask[k].ensure(npad); foam[k].ensure(npad); }
+    Plane2 *groups[] = {f, tq, fdrag, dudt, vold, uold, xhold};
+    for (size_t g = 0; g < sizeof(groups) / sizeof(groups[0]); g++)
+      for (int d = 0; d < 3; d++) { groups[g][d].b[0].ensure(npad); groups[g][d].b[1].ensure(npad); }
+    for (int w = 0; w < cfg().nwalls && w < MAX_WALLS; w++)
+      for (int d = 0; d < 3; d++) { wshear[w][d].b[0].ensure(npad); wshear[w][d].b[1].ensure(npad); }
+    cellid.ensure(npad); order.ensure(npad); cell.ensure(npad); rowstart.ensure(npad + 1);
+  }
+
+  void zero_plane(Plane2 &p) {
+    CK(cudaMemsetAsync(p.b[0].p, 0, p.b[0].cap * sizeof(double), stream));
+    CK(cudaMemsetAsync(p.b[1].p, 0, p.b[1].cap * sizeof(double), stream));
+  }
+
+  void load_atoms() {
+    need_device();
+    const AtomData &a = script.atoms;
+    if (cfg().nwalls > MAX_WALLS) fatal("Too many wall fixes");
+    if (cfg().ntypes > MAX_TYPES) fatal("Too many atom types for the device cut-off table");
+    if ((int)cfg().fixes.size() > MAX_FIXES) fatal("Too many fixes");
+    nlocal = (int)a.size();
+    n = nlocal;
+    if (n > (int)NB_IDX_MASK) fatal("Too many particles per GPU for the 25-bit neighbour index");
+    alloc_rows(n);
+    std::vector<D4> hp(n), hv(n), hw(n);
+    maxtag = 0;
+    for (int i = 0; i < n; i++) {
+      hp[i].x = a.x[3 * i]; hp[i].y = a.x[3 * i + 1]; hp[i].z = a.x[3 * i + 2]; hp[i].w = a.radius[i];
+      hv[i].x = a.v[3 * i]; hv[i].y = a.v[3 * i + 1]; hv[i].z = a.v[3 * i + 2]; hv[i].w = a.rmass[i];
+      hw[i].x = a.omega[3 * i]; hw[i].y = a.omega[3 * i + 1]; hw[i].z = a.omega[3 * i + 2];
+      if (a.tag[i] < 0) fatal("Negative atom tag");
+      if (script.mask[i] > 0xFFFF) fatal("Too many groups for the 16-bit device mask");
+      const unsigned long long b = pack_bits(a.tag[i], script.mask[i], a.type[i], 0);
+      long long sb = (long long)b;
+      memcpy(&hw[i].w, &sb, 8);
+      maxtag = std::max(maxtag, a.tag[i]);
+    }
+    cur = 0; icur = 0; ecur = 0;
+    ell[0].valid = ell[1].valid = false;
+    if (n) {
+      CK(cudaMemcpyAsync(posr[0].p, hp.data(), n * sizeof(D4), cudaMemcpyHostToDevice, stream));
+      CK(cudaMemcpyAsync(velm[0].p, hv.data(), n * sizeof(D4), cudaMemcpyHostToDevice, stream));
+      CK(cudaMemcpyAsync(omgt[0].p, hw.data(), n * sizeof(D4), cudaMemcpyHostToDevice, stream));
+    }
+    Plane2 *groups[] = {f, tq, fdrag, dudt, vold, uold, xhold};
+    for (size_t g = 0; g < sizeof(groups) / sizeof(groups[0]); g++) for (int d = 0; d < 3; d++) { groups[g][d].cur = 0; zero_plane(groups[g][d]); }
+    for (int w = 0; w < cfg().nwalls; w++) for (int d = 0; d < 3; d++) { wshear[w][d].cur = 0; zero_plane(wshear[w][d]); }
+    for (int k = 0; k < 2; k++) {
+      CK(cudaMemsetAsync(wmask[k].p, 0, wmask[k].cap * sizeof(unsigned), stream));
+      CK(cudaMemsetAsync(foam[k].p, 0, foam[k].cap * sizeof(int), stream));
+    }
+    tag2idx.ensure((size_t)maxtag + 2);
+    CK(cudaMemsetAsync(tag2idx.p, 0xFF, tag2idx.cap * sizeof(int), stream));
+    CK(cudaStreamSynchronize(stream));  // host vectors go out of scope
+    loaded = true; setup_done = false; cell_valid = false;
+  }
+
+  // ---- cut-offs: EXTERNAL PairGranHookeHistory::init_one / PairLubricate::init_one / Neighbor::init -------------
+  // (same rules as the oracle driver, evaluated on the host from the script's atoms)
+  void compute_cutoffs() {
+    const int nt = cfg().ntypes;
+    const AtomData &a = script.atoms;
+    std::vector<double> maxdyn(nt + 1, 0.0), maxfrz(nt + 1, 0.0);
+    for (size_t i = 0; i < a.size(); i++) {
+      const int t = a.type[i];
+      if (t < 1 || t > nt) fatal("Atom type out of range");
+      if (script.mask[i] & cfg().freeze_group_bit) maxfrz[t] = std::max(maxfrz[t], a.radius[i]);
+      else maxdyn[t] = std::max(maxdyn[t], a.radius[i]);
+    }
+    comm.allreduce_max_host(maxdyn.data(), nt + 1);
+    comm.allreduce_max_host(maxfrz.data(), nt + 1);
+    double cutmax = 0.0;
+    memset(cutneighsq, 0, sizeof(cutneighsq));
+    for (int ta = 1; ta <= nt; ta++)
+      for (int tb = 1; tb <= nt; tb++) {
+        double c = 0.0;
+        if (cfg().pair != PAIR_NONE) {
+          c = maxdyn[ta] + maxdyn[tb];
+          c = std::max(c, maxfrz[ta] + maxdyn[tb]);
+          c = std::max(c, maxdyn[ta] + maxfrz[tb]);
+        }
+        if (cfg().lub.enabled) c = std::max(c, cfg().lub.cut_global);
+        const double cn = c + cfg().skin;
+        cutneighsq[ta * (MAX_TYPES + 1) + tb] = cn * cn;
+        cutmax = std::max(cutmax, c);
+      }
+    cutneighmax = cutmax + cfg().skin;
+    if (!(cutneighmax > 0.0)) cutneighmax = std::max(cfg().skin, 1e-30);
+  }
+
+  bool want_type_list() const {
+    for (size_t k = 0; k < script.cfg.fixes.size(); k++) if (script.cfg.fixes[k].kind == FIX_COHESIVE) return true;
+    return script.cfg.lub.enabled != 0;
+  }
+
+  // loop-invariant of the "Fix" damping model, evaluated with the reference's own expression
+  // (pair_gran_hertzFix_history.cpp:195-196, fix_wall_granFix.cpp:602-603)
+  static double fix_beta(double gamman) {
+    const double lg = log(gamman) / log(exp(1.0));
+    return -lg / sqrt(lg * lg + SEDI_MY_PI * SEDI_MY_PI);
+  }
+
+  void setup_bins() {
+    // one bin >= the largest neighbour cut-off, 27-cell stencil; periodic dimensions are tiled exactly
+    long long total = 1;
+    double grow = 1.0;
+    for (int pass = 0; pass < 40; pass++) {
+      total = 1;
+      for (int d = 0; d < 3; d++) {
+        const double lo = comm.sublo(cfg(), d, cutneighmax), hi = comm.subhi(cfg(), d, cutneighmax);
+        const double len = hi - lo;
+        int nb = (int)floor(len / (cutneighmax * grow));
+        if (nb < 1) nb = 1;
+        bin.nb[d] = nb; bin.lo[d] = lo; bin.inv[d] = nb / len;
+        bin.periodic[d] = comm.wraps(cfg(), d) ? 1 : 0;
+        total *= nb;
+      }
+      if (total <= (1ll << 26)) break;
+      grow *= 1.3;
+    }
+    bin.n = n;
+    cellcount.ensure((size_t)total + 1); cellstart.ensure((size_t)total + 1); cellfill.ensure((size_t)total + 1);
+    blocksum.ensure((size_t)cdiv(total + 1, SCAN_ITEMS) + 1);
+  }
+
+  long long ncells_bin() const { return (long long)bin.nb[0] * bin.nb[1] * bin.nb[2]; }
+
+  void build_base_params() {
+    StepParams &P = base;
+    memset(&P, 0, sizeof(P));
+    const SimConfig &c = cfg();
+    P.n = n; P.npad = ell[ecur].npad; P.nfix = (int)c.fixes.size(); P.pair = c.pair;
+    P.lub_enabled = c.lub.enabled; P.lub_flaglog = c.lub.flaglog; P.lub_flagfld = c.lub.flagfld; P.lub_flagHI = c.lub.flagHI;
+    P.freeze_groupbit = c.freeze_group_bit;
+    P.periodic_any = c.periodic[0] | c.periodic[1] | c.periodic[2];
+    P.dtv = dt_init; P.dtf = 0.5 * dt_init; P.dt_live = c.dt;
+    P.trigger_sq = 0.25 * c.skin * c.skin;
+    P.kn = c.gran.kn; P.kt = c.gran.kt; P.gamman = c.gran.gamman; P.gammat = c.gran.gammat; P.xmu = c.gran.xmu;
+    P.beta = (c.pair == PAIR_HERTZFIX_HISTORY) ? fix_beta(c.gran.gamman) : 0.0;
+    for (int d = 0; d < 3; d++) P.prd[d] = c.boxhi[d] - c.boxlo[d];
+    P.lub_mu = c.lub.mu; P.lub_cutsq = c.lub.cut_global * c.lub.cut_global; P.lub_cut_inner = c.lub.cut_inner;
+    P.lub_R0 = lub_R0; P.lub_RT0 = lub_RT0;
+    P.ctrl = ctrl.p;
+    P.counters = count_in_kernel ? counters.p + 4 : 0;
+    for (size_t k = 0; k < c.fixes.size(); k++) {
+      const FixSpec &s = c.fixes[k];
+      FixDev &F = P.fix[k];
+      F.kind = s.kind; F.groupbit = s.groupbit; F.time_origin = s.time_origin; F.wall_index = s.wall_index;
+      switch (s.kind) {
+        case FIX_NVE_SPHERE: P.nve_groupbit |= s.groupbit; break;
+        case FIX_GRAVITY: for (int d = 0; d < 3; d++) F.d[d] = s.g * s.gdir[d]; break;
+        case FIX_FDRAG: F.d[0] = s.carrier_rho; break;
+        case FIX_COHESIVE: F.d[0] = s.ah; F.d[1] = s.lam; F.d[2] = s.smin; F.d[3] = s.smax; F.i0 = s.opt; P.has_cohesive = 1; break;
+        case FIX_WALL_GRAN:
+          F.i0 = s.wallstyle; F.i1 = s.wiggle; F.i2 = s.wshear; F.i3 = s.axis;
+          F.d[0] = s.wall.kn; F.d[1] = s.wall.kt; F.d[2] = s.wall.gamman; F.d[3] = s.wall.gammat; F.d[4] = s.wall.xmu;
+          F.d[5] = s.lo; F.d[6] = s.hi; F.d[7] = s.cylradius;
+          F.d[8] = (c.pair == PAIR_HERTZFIX_HISTORY) ? fix_beta(s.wall.gamman) : 0.0;
+          F.d[9] = s.wshear ? s.vshear : 0.0; F.aux = s.vshear;
+          break;
+        default: break;
+      }
+    }
+    params_dirty = false;
+  }
+
+  // per-launch part of the parameter block
+  void fill_launch(StepParams &P, int mode, int in, long long ntimestep) {
+    P = base;
+    P.mode = mode; P.ntimestep = ntimestep;
+    P.n = n;
+    Ell &L = ell[ecur];
+    P.npad = L.npad; P.nn = L.nn.p; P.nbr = L.nbr.p; P.shear = L.shear.p; P.tmask = L.tmask.p;
+    P.posr_in = posr[in].p; P.velm_in = velm[in].p; P.omgt_in = omgt[in].p;
+    P.posr_out = posr[in ^ 1].p; P.velm_out = velm[in ^ 1].p; P.omgt_out = omgt[in ^ 1].p;
+    for (int d = 0; d < 3; d++) {
+      P.f[d] = f[d].get(); P.tq[d] = tq[d].get(); P.fdrag[d] = fdrag[d].get(); P.dudt[d] = dudt[d].get();
+      P.vold[d] = vold[d].get(); P.xhold[d] = xhold[d].get();
+      for (int w = 0; w < cfg().nwalls; w++) P.wshear[w][d] = wshear[w][d].get();
+    }
+    P.wmask = wmask[icur].p;
+    const SimConfig &c = cfg();
+    for (size_t k = 0; k < c.fixes.size(); k++) {
+      const FixSpec &s = c.fixes[k];
+      if (s.kind != FIX_WALL_GRAN || !s.wiggle) continue;
+      FixDev &F = P.fix[k];  // fix_wall_granFix.cpp:254-262
+      const double omega = 2.0 * SEDI_MY_PI / s.period;
+      const double arg = omega * (ntimestep - s.time_origin) * dt_init;
+      if (s.wallstyle == s.axis) {
+        F.d[5] = s.lo + s.amplitude - s.amplitude * cos(arg);
+        F.d[6] = s.hi + s.amplitude - s.amplitude * cos(arg);
+      }
+      F.d[9] = s.amplitude * omega * sin(arg);
+    }
+  }
+
+  void launch_step(int mode, int in, long long ntimestep, int seq) {
+    StepParams P;
+    fill_launch(P, mode, in, ntimestep);
+    const int blocks = cdiv(n, 128);
+    if (!blocks) return;
+    switch (cfg().pair) {
+      case PAIR_HERTZFIX_HISTORY: k_step<PAIR_HERTZFIX_HISTORY><<<blocks, 128, 0, stream>>>(P, seq); break;
+      case PAIR_HOOKE_HISTORY: k_step<PAIR_HOOKE_HISTORY><<<blocks, 128, 0, stream>>>(P, seq); break;
+      case PAIR_HOOKE: k_step<PAIR_HOOKE><<<blocks, 128, 0, stream>>>(P, seq); break;
+      default: k_step<PAIR_NONE><<<blocks, 128, 0, stream>>>(P, seq); break;
+    }
+    launches++;
+  }
+
+  void launch_initial(int in, int seq) {
+    StepParams P;
+    fill_launch(P, MODE_FUSED, in, cfg().ntimestep);
+    const int blocks = cdiv(n, 256);
+    if (!blocks) return;
+    k_initial_integrate<<<blocks, 256, 0, stream>>>(P, seq);
+    launches++;
+  }
+
+  // ---- neighbour rebuild (EXTERNAL Verlet: pre_exchange history save, pbc, exchange, borders, Neighbor::build) ---
+  void rebuild() {
+    need_device();
+    if (comm.nranks > 1) comm.exchange_and_borders(*this);
+    bin.n = n;
+    const long long nc = ncells_bin();
+    const int T = 256;
+    CK(cudaMemsetAsync(cellcount.p, 0, (size_t)(nc + 1) * sizeof(int), stream));
+    CK(cudaMemsetAsync(cellfill.p, 0, (size_t)(nc + 1) * sizeof(int), stream));
+    const SimConfig &c = cfg();
+    if (n) {
+      k_wrap_bin<<<cdiv(n, T), T, 0, stream>>>(posr[cur].p, omgt[cur].p, n, bin, c.boxhi[0], c.boxhi[1], c.boxhi[2], c.boxhi[0] - c.boxlo[0],
+                                               c.boxhi[1] - c.boxlo[1], c.boxhi[2] - c.boxlo[2], cellid.p, cellcount.p,
+                                               c.periodic[0], c.periodic[1], c.periodic[2], c.boxlo[0], c.boxlo[1], c.boxlo[2]);
+    }
+    const int nscan = (int)(nc + 1);
+    const int nblk = cdiv(nscan, SCAN_ITEMS);
+    k_scan_local<<<nblk, 1024, 0, stream>>>(cellcount.p, cellstart.p, nscan, blocksum.p);
+    k_scan_sums<<<1, 1024, 0, stream>>>(blocksum.p, nblk);
+    k_scan_add<<<cdiv(nscan, T), T, 0, stream>>>(cellstart.p, nscan, blocksum.p, 0);
+    launches += 4;
+    if (n) {
+      k_bin_scatter<<<cdiv(n, T), T, 0, stream>>>(cellid.p, n, cellstart.p, cellfill.p, order.p);
+      k_cell_sort<<<cdiv(nc, T), T, 0, stream>>>(cellstart.p, (int)nc, n, order.p, omgt[cur].p);
+      // physical re-ordering into cell order: quads cur -> cur^1, planes get() -> alt()
+      k_permute_quads<<<cdiv(n, T), T, 0, stream>>>(order.p, n, posr[cur].p, velm[cur].p, omgt[cur].p, posr[cur ^ 1].p, velm[cur ^ 1].p,
+                                                    omgt[cur ^ 1].p, xhold[0].get(), xhold[1].get(), xhold[2].get(), tag2idx.p, maxtag,
+                                                    wmask[icur].p, wmask[icur ^ 1].p, foam[icur].p, foam[icur ^ 1].p);
+      PlaneList L;
+      L.nplanes = 0;
+      Plane2 *groups[] = {f, tq, fdrag, dudt, vold, uold};
+      for (int g = 0; g < NPLANES_BASE; g++) for (int d = 0; d < 3; d++) { L.src[L.nplanes] = groups[g][d].get(); L.dst[L.nplanes] = groups[g][d].alt(); L.nplanes++; }
+      for (int w = 0; w < c.nwalls; w++) for (int d = 0; d < 3; d++) { L.src[L.nplanes] = wshear[w][d].get(); L.dst[L.nplanes] = wshear[w][d].alt(); L.nplanes++; }
+      k_permute_planes<<<cdiv(n, T), T, 0, stream>>>(order.p, n, L);
+      for (int g = 0; g < NPLANES_BASE; g++) for (int d = 0; d < 3; d++) groups[g][d].cur ^= 1;
+      for (int w = 0; w < c.nwalls; w++) for (int d = 0; d < 3; d++) wshear[w][d].cur ^= 1;
+      launches += 4;
+    }
+    const int oldq = cur;
+    cur ^= 1; icur ^= 1;
+    // directed ELL list + history re-attachment
+    Ell &Lo = ell[ecur], &Ln = ell[ecur ^ 1];
+    BuildParams B;
+    memset(&B, 0, sizeof(B));
+    B.n = n; B.want_gran = (c.pair != PAIR_NONE); B.want_type = want_type_list() ? 1 : 0; B.ntypes = c.ntypes;
+    B.posr = posr[cur].p; B.omgt = omgt[cur].p; B.cellstart = cellstart.p;
+    for (int d = 0; d < 3; d++) { B.nb[d] = bin.nb[d]; B.periodic[d] = bin.periodic[d]; B.lo[d] = bin.lo[d]; B.inv[d] = bin.inv[d]; B.prd[d] = c.boxhi[d] - c.boxlo[d]; }
+    B.skin = c.skin;
+    memcpy(B.cutneighsq, cutneighsq, sizeof(cutneighsq));
+    B.have_old = Lo.valid ? 1 : 0; B.npad_old = Lo.npad; B.oldidx = order.p;
+    B.nbr_old = Lo.nbr.p; B.nn_old = Lo.nn.p; B.tmask_old = Lo.tmask.p; B.shear_old = Lo.shear.p; B.omgt_old = omgt[oldq].p;
+    B.maxcount = ctrl.p + 3; B.npairs = counters.p;
+    if (Ln.cap < 8) Ln.cap = std::max(Lo.cap, 0);
+    for (int attempt = 0; attempt < 3; attempt++) {
+      Ln.npad = npad;
+      Ln.nn.ensure(npad); Ln.tmask.ensure(npad);
+      if (Ln.cap > 0) { Ln.nbr.ensure((size_t)Ln.cap * npad); Ln.shear.ensure((size_t)Ln.cap * npad); }
+      B.npad = Ln.npad; B.cap = Ln.cap; B.nbr = Ln.nbr.p; B.nn = Ln.nn.p; B.tmask = Ln.tmask.p; B.shear = Ln.shear.p;
+      CK(cudaMemsetAsync(ctrl.p + 3, 0, sizeof(int), stream));
+      CK(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned long long), stream));
+      if (n) k_build_list<<<cdiv(n, 128), 128, 0, stream>>>(B);
+      launches++;
+      CK(cudaMemcpyAsync(h_ctrl.p, ctrl.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+      CK(cudaMemcpyAsync(h_counters.p, counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      CK(cudaGetLastError());
+      const int maxrow = h_ctrl.p[3];
+      if (maxrow <= Ln.cap) break;
+      if (maxrow > MAX_SLOTS) fatal("Neighbour row longer than 64 entries: reduce the skin / cut-off (contact-history mask is 64 bits)");
+      Ln.cap = std::min(MAX_SLOTS, ((maxrow + 2 + 3) / 4) * 4);
+      if (attempt == 2) fatal("Neighbour list capacity did not converge");
+    }
+    list_gran_dir = (long long)h_counters.p[0]; list_type_dir = (long long)h_counters.p[1];
+    list_gran_img = (long long)h_counters.p[2]; list_type_img = (long long)h_counters.p[3];
+    Ln.valid = true; Lo.valid = false;
+    ecur ^= 1;
+    nbuilds++;
+    cell_valid = false;
+  }
+
+  // undirected granular list size as LAMMPS counts it (owned-ghost image pairs are stored by both owners)
+  long long list_pairs_undirected() const { return (list_gran_dir - list_gran_img) / 2 + list_gran_img; }
+
+  // ---- Verlet::setup (first `run` of the session, even with `pre no`; softParticleCloud.C:189 lammps_step(0)) -----
+  void setup() {
+    if (!loaded) load_atoms();
+    need_device();
+    dt_init = cfg().dt;
+    compute_cutoffs();
+    if (cfg().lub.enabled) {  // PairLubricatePoly::init_style, pair_lubricate_poly.cpp:533-559 (vol_T = box volume)
+      const AtomData &a = script.atoms;
+      const double MY_PI = SEDI_MY_PI;
+      const double vol_T = (cfg().boxhi[0] - cfg().boxlo[0]) * (cfg().boxhi[1] - cfg().boxlo[1]) * (cfg().boxhi[2] - cfg().boxlo[2]);
+      double volP = 0.0;
+      for (size_t i = 0; i < a.size(); i++) volP += (4.0 / 3.0) * MY_PI * pow(a.radius[i], 3.0);
+      comm.allreduce_sum_host(&volP, 1);
+      double vol_f = volP / vol_T;
+      if (!cfg().lub.flagVF) vol_f = 0;
+      const double mu = cfg().lub.mu;
+      if (cfg().lub.flaglog == 0) {
+        lub_R0 = 6 * MY_PI * mu * (1.0 + 2.16 * vol_f);
+        lub_RT0 = 8 * MY_PI * mu;
+        lub_RS0 = 20.0 / 3.0 * MY_PI * mu * (1.0 + 3.33 * vol_f + 2.80 * vol_f * vol_f);
+      } else {
+        lub_R0 = 6 * MY_PI * mu * (1.0 + 2.725 * vol_f - 6.583 * vol_f * vol_f);
+        lub_RT0 = 8 * MY_PI * mu * (1.0 + 0.749 * vol_f - 2.469 * vol_f * vol_f);
+        lub_RS0 = 20.0 / 3.0 * MY_PI * mu * (1.0 + 3.64 * vol_f - 6.95 * vol_f * vol_f);
+      }
+    }
+    setup_bins();
+    rebuild();
+    build_base_params();
+    launch_step(MODE_SETUP, cur, cfg().ntimestep, 0);
+    pair_evals += list_pairs_undirected();
+    setup_done = true;
+  }
+
+  // ---- Verlet::run: n DEM sub-steps, chunked so that the host only synchronises every `chunk` launches ------------
+  void run(long long nsteps) {
+    if (!setup_done) setup();
+    need_device();
+    if (params_dirty) build_base_params();
+    if (nsteps <= 0) return;
+    CK(cudaEventRecord(ev0, stream));
+    long long remaining = nsteps;
+    bool pending_initial = true;  // the next thing a step needs is its initial_integrate
+    while (remaining > 0) {
+      CK(cudaMemsetAsync(ctrl.p, 0, 2 * sizeof(int), stream));
+      const int K = (int)std::min<long long>(remaining, chunk);
+      int seq = 0, in = cur, nk = 0;
+      if (pending_initial) { launch_initial(in, ++seq); in ^= 1; nk++; }
+      if (prof_on) CK(cudaEventRecord(evk0, stream));
+      for (int s = 0; s < K; s++) {
+        const bool last = (remaining - s == 1);
+        launch_step(last ? MODE_LAST : MODE_FUSED, in, cfg().ntimestep + s + 1, ++seq);
+        in ^= 1;
+      }
+      if (prof_on) CK(cudaEventRecord(evk1, stream));
+      CK(cudaMemcpyAsync(h_ctrl.p, ctrl.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      CK(cudaGetLastError());
+      const int flag = h_ctrl.p[0], done = h_ctrl.p[1];
+      if (prof_on) {  // the K k_step launches are back to back on the stream: their summed duration / executed count
+        float kms = 0.f;
+        CK(cudaEventElapsedTime(&kms, evk0, evk1));
+        prof_ms += kms; prof_steps += done;
+      }
+      if (h_ctrl.p[2]) fatal("Device-side error flag raised during the DEM step");
+      if ((nk + done) & 1) cur ^= 1;
+      pair_evals += (long long)done * list_pairs_undirected();
+      steps_done += done;
+      remaining -= done;
+      cfg().ntimestep += done;
+      pending_initial = false;
+      if (flag != 0) {
+        if (remaining <= 0) fatal("internal: rebuild requested after the last sub-step");
+        rebuild();   // positions of step ntimestep+1 are already integrated; its forces come next
+      } else if (done != K) fatal("internal: sub-step chunk ended early without a rebuild request");
+    }
+    CK(cudaEventRecord(ev1, stream));
+    CK(cudaEventSynchronize(ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    last_step_ms = ms;
+    cell_valid = false;
+  }
+
+  // ---- C-ABI data movement ---------------------------------------------------------------------------------------
+  void put_local(int nin, const double *fd, const int *foamin, const int *tagin) {
+    if (!loaded) load_atoms();
+    need_device();
+    if (nin != nlocal) {  // the reference only warns and then indexes out of range (library.cpp:335-341): fatal here
+      fprintf(stderr, "Incoming drag not consistent with local particle number.\nIncoming drag is: %5d, local particle number is: %5d.\n", nin, nlocal);
+      fatal("lammps_put_local_info: particle count mismatch");
+    }
+    if (!nin) return;
+    if (!setup_done) setup();  // tag2idx is filled by the first build
+    h_stage_a.ensure(3 * (size_t)nin); h_stage_i.ensure(nin); h_stage_j.ensure(nin);
+    d_stage_a.ensure(3 * (size_t)nin); d_stage_i.ensure(nin); d_stage_j.ensure(nin);
+    memcpy(h_stage_a.p, fd, 3 * (size_t)nin * sizeof(double));
+    memcpy(h_stage_i.p, tagin, nin * sizeof(int));
+    if (foamin) memcpy(h_stage_j.p, foamin, nin * sizeof(int));
+    CK(cudaMemcpyAsync(d_stage_a.p, h_stage_a.p, 3 * (size_t)nin * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_stage_i.p, h_stage_i.p, nin * sizeof(int), cudaMemcpyHostToDevice, stream));
+    if (foamin) CK(cudaMemcpyAsync(d_stage_j.p, h_stage_j.p, nin * sizeof(int), cudaMemcpyHostToDevice, stream));
+    k_put_fdrag<<<cdiv(nin, 256), 256, 0, stream>>>(nin, d_stage_a.p, d_stage_i.p, foamin ? d_stage_j.p : 0, tag2idx.p, maxtag,
+                                                    fdrag[0].get(), fdrag[1].get(), fdrag[2].get(), foam[icur].p, ctrl.p + 2);
+    launches++;
+    CK(cudaMemcpyAsync(h_ctrl.p, ctrl.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (h_ctrl.p[2]) fatal("lammps_put_local_info: incoming tag not owned by this rank");
+  }
+
+  void get_local(double *x, double *v, int *foamid, int *lmpid, int *tag) {
+    if (!loaded) load_atoms();
+    need_device();
+    const int m = nlocal;
+    if (!m) return;
+    h_stage_a.ensure(3 * (size_t)m); h_stage_b.ensure(3 * (size_t)m); h_stage_i.ensure(m); h_stage_j.ensure(m);
+    d_stage_a.ensure(3 * (size_t)m); d_stage_b.ensure(3 * (size_t)m); d_stage_i.ensure(m); d_stage_j.ensure(m);
+    k_pack_local<<<cdiv(m, 256), 256, 0, stream>>>(posr[cur].p, velm[cur].p, omgt[cur].p, foam[icur].p, m, d_stage_a.p, d_stage_b.p,
+                                                   d_stage_i.p, d_stage_j.p);
+    launches++;
+    CK(cudaMemcpyAsync(h_stage_a.p, d_stage_a.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(h_stage_b.p, d_stage_b.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(h_stage_i.p, d_stage_i.p, m * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(h_stage_j.p, d_stage_j.p, m * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (x) memcpy(x, h_stage_a.p, 3 * (size_t)m * sizeof(double));
+    if (v) memcpy(v, h_stage_b.p, 3 * (size_t)m * sizeof(double));
+    if (tag) memcpy(tag, h_stage_i.p, m * sizeof(int));
+    if (foamid) memcpy(foamid, h_stage_j.p, m * sizeof(int));
+    if (lmpid) for (int i = 0; i < m; i++) lmpid[i] = comm.rank;
+  }
+
+  // full state in device row order (owned rows first `nlocal` rows are owned; ghosts follow)
+  void get_state(double *x, double *v, double *w, double *fo, double *to, double *radius, double *rmass, int *tag, int *type, int *mask) {
+    if (!loaded) load_atoms();
+    need_device();
+    const int m = nlocal;
+    if (!m) return;
+    Buf<double> dx, dv, dw, dr, dm, df;
+    Buf<int> dt, dy, dk;
+    dx.ensure(3 * (size_t)m); dv.ensure(3 * (size_t)m); dw.ensure(3 * (size_t)m); dr.ensure(m); dm.ensure(m); df.ensure(3 * (size_t)m);
+    dt.ensure(m); dy.ensure(m); dk.ensure(m);
+    k_unpack_state<<<cdiv(m, 256), 256, 0, stream>>>(posr[cur].p, velm[cur].p, omgt[cur].p, m, dx.p, dv.p, dw.p, dr.p, dm.p, dt.p, dy.p, dk.p);
+    if (x) CK(cudaMemcpyAsync(x, dx.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (v) CK(cudaMemcpyAsync(v, dv.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (w) CK(cudaMemcpyAsync(w, dw.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (radius) CK(cudaMemcpyAsync(radius, dr.p, m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (rmass) CK(cudaMemcpyAsync(rmass, dm.p, m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (tag) CK(cudaMemcpyAsync(tag, dt.p, m * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (type) CK(cudaMemcpyAsync(type, dy.p, m * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (mask) CK(cudaMemcpyAsync(mask, dk.p, m * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (fo) {
+      k_interleave3<<<cdiv(m, 256), 256, 0, stream>>>(f[0].get(), f[1].get(), f[2].get(), m, df.p);
+      CK(cudaMemcpyAsync(fo, df.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+    }
+    if (to) {
+      k_interleave3<<<cdiv(m, 256), 256, 0, stream>>>(tq[0].get(), tq[1].get(), tq[2].get(), m, df.p);
+      CK(cudaMemcpyAsync(to, df.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+    }
+    dx.release(); dv.release(); dw.release(); dr.release(); dm.release(); df.release(); dt.release(); dy.release(); dk.release();
+  }
+
+  long long get_pairs(int *ti, int *tj, unsigned *meta, int *touch, double *shear, long long capacity) {
+    if (!setup_done) setup();
+    need_device();
+    Ell &L = ell[ecur];
+    std::vector<int> hn(n), rs(n + 1, 0);
+    if (n) CK(cudaMemcpyAsync(hn.data(), L.nn.p, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    for (int i = 0; i < n; i++) rs[i + 1] = rs[i] + hn[i];
+    const long long total = rs[n];
+    if (capacity < total || !total) return total;
+    Buf<int> dti, dtj, dto;
+    Buf<unsigned> dme;
+    Buf<double> dsh;
+    dti.ensure(total); dtj.ensure(total); dto.ensure(total); dme.ensure(total); dsh.ensure(3 * (size_t)total);
+    CK(cudaMemcpyAsync(rowstart.p, rs.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    k_export_pairs<<<cdiv(n, 128), 128, 0, stream>>>(n, L.npad, L.nn.p, L.nbr.p, omgt[cur].p, rowstart.p, dti.p, dtj.p, dme.p, L.tmask.p,
+                                                     L.shear.p, dto.p, dsh.p);
+    if (ti) CK(cudaMemcpyAsync(ti, dti.p, total * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (tj) CK(cudaMemcpyAsync(tj, dtj.p, total * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (meta) CK(cudaMemcpyAsync(meta, dme.p, total * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+    if (touch) CK(cudaMemcpyAsync(touch, dto.p, total * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (shear) CK(cudaMemcpyAsync(shear, dsh.p, 3 * (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    dti.release(); dtj.release(); dto.release(); dme.release(); dsh.release();
+    return total;
+  }
+
+  void get_wall_shear(int w, double *out) {
+    need_device();
+    if (w < 0 || w >= cfg().nwalls) fatal("sedi_get_wall_shear: no such wall");
+    const int m = nlocal;
+    if (!m) return;
+    Buf<double> d;
+    d.ensure(3 * (size_t)m);
+    // rows whose wall-touch bit is clear hold stale values; the reference zeroes them eagerly (:326-331)
+    k_wall_shear_export<<<cdiv(m, 256), 256, 0, stream>>>(wshear[w][0].get(), wshear[w][1].get(), wshear[w][2].get(), wmask[icur].p, w, m, d.p);
+    CK(cudaMemcpyAsync(out, d.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    d.release();
+  }
+
+  void set_omega(int m, const int *tag, const double *w) {
+    if (!loaded) load_atoms();
+    if (!setup_done) setup();
+    Buf<int> dt; Buf<double> dw;
+    dt.ensure(m); dw.ensure(3 * (size_t)m);
+    CK(cudaMemcpyAsync(dt.p, tag, m * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(dw.p, w, 3 * (size_t)m * sizeof(double), cudaMemcpyHostToDevice, stream));
+    k_set_omega<<<cdiv(m, 256), 256, 0, stream>>>(m, dt.p, dw.p, tag2idx.p, maxtag, omgt[cur].p);
+    CK(cudaStreamSynchronize(stream));
+    dt.release(); dw.release();
+  }
+
+  // ---- coupling (device-resident mirror of enhancedCloud) -----------------------------------------------------------
+  void mesh_box(const double *lo, const double *hi, const int *nc) {
+    need_device();
+    long long C = 1;
+    for (int d = 0; d < 3; d++) { mesh.lo[d] = lo[d]; mesh.hi[d] = hi[d]; mesh.nc[d] = nc[d]; mesh.dx[d] = (hi[d] - lo[d]) / nc[d]; C *= nc[d]; }
+    if (C <= 0 || C > 0x7fffffff) fatal("sedi_mesh_box: bad cell count");
+    ncells = (int)C;
+    Uf.ensure(3 * (size_t)C); gamma.ensure(C); gradp.ensure(3 * (size_t)C); DDtU.ensure(3 * (size_t)C); curlU.ensure(3 * (size_t)C);
+    cellV.ensure(C); Ue.ensure(3 * (size_t)C); Asrc.ensure(3 * (size_t)C);
+    CK(cudaMemsetAsync(Uf.p, 0, 3 * (size_t)C * sizeof(double), stream));
+    CK(cudaMemsetAsync(gamma.p, 0, (size_t)C * sizeof(double), stream));
+    CK(cudaMemsetAsync(gradp.p, 0, 3 * (size_t)C * sizeof(double), stream));
+    const double V = mesh.dx[0] * mesh.dx[1] * mesh.dx[2];
+    k_fill_double<<<cdiv(C, 256), 256, 0, stream>>>(cellV.p, (size_t)C, V);
+    have_mesh = true; have_DDtU = have_curlU = false; have_gradp = true; cell_valid = false;
+  }
+
+  void put_cell_fields(const double *hUf, const double *hgamma, const double *hgradp, const double *hDDtU, const double *hcurlU) {
+    if (!have_mesh) fatal("sedi_put_cell_fields: call sedi_mesh_box first");
+    need_device();
+    const size_t C = ncells;
+    if (hUf) CK(cudaMemcpyAsync(Uf.p, hUf, 3 * C * sizeof(double), cudaMemcpyHostToDevice, stream));
+    if (hgamma) CK(cudaMemcpyAsync(gamma.p, hgamma, C * sizeof(double), cudaMemcpyHostToDevice, stream));
+    if (hgradp) CK(cudaMemcpyAsync(gradp.p, hgradp, 3 * C * sizeof(double), cudaMemcpyHostToDevice, stream));
+    if (hDDtU) { CK(cudaMemcpyAsync(DDtU.p, hDDtU, 3 * C * sizeof(double), cudaMemcpyHostToDevice, stream)); have_DDtU = true; }
+    if (hcurlU) { CK(cudaMemcpyAsync(curlU.p, hcurlU, 3 * C * sizeof(double), cudaMemcpyHostToDevice, stream)); have_curlU = true; }
+    CK(cudaStreamSynchronize(stream));  // caller may reuse / free its arrays (pageable copies are staged by the driver)
+  }
+
+  void locate() {
+    if (!have_mesh) fatal("sedi_locate: call sedi_mesh_box first");
+    if (!loaded) load_atoms();
+    need_device();
+    if (n) k_locate_cells<<<cdiv(n, 256), 256, 0, stream>>>(posr[cur].p, n, mesh, cell.p);
+    launches++;
+    cell_valid = true;
+  }
+
+  void fluid_force() {
+    if (!setup_done) setup();
+    if (!cell_valid) locate();
+    if ((force_flags & SEDI_FORCE_ADDEDMASS) && !have_DDtU) fatal("added-mass force needs DDtU");
+    if ((force_flags & SEDI_FORCE_LIFT) && !have_curlU) fatal("lift force needs curlU");
+    ForceParams P;
+    memset(&P, 0, sizeof(P));
+    P.n = nlocal; P.model = drag_model; P.flags = force_flags;
+    P.posr = posr[cur].p; P.velm = velm[cur].p; P.cell = cell.p;
+    P.Uf = Uf.p; P.gamma = gamma.p; P.gradp = gradp.p; P.DDtU = have_DDtU ? DDtU.p : 0; P.curlU = have_curlU ? curlU.p : 0;
+    for (int d = 0; d < 3; d++) { P.uold[d] = uold[d].get(); P.fdrag[d] = fdrag[d].get(); P.dudt[d] = dudt[d].get(); }
+    if (want_diag) {
+      dg_Uri.ensure(3 * (size_t)npad); dg_mag.ensure(npad); dg_alpha.ensure(npad); dg_Jd.ensure(npad);
+      P.Uri = dg_Uri.p; P.magUri = dg_mag.p; P.alphap = dg_alpha.p; P.Jd = dg_Jd.p;
+    }
+    P.nub = nub; P.rhob = rhob; P.deltaT = deltaT;
+    for (int d = 0; d < 3; d++) P.g[d] = gvec[d];
+    if (nlocal) k_particle_force<<<cdiv(nlocal, 256), 256, 0, stream>>>(P);
+    launches++;
+  }
+
+  void scatter_alpha_u(double *hgamma, double *hUe) {
+    if (!setup_done) setup();
+    if (!cell_valid) locate();
+    const size_t C = ncells;
+    CK(cudaMemsetAsync(gamma.p, 0, C * sizeof(double), stream));
+    CK(cudaMemsetAsync(Ue.p, 0, 3 * C * sizeof(double), stream));
+    if (nlocal) k_scatter_alpha_u<<<cdiv(nlocal, 256), 256, 0, stream>>>(posr[cur].p, velm[cur].p, cell.p, nlocal, gamma.p, Ue.p);
+    if (comm.nranks > 1) { comm.allreduce_sum_dev(gamma.p, C, stream); comm.allreduce_sum_dev(Ue.p, 3 * C, stream); }
+    k_finalize_alpha_u<<<cdiv(C, 256), 256, 0, stream>>>((int)C, cellV.p, gamma.p, Ue.p);
+    launches += 2;
+    if (hgamma) CK(cudaMemcpyAsync(hgamma, gamma.p, C * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (hUe) CK(cudaMemcpyAsync(hUe, Ue.p, 3 * C * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+  }
+
+  void calc_tc(double *hAsrc, double *hOmega) {
+    if (!setup_done) setup();
+    if (!cell_valid) locate();
+    const size_t C = ncells;
+    CK(cudaMemsetAsync(Asrc.p, 0, 3 * C * sizeof(double), stream));
+    if (nlocal)
+      k_scatter_asrc<<<cdiv(nlocal, 256), 256, 0, stream>>>(posr[cur].p, velm[cur].p, cell.p, nlocal, Uf.p, gamma.p, cellV.p, drag_model, nub, rhob, Asrc.p);
+    if (comm.nranks > 1) comm.allreduce_sum_dev(Asrc.p, 3 * C, stream);
+    k_finalize_asrc<<<cdiv(C, 256), 256, 0, stream>>>((int)C, gamma.p, Asrc.p);
+    launches += 2;
+    if (hAsrc) CK(cudaMemcpyAsync(hAsrc, Asrc.p, 3 * C * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (hOmega) memset(hOmega, 0, C * sizeof(double));  // enhancedCloud.C:391
+  }
+
+  void get_coupling_diag(int *hcell, double *Uri, double *mag, double *al, double *Jd, double *F) {
+    need_device();
+    const int m = nlocal;
+    if (!m) return;
+    if (hcell) CK(cudaMemcpyAsync(hcell, cell.p, m * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (want_diag && dg_Uri.p) {
+      if (Uri) CK(cudaMemcpyAsync(Uri, dg_Uri.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      if (mag) CK(cudaMemcpyAsync(mag, dg_mag.p, m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      if (al) CK(cudaMemcpyAsync(al, dg_alpha.p, m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      if (Jd) CK(cudaMemcpyAsync(Jd, dg_Jd.p, m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    }
+    if (F) {
+      Buf<double> d;
+      d.ensure(3 * (size_t)m);
+      k_interleave3<<<cdiv(m, 256), 256, 0, stream>>>(fdrag[0].get(), fdrag[1].get(), fdrag[2].get(), m, d.p);
+      CK(cudaMemcpyAsync(F, d.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      d.release();
+    }
+    CK(cudaStreamSynchronize(stream));
+  }
+
+  // UOld = U before the particles are advanced (softParticleCloud.C:571-572); only the added-mass force reads it
+  void save_uold_if_ready() {
+    if (!loaded || !setup_done || !(force_flags & SEDI_FORCE_ADDEDMASS) || !nlocal) return;
+    need_device();
+    k_save_uold<<<cdiv(nlocal, 256), 256, 0, stream>>>(velm[cur].p, nlocal, uold[0].get(), uold[1].get(), uold[2].get());
+    launches++;
+  }
+
+  // ---- particle injection / deletion (library.cpp:406-621).  Host round trip: the device state is
+  // folded back into the script's atom table, edited there, and uploaded again; the next run re-does setup.  Contact
+  // and wall history of surviving particles restart from zero (the reference keeps them) -- documented in DESIGN.md.
+  void sync_host_atoms() {
+    if (!loaded || !nlocal) return;
+    const int m = nlocal;
+    std::vector<double> x(3 * (size_t)m), v(3 * (size_t)m), w(3 * (size_t)m), r(m), ms(m);
+    std::vector<int> tg(m), ty(m), mk(m);
+    get_state(x.data(), v.data(), w.data(), 0, 0, r.data(), ms.data(), tg.data(), ty.data(), mk.data());
+    AtomData &a = script.atoms;
+    a.tag = tg; a.type = ty; a.x = x; a.v = v; a.omega = w; a.radius = r; a.rmass = ms;
+    script.mask = mk;
+  }
+  void create_particles(int np, const double *pos, const double *tagd, double diameter, double rho, int type, const double *vel) {
+    sync_host_atoms();
+    const int active = cfg().find_group("active");  // library.cpp:447-450: mask = 1 | bit("active")
+    for (int m = 0; m < np; m++) {
+      script.add_atom((int)tagd[m], type, diameter, rho, pos + 3 * (size_t)m, vel);
+      // the reference uses its truncated pi literal for the mass of injected particles (library.cpp:460)
+      const double rad = 0.5 * diameter;
+      script.atoms.rmass.back() = 4.0 * SEDI_PI_LIBRARY / 3.0 * rad * rad * rad * rho;
+      script.mask.back() = 1 | active;
+    }
+    loaded = false; setup_done = false;
+  }
+  void delete_particles(const int *list, int nd) {  // list holds atom tags (library.cpp:507-621)
+    sync_host_atoms();
+    std::vector<int> del(list, list + nd);
+    std::sort(del.begin(), del.end());
+    AtomData &a = script.atoms, b;
+    std::vector<int> mk;
+    for (size_t i = 0; i < a.size(); i++) {
+      if (std::binary_search(del.begin(), del.end(), a.tag[i])) continue;
+      b.tag.push_back(a.tag[i]); b.type.push_back(a.type[i]); b.radius.push_back(a.radius[i]); b.rmass.push_back(a.rmass[i]);
+      for (int d = 0; d < 3; d++) { b.x.push_back(a.x[3 * i + d]); b.v.push_back(a.v[3 * i + d]); b.omega.push_back(a.omega[3 * i + d]); }
+      mk.push_back(script.mask[i]);
+    }
+    script.atoms = b; script.mask = mk;
+    loaded = false; setup_done = false;
+  }
+};
+
+}  // namespace sedi
+
+#include "sedi_comm_impl.cuh"
+
+// =====================================================================================================================
+// C-ABI
+// =====================================================================================================================
+using sedi::Engine;
+static inline Engine *E(void *p) {
+  if (!p) sedi::fatal("NULL engine handle passed to libsedi_b200");
+  return (Engine *)p;
+}
+
+extern "C" {
+
+void lammps_open(int, char **, MPI_Comm, void **ptr) { *ptr = (void *)new Engine(); }
+void lammps_close(void *ptr) { delete (Engine *)ptr; }
+void lammps_file(void *ptr, char *path) { E(ptr)->file(path); }
+char *lammps_command(void *ptr, char *line) { E(ptr)->command(line); return NULL; }
+void lammps_sync(void *ptr) { Engine *e = E(ptr); if (e->dev_ready) { CK(cudaSetDevice(e->device)); CK(cudaStreamSynchronize(e->stream)); } e->comm.barrier(); }
+int lammps_get_global_n(void *ptr) { Engine *e = E(ptr); long long m = e->loaded ? e->nlocal : (long long)e->script.atoms.size(); return (int)e->comm.allreduce_sum_ll(m); }
+void lammps_get_initial_np(void *ptr, int *np) {
+  Engine *e = E(ptr);
+  const int m = e->loaded ? e->nlocal : (int)e->script.atoms.size();
+  e->comm.allgather_int(m, np);
+}
+void lammps_get_initial_info(void *ptr, double *coords, double *velos, double *diam, double *rho, int *tag, int *lmpCpuId,
+                             int *type) {
+  Engine *e = E(ptr);
+  if (!e->loaded) {  // before the first run the atoms still live in the script (read_data order)
+    const sedi::AtomData &a = e->script.atoms;
+    for (size_t i = 0; i < a.size(); i++) {
+      for (int d = 0; d < 3; d++) { coords[3 * i + d] = a.x[3 * i + d]; velos[3 * i + d] = a.v[3 * i + d]; }
+      const double r = a.radius[i];
+      diam[i] = r * 2.0;
+      rho[i] = 3.0 * a.rmass[i] / (4.0 * sedi::SEDI_PI_LIBRARY * r * r * r);  // library.cpp:200
+      type[i] = a.type[i]; tag[i] = a.tag[i]; lmpCpuId[i] = e->comm.rank;
+    }
+    return;
+  }
+  const int m = e->nlocal;
+  std::vector<double> r(m), ms(m);
+  e->get_state(coords, velos, 0, 0, 0, r.data(), ms.data(), tag, type, 0);
+  for (int i = 0; i < m; i++) {
+    diam[i] = r[i] * 2.0;
+    rho[i] = 3.0 * ms[i] / (4.0 * sedi::SEDI_PI_LIBRARY * r[i] * r[i] * r[i]);
+    lmpCpuId[i] = e->comm.rank;
+  }
+}
+int lammps_get_local_n(void *ptr) { Engine *e = E(ptr); return e->loaded ? e->nlocal : (int)e->script.atoms.size(); }
+void lammps_get_local_domain(void *ptr, double *dom) {
+  Engine *e = E(ptr);
+  for (int d = 0; d < 3; d++) { dom[2 * d] = e->comm.sublo(e->cfg(), d, 0.0); dom[2 * d + 1] = e->comm.subhi(e->cfg(), d, 0.0); }
+}
+void lammps_get_local_info(void *ptr, double *coords, double *velos, int *foamCpuId, int *lmpCpuId, int *tag) {
+  E(ptr)->get_local(coords, velos, foamCpuId, lmpCpuId, tag);
+}
+void lammps_put_local_info(void *ptr, int nLocalIn, double *fdrag, double *DuDt, int *foamCpuIdIn, int *tagIn) {
+  (void)DuDt;  // ignored by the reference as well (library.cpp:314-367 never reads it)
+  E(ptr)->put_local(nLocalIn, fdrag, foamCpuIdIn, tagIn);
+}
+void lammps_step(void *ptr, int n) { Engine *e = E(ptr); e->save_uold_if_ready(); e->run(n); }
+void lammps_set_timestep(void *ptr, double dt) { Engine *e = E(ptr); e->cfg().dt = dt; e->params_dirty = true; }
+double lammps_get_timestep(void *ptr) { return E(ptr)->cfg().dt; }
+void lammps_create_particle(void *ptr, int npAdd, double *position, double *tag, double diameter, double rho, int type,
+                            double *vel) {
+  E(ptr)->create_particles(npAdd, position, tag, diameter, rho, type, vel);
+}
+void lammps_delete_particle(void *ptr, int *deleteList, int nDelete) { E(ptr)->delete_particles(deleteList, nDelete); }
+
+int sedi_abi_version(void) { return 1; }
+int sedi_device_count(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return cnt;
+}
+void sedi_set_device(void *ptr, int dev) { Engine *e = E(ptr); if (e->dev_ready) sedi::fatal("sedi_set_device must precede the first compute call"); e->device = dev; }
+void sedi_set_box(void *ptr, const double *lo, const double *hi, int ntypes) {
+  Engine *e = E(ptr);
+  for (int d = 0; d < 3; d++) { e->cfg().boxlo[d] = lo[d]; e->cfg().boxhi[d] = hi[d]; }
+  e->cfg().have_box = 1; e->cfg().ntypes = ntypes; e->params_dirty = true;
+}
+void sedi_add_atoms(void *ptr, int n, const int *tag, const int *type, const double *diameter, const double *density, const double *x,
+                    const double *v) {
+  Engine *e = E(ptr);
+  for (int i = 0; i < n; i++) e->script.add_atom(tag[i], type[i], diameter[i], density[i], x + 3 * (size_t)i, v ? v + 3 * (size_t)i : 0);
+  e->loaded = false; e->setup_done = false;
+}
+void sedi_set_omega(void *ptr, int n, const int *tag, const double *omega) { E(ptr)->set_omega(n, tag, omega); }
+void sedi_get_state(void *ptr, double *x, double *v, double *omega, double *f, double *torque, double *radius, double *rmass, int *tag,
+                    int *type, int *mask) {
+  E(ptr)->get_state(x, v, omega, f, torque, radius, rmass, tag, type, mask);
+}
+long long sedi_get_pairs(void *ptr, int *tag_i, int *tag_j, unsigned *meta, int *touch, double *shear, long long cap) {
+  return E(ptr)->get_pairs(tag_i, tag_j, meta, touch, shear, cap);
+}
+void sedi_get_wall_shear(void *ptr, int wall, double *shear) { E(ptr)->get_wall_shear(wall, shear); }
+void sedi_force_rebuild(void *ptr) { Engine *e = E(ptr); if (!e->setup_done) e->setup(); else e->rebuild(); }
+long long sedi_get_stat(void *ptr, int which) {
+  Engine *e = E(ptr);
+  switch (which) {
+    case 0: return e->nbuilds;
+    case 1: return e->pair_evals;
+    case 2: return e->steps_done;
+    case 3: return e->list_gran_dir;
+    case 4: return e->list_type_dir;
+    case 5: return e->ell[e->ecur].cap;
+    case 6: return e->launches;
+    case 7: return e->nlocal;
+    case 8: return e->list_pairs_undirected();
+    case 9: return e->n - e->nlocal;
+    default: return -1;
+  }
+}
+void sedi_reset_stats(void *ptr) { Engine *e = E(ptr); e->nbuilds = e->pair_evals = e->steps_done = e->launches = 0; }
+void sedi_synchronize(void *ptr) { Engine *e = E(ptr); if (e->dev_ready) { CK(cudaSetDevice(e->device)); CK(cudaStreamSynchronize(e->stream)); } }
+void *sedi_stream(void *ptr) { Engine *e = E(ptr); e->need_device(); return (void *)e->stream; }
+double sedi_last_step_ms(void *ptr) { return E(ptr)->last_step_ms; }
+void sedi_timer_start(void *ptr) { Engine *e = E(ptr); e->need_device(); CK(cudaEventRecord(e->evt0, e->stream)); }
+double sedi_timer_stop_ms(void *ptr) {
+  Engine *e = E(ptr);
+  e->need_device();
+  CK(cudaEventRecord(e->evt1, e->stream));
+  CK(cudaEventSynchronize(e->evt1));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, e->evt0, e->evt1));
+  return ms;
+}
+void sedi_profile(void *ptr, int on) { Engine *e = E(ptr); e->prof_on = (on != 0); e->prof_ms = 0; e->prof_steps = 0; }
+long long sedi_get_profile(void *ptr, double *kernel_ms) { Engine *e = E(ptr); if (kernel_ms) *kernel_ms = e->prof_ms; return e->prof_steps; }
+
+void sedi_mesh_box(void *ptr, const double *lo, const double *hi, const int *ncell) { E(ptr)->mesh_box(lo, hi, ncell); }
+int sedi_mesh_ncells(void *ptr) { return E(ptr)->ncells; }
+void sedi_coupling_config(void *ptr, int drag_model, int force_flags, double nub, double rhob, const double *g, double deltaT) {
+  Engine *e = E(ptr);
+  if (drag_model != SEDI_DRAG_ERGUN_WENYU_ID && drag_model != SEDI_DRAG_SYAMLAL_OBRIEN_ID) sedi::fatal("Unknown dragModel id");
+  e->drag_model = drag_model; e->force_flags = force_flags; e->nub = nub; e->rhob = rhob; e->deltaT = deltaT;
+  for (int d = 0; d < 3; d++) e->gvec[d] = g ? g[d] : 0.0;
+}
+void sedi_put_cell_fields(void *ptr, const double *Uf, const double *gamma, const double *gradp, const double *DDtU, const double *curlU) {
+  E(ptr)->put_cell_fields(Uf, gamma, gradp, DDtU, curlU);
+}
+void sedi_locate(void *ptr) { Engine *e = E(ptr); if (!e->setup_done) e->setup(); e->locate(); }
+void sedi_compute_fluid_force(void *ptr) { E(ptr)->fluid_force(); }
+void sedi_scatter_alpha_u(void *ptr, double *gamma, double *Ue) { E(ptr)->scatter_alpha_u(gamma, Ue); }
+void sedi_calc_tc(void *ptr, double *Asrc, double *Omega) { E(ptr)->calc_tc(Asrc, Omega); }
+void sedi_enable_diag(void *ptr, int on) { E(ptr)->want_diag = (on != 0); }
+void sedi_get_coupling_diag(void *ptr, int *cell, double *Uri, double *magUri, double *alphap, double *Jd, double *F) {
+  E(ptr)->get_coupling_diag(cell, Uri, magUri, alphap, Jd, F);
+}
+void sedi_step(void *ptr, int n) { Engine *e = E(ptr); e->save_uold_if_ready(); e->run(n); }
+
+int sedi_comm_init(void *ptr, int rank, int nranks, const void *nccl_unique_id, int id_bytes, const int *procgrid) {
+  return E(ptr)->comm.init(*E(ptr), rank, nranks, nccl_unique_id, id_bytes, procgrid);
+}
+int sedi_comm_unique_id(void *out, int cap) { return sedi::Comm::unique_id(out, cap); }
+
+}  // extern "C"

@@ -1,0 +1,155 @@
+"""-m gpu: the drop-in boundary (interfaceToLammps/library.h) and the coupling kernels against the oracle."""
+import numpy as np
+import pytest
+
+from sedifoam_b200 import cases
+from sedifoam_b200 import DRAG_ERGUN_WENYU, DRAG_SYAMLAL_OBRIEN, FORCE_DRAG, FORCE_PGRAD, FORCE_BUOY, FORCE_ADDEDMASS, FORCE_LIFT
+from util import make_engine, make_oracle, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_initial_info_and_local_info(oracle_mod):
+    case = cases.fluidized_bed(dims=(6, 7, 6))
+    e = make_engine(case)
+    n = len(case["tag"])
+    assert e.get_global_n() == n and e.get_local_n() == n
+    assert e.get_initial_np(1)[0] == n
+    info = e.get_initial_info()
+    o = np.argsort(info["tag"])
+    assert np.array_equal(info["tag"][o], case["tag"])
+    assert np.array_equal(info["x"][o], case["x"])
+    assert np.array_equal(info["diam"][o], case["diam"])
+    # density comes back through the reference's truncated-pi literal (library.cpp:200): close to, not equal to, rho
+    assert np.all(np.abs(info["rho"][o] / case["rho"] - 1.0) < 1e-11) and not np.array_equal(info["rho"][o], case["rho"])
+    assert np.allclose(e.get_local_domain(), np.stack([case["box_lo"], case["box_hi"]], axis=1).ravel())
+    e.setup()
+    info2 = e.get_initial_info()   # now served from the device
+    o2 = np.argsort(info2["tag"])
+    for k in ("x", "v", "diam", "rho", "type"):
+        assert np.array_equal(info2[k][o2], info[k][o])
+    rng = np.random.default_rng(3)
+    foam = rng.integers(0, 4, size=n).astype(np.int32)
+    perm = rng.permutation(n)
+    e.put_local_info(np.zeros((n, 3)), case["tag"][perm], foam_cpu=foam[perm])
+    loc = e.get_local_info()
+    o3 = np.argsort(loc["tag"])
+    assert np.array_equal(loc["tag"][o3], case["tag"])
+    assert np.array_equal(loc["foamCpuId"][o3], foam)
+    assert np.all(loc["lmpCpuId"] == 0)
+    assert np.array_equal(loc["x"][o3], case["x"])
+
+
+def test_timestep_accessors():
+    case = cases.fluidized_bed(dims=(4, 4, 4))
+    e = make_engine(case)
+    assert e.get_timestep() == 2.0e-6
+    e.set_timestep(1.0e-6)
+    assert e.get_timestep() == 1.0e-6
+
+
+def test_put_local_info_drives_fdrag(oracle_mod):
+    """a free particle under a constant fluid force: v = F/m * t exactly as the oracle integrates it"""
+    case = cases.sediment_column(dims=(4, 4, 4), phi=0.05, jitter_frac=0.0)
+    case["script"] = case["script"].replace("fix 2 all gravity 9.8", "fix 2 all gravity 0.0")
+    o = make_oracle(oracle_mod, case); e = make_engine(case)
+    n = len(case["tag"])
+    F = np.tile([1e-7, -2e-7, 3e-7], (n, 1)) * np.arange(1, n + 1)[:, None]
+    o.setup(); e.setup()
+    perm = np.random.default_rng(5).permutation(n)
+    o.put_fdrag(F[perm], case["tag"][perm]); e.put_local_info(F[perm], case["tag"][perm])
+    o.run(50); e.step(50)
+    a, b = o.atoms(), e.atoms()
+    assert np.array_equal(a["v"], b["v"]) and np.array_equal(a["x"], b["x"])   # no pair forces: bitwise
+    m = case["rho"] * np.pi / 6 * case["diam"] ** 3
+    # the setup force evaluation preceded the put, so the first half kick saw no fluid force: 49.5 steps of F/m
+    assert np.allclose(b["v"], F / m[:, None] * 49.5 * 2e-6, rtol=1e-9)
+
+
+def test_added_mass_carrier_rho(oracle_mod):
+    """fix fdrag <carrier_rho>: LAMMPS-side added-mass term (fix_fluid_drag.cpp:144-163)"""
+    case = cases.sediment_column(dims=(5, 6, 5), phi=0.45, jitter_frac=0.08)
+    case["script"] = case["script"].replace("fix 3 all fdrag", "fix 3 all fdrag 1000")
+    o = make_oracle(oracle_mod, case); e = make_engine(case)
+    o.run(200); e.step(200)
+    a, b = o.atoms(), e.atoms()
+    assert rel_err(b["v"], a["v"]) < 1e-6 and rel_err(b["x"], a["x"]) < 1e-6
+
+
+def _fields(case, rng):
+    C = int(np.prod(case["mesh_n"]))
+    Uf = rng.normal(scale=0.05, size=(C, 3)); gradp = rng.normal(scale=100.0, size=(C, 3))
+    DDtU = rng.normal(scale=5.0, size=(C, 3)); curlU = rng.normal(scale=20.0, size=(C, 3))
+    gamma = rng.uniform(0.0, 0.6, size=C)
+    return Uf, gamma, gradp, DDtU, curlU
+
+
+@pytest.mark.parametrize("model", [DRAG_ERGUN_WENYU, DRAG_SYAMLAL_OBRIEN])
+@pytest.mark.parametrize("flags", [FORCE_DRAG | FORCE_PGRAD, FORCE_DRAG | FORCE_PGRAD | FORCE_BUOY | FORCE_ADDEDMASS | FORCE_LIFT])
+def test_coupling_gather_force_scatter(oracle_mod, model, flags):
+    case = cases.fluidized_bed(dims=(12, 14, 12), vjit=0.05)
+    rng = np.random.default_rng(17)
+    e = make_engine(case)
+    e.mesh_box(case["mesh_lo"], case["mesh_hi"], case["mesh_n"])
+    e.coupling_config(model, flags, case["nub"], case["rhob"], case["g"], 2.0e-4)
+    Uf, gamma, gradp, DDtU, curlU = _fields(case, rng)
+    e.step(30)   # also records UOld for the added-mass term
+    st0 = e.atoms()
+    e.step(20)
+    st = e.atoms()
+    e.put_cell_fields(Uf, gamma, gradp, DDtU, curlU)
+    e.enable_diag(True)
+    e.compute_fluid_force()
+    dg = e.coupling_diag()
+    # cell owner: bit exact
+    cell = oracle_mod.cell_owner(st["x"], case["mesh_lo"], case["mesh_hi"], case["mesh_n"])
+    assert np.array_equal(dg["cell"], cell)
+    d = 2.0 * st["radius"]
+    ref = oracle_mod.particle_force(cell, d, st["v"], st0["v"] if False else _uold(e, st0, st), Uf, gamma, gradp, DDtU, curlU, model, flags,
+                                    case["nub"], case["rhob"], np.asarray(case["g"], float), 2.0e-4)
+    assert rel_err(dg["Uri"], ref["Uri"]) < 1e-14
+    assert rel_err(dg["alpha"], ref["alpha"]) == 0
+    assert rel_err(dg["Jd"], ref["Jd"]) < 1e-12      # pow() differs from glibc in the last ulps
+    assert rel_err(dg["F"], ref["F"]) < 1e-12
+    # scatter 1 (particleToEulerianField) and scatter 2 (calcTcFields)
+    C = len(gamma)
+    cellV = np.full(C, np.prod((case["mesh_hi"] - case["mesh_lo"]) / case["mesh_n"]))
+    g_ref, Ue_ref = oracle_mod.particle_to_eulerian(cell, d, st["v"], cellV)
+    e.put_cell_fields(gamma=gamma)
+    A_ref, Om_ref = oracle_mod.calc_tc(cell, d, st["v"], Uf, gamma, cellV, model, case["nub"], case["rhob"])
+    A, Om = e.calc_tc()
+    assert rel_err(A, A_ref) < 1e-11 and np.all(Om == 0) and np.all(Om_ref == 0)
+    g, Ue = e.scatter_alpha_u()
+    assert rel_err(g, g_ref) < 1e-12 and rel_err(Ue, Ue_ref) < 1e-11
+    # conservation: sum gamma V = sum Vp  (the reference's built-in invariant, enhancedCloud.C:964-976)
+    assert abs((g * cellV).sum() / (np.pi / 6 * (d[cell >= 0] ** 3).sum()) - 1.0) < 1e-12
+
+
+def _uold(e, st0, st):
+    # UOld is the velocity before the last lammps_step call
+    return st0["v"]
+
+
+def test_single_sphere_golden_curve():
+    """configs[0] = shipped cases/auto-testing/test-cases/xiaocase3: v_y(t) against data/lammps08.dat and xiaoCase3.dat"""
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = np.loadtxt(os.path.join(here, "golden", "xiaocase3_lammps08.dat"))
+    xiao = np.loadtxt(os.path.join(here, "golden", "xiaocase3_xiaoCase3.dat"))
+    case = cases.single_sphere()
+    e = make_engine(case)
+    e.mesh_box(case["mesh_lo"], case["mesh_hi"], case["mesh_n"])
+    e.coupling_config(DRAG_SYAMLAL_OBRIEN, FORCE_DRAG | FORCE_PGRAD, case["nub"], case["rhob"], case["g"], 2e-5)
+    Uf, gamma, gradp = cases.uniform_fields(case)
+    e.put_cell_fields(Uf, gamma, gradp)
+    t, vy = [0.0], [0.0]
+    for k in range(250):
+        e.compute_fluid_force()
+        e.sedi_step(100)
+        t.append((k + 1) * 2e-5); vy.append(e.atoms()["v"][0, 1])
+    t = np.array(t); vy = np.array(vy)
+    for row in gold[2:]:   # see tests/test_oracle_golden.py for the tolerances
+        assert abs(np.interp(row[0], t, vy) - row[2]) < 0.04 * 0.05
+    for tt, vv in xiao:
+        if tt > 2e-4:
+            assert abs(np.interp(tt, t, vy) - vv) < 0.05 * 0.05
