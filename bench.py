@@ -21,7 +21,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -84,34 +83,51 @@ def cpu_throughput(nsteps, cores, dims_total=BED_DIMS):
 
 
 # --------------------------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index = index
-        self.samples = []
-        self.reasons = set()
-        self.stop_flag = False
-        self.max_mhz = None
+class ClockSampler:
+    """one long-running `nvidia-smi -lms 200` (the profiling recipe's clocks line) for the duration of the timed regions"""
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop_flag:
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        import tempfile
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="sedi_clocks_", suffix=".csv")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=fd, stderr=subprocess.DEVNULL)
+            os.close(fd)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is not None:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
-                for nm, v in zip(names, out[2:]):
-                    if "Active" in v and "Not" not in v:
-                        self.reasons.add(nm)
+                self.proc.terminate()
+                self.proc.wait(timeout=5)
             except Exception:
                 pass
-            time.sleep(0.2)
 
     def summary(self):
-        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons)}
+        samples, reasons, mx = [], set(), None
+        try:
+            for ln in open(self.path):
+                out = [v.strip() for v in ln.split(",")]
+                if len(out) < 6:
+                    continue
+                samples.append(float(out[0])); mx = float(out[1])
+                for nm, v in zip(self.NAMES, out[2:]):
+                    if v.startswith("Active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return {"sm_mhz": float(np.median(samples)) if samples else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(samples)}
 
 
 def load_peak():
@@ -121,7 +137,18 @@ def load_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def log(msg):
+    if os.environ.get("SEDI_BENCH_VERBOSE"):
+        print("[bench %.1fs] %s" % (time.perf_counter() - T_START, msg), file=sys.stderr, flush=True)
+
+
+T_START = time.perf_counter()
+
+
 def main():
+    if os.environ.get("SEDI_BENCH_TRACE"):
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["SEDI_BENCH_TRACE"]), repeat=True, file=sys.stderr)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -146,7 +173,7 @@ def main():
             return 0
         cores = os.cpu_count() or 1
         cores = 8 if cores >= 8 else (4 if cores >= 4 else (2 if cores >= 2 else 1))
-        nsteps = 10
+        nsteps = S
         # each "step" of the reference arm is a bounded sample: `nsteps` DEM sub-steps of the same bed on all host cores
         vals = []
         t_all = time.perf_counter()
@@ -163,7 +190,7 @@ def main():
                 "impl": "reference", "config": config,
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": vals[-1]["cores"], "kind": vals[-1]["kind"], "sample": vals[-1]["sample"]},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
         return 0
 
     import torch
@@ -196,6 +223,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    log("generating case")
     case = cases.fluidized_bed(dims=dims, seed=cases.SEED + rank)
     n = len(case["tag"])
     eng = sb.Lammps(device=local_rank)
@@ -204,8 +232,10 @@ def main():
     eng.coupling_config(sb.DRAG_ERGUN_WENYU, sb.FORCE_DRAG | sb.FORCE_PGRAD, case["nub"], case["rhob"], case["g"], S * case["dt"])
     Uf, gamma, gradp = cases.uniform_fields(case)
     eng.put_cell_fields(Uf, gamma, gradp)
+    log("setup")
     eng.setup()
     eng.scatter_alpha_u(device_only=True)
+    log("setup done, %d particles, %d pairs" % (n, eng.stat("gran_pairs")))
 
     def device_step():
         eng.compute_fluid_force()
@@ -215,6 +245,7 @@ def main():
 
     for _ in range(W):
         device_step()
+        log("warm-up step done: %.2f ms, rebuilds so far %d" % (eng.last_step_ms(), eng.stat("nbuilds")))
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -226,6 +257,7 @@ def main():
     for _ in range(K):
         device_step()
     ms_dev = eng.timer_stop_ms()
+    log("timed region done: %.2f ms" % ms_dev)
     eng.synchronize(); barrier()
     wall = time.perf_counter() - t0
     ms = allmax(max(ms_dev, 0.0))
@@ -256,13 +288,13 @@ def main():
     eng.synchronize()
     e2e_s = allmax(time.perf_counter() - t1)
     barrier()
+    log("e2e region done: %.3f s" % e2e_s)
     e2e_evals = allsum(float(eng.stat("pair_evals")))
     e2e_value = e2e_evals / e2e_s / 1e6
     h2d = n * (24 + 4 + 4)
     d2h = n * (24 + 24 + 4 + 4)
     if rank == 0:
-        sampler.stop_flag = True
-        sampler.join(timeout=2)
+        sampler.stop()
 
     # ---- roofline of the dominant kernel (fused DEM sub-step): 188 B / particle + 56 B / undirected pair per launch
     peak, peak_src = load_peak()
@@ -286,7 +318,7 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         try:
             cores = 8 if (os.cpu_count() or 1) >= 8 else 1
-            cpu = cpu_throughput(10, cores, dims)
+            cpu = cpu_throughput(2 * S, cores, dims)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:  # the checker is test infrastructure; its absence must not break the GPU number
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
@@ -301,8 +333,10 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
                 "particle_steps_per_s": world * n * K * S / (ms * 1e-3), "wall_s_timed_region": wall}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    eng.close()
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
@@ -312,4 +346,6 @@ def eng_steps(K, S):
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    rc = main()
+    sys.stdout.flush(); sys.stderr.flush()
+    os._exit(rc)   # skip interpreter finalisation: two CUDA runtimes (torch's and the engine's) tear down in undefined order

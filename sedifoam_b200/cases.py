@@ -133,7 +133,7 @@ fix yt all wall/granFix {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 yplane NULL {hi[1]
                  extra=dict(name="cohesive_shear_bed", Uf=(0.05, 0.0, 0.0), g=(0.0, -9.8, 0.0), dt=dt, substeps=100))
 
 
-def poly_lubricated(dims=(20, 20, 20), dmin=3.0e-4, dmax=7.0e-4, rho=2650.0, phi=0.45, dt=2.0e-6, kn=1.0e7, e=0.9, mu=0.4,
+def poly_lubricated(dims=(20, 20, 20), dmin=3.0e-4, dmax=7.0e-4, rho=2650.0, phi=0.18, dt=2.0e-6, kn=1.0e7, e=0.9, mu=0.4,
                     visc=1.0e-3, seed=SEED, vjit=0.01):
     """configs[4]: polydisperse periodic packing with hybrid/overlay gran/hertzFix/history + lubricate/poly (full list).
     cut_inner is 1.001*dmax: the reference switches lubrication off inside cut_inner (pair_lubricate_poly.cpp:294-297)

@@ -121,13 +121,16 @@ __global__ void k_save_uold(const D4 *velm, int n, double *u0, double *u1, doubl
 __device__ __forceinline__ void warp_cell_add4(int key, double a, double b, double c, double d, double *dsta, double *dstv) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  for (int o = 1; o < 32; o <<= 1) {
-    const int k2 = __shfl_down_sync(full, key, o);
-    const double a2 = __shfl_down_sync(full, a, o), b2 = __shfl_down_sync(full, b, o), c2 = __shfl_down_sync(full, c, o), d2 = __shfl_down_sync(full, d, o);
-    if (lane + o < 32 && k2 == key) { a += a2; b += b2; c += c2; d += d2; }
-  }
   const int kprev = __shfl_up_sync(full, key, 1);
-  if (key >= 0 && (lane == 0 || kprev != key)) {
+  const bool head = (lane == 0) || (kprev != key);
+  const unsigned heads = __ballot_sync(full, head);
+  const unsigned above = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));  // run heads strictly above this lane
+  const int end = above ? (__ffs(above) - 1) : 32;                            // first lane of the next run
+  for (int o = 1; o < 32; o <<= 1) {
+    const double a2 = __shfl_down_sync(full, a, o), b2 = __shfl_down_sync(full, b, o), c2 = __shfl_down_sync(full, c, o), d2 = __shfl_down_sync(full, d, o);
+    if (lane + o < end) { a += a2; b += b2; c += c2; d += d2; }
+  }
+  if (key >= 0 && head) {
     if (dsta) atomicAdd(&dsta[key], a);
     atomicAdd(&dstv[3 * (size_t)key], b); atomicAdd(&dstv[3 * (size_t)key + 1], c); atomicAdd(&dstv[3 * (size_t)key + 2], d);
   }
