@@ -82,6 +82,15 @@ struct StepParams {
   double kn, kt, gamman, gammat, xmu, beta;
   double prd[3];
   double lub_mu, lub_cutsq, lub_cut_inner, lub_R0, lub_RT0;
+  // host-folded constants of the Hertz-Mindlin "Fix" law (pair_gran_hertzFix_history.cpp:192-236)
+  double c_sn;     // 2/1.82 * kn              : sn = c_sn * polyhertz
+  double c_ccel;   // 4/5.46 * kn              : elastic part of ccel = polyhertz * c_ccel * (radsum - r) / r
+  double c_damp;   // 2 sqrt(5/6) beta         : damp = c_damp * vnnr / rsq
+  double c_kts;    // 8/8.84 * kt              : tangential spring = -polyhertz * c_kts * shear
+  double c_ctd;    // sqrt(st/sn) 2 sqrt(5/6) beta : tangential dashpot = sqrt(sn meff) * c_ctd
+  double c_ekt;    // 8/(8.84 kt)              : Coulomb rescale offset = ctd * vtr * c_ekt
+  int has_fdrag, fdrag_added_mass;
+  double imgshift[27][3];  // periodic image code -> shift vector
   FixDev fix[MAX_FIXES];
 };
 

@@ -442,7 +442,20 @@ class Engine {
     P.trigger_sq = 0.25 * c.skin * c.skin;
     P.kn = c.gran.kn; P.kt = c.gran.kt; P.gamman = c.gran.gamman; P.gammat = c.gran.gammat; P.xmu = c.gran.xmu;
     P.beta = (c.pair == PAIR_HERTZFIX_HISTORY) ? fix_beta(c.gran.gamman) : 0.0;
+    {  // loop invariants of the Hertz-Mindlin "Fix" law, folded once (see hertzfix_fast)
+      const double s56 = sqrt(5.0 / 6.0);
+      P.c_sn = 2.0 * 1.0 / 1.82 * P.kn;
+      P.c_ccel = 4.0 / 5.46 * P.kn;
+      P.c_damp = 2.0 * s56 * P.beta;
+      P.c_kts = 8.0 / 8.84 * P.kt;
+      P.c_ctd = sqrt((8.0 / 8.84) / (2.0 / 1.82)) * (2.0 * s56 * P.beta);
+      P.c_ekt = (P.kt != 0.0) ? 8.0 / (8.84 * P.kt) : 0.0;
+    }
     for (int d = 0; d < 3; d++) P.prd[d] = c.boxhi[d] - c.boxlo[d];
+    for (int img = 0; img < 27; img++) {
+      const int ix = img % 3 - 1, iy = (img / 3) % 3 - 1, iz = img / 9 - 1;
+      P.imgshift[img][0] = ix * P.prd[0]; P.imgshift[img][1] = iy * P.prd[1]; P.imgshift[img][2] = iz * P.prd[2];
+    }
     P.lub_mu = c.lub.mu; P.lub_cutsq = c.lub.cut_global * c.lub.cut_global; P.lub_cut_inner = c.lub.cut_inner;
     P.lub_R0 = lub_R0; P.lub_RT0 = lub_RT0;
     P.ctrl = ctrl.p;
@@ -454,7 +467,7 @@ class Engine {
       switch (s.kind) {
         case FIX_NVE_SPHERE: P.nve_groupbit |= s.groupbit; break;
         case FIX_GRAVITY: for (int d = 0; d < 3; d++) F.d[d] = s.g * s.gdir[d]; break;
-        case FIX_FDRAG: F.d[0] = s.carrier_rho; break;
+        case FIX_FDRAG: F.d[0] = s.carrier_rho; P.has_fdrag = 1; if (s.carrier_rho != 0.0) P.fdrag_added_mass = 1; break;
         case FIX_COHESIVE: F.d[0] = s.ah; F.d[1] = s.lam; F.d[2] = s.smin; F.d[3] = s.smax; F.i0 = s.opt; P.has_cohesive = 1; break;
         case FIX_WALL_GRAN:
           F.i0 = s.wallstyle; F.i1 = s.wiggle; F.i2 = s.wshear; F.i3 = s.axis;
@@ -504,11 +517,24 @@ class Engine {
     fill_launch(P, mode, in, ntimestep);
     const int blocks = cdiv(n, 128);
     if (!blocks) return;
+    const bool tl = P.has_cohesive || P.lub_enabled;
     switch (cfg().pair) {
-      case PAIR_HERTZFIX_HISTORY: k_step<PAIR_HERTZFIX_HISTORY><<<blocks, 128, 0, stream>>>(P, seq); break;
-      case PAIR_HOOKE_HISTORY: k_step<PAIR_HOOKE_HISTORY><<<blocks, 128, 0, stream>>>(P, seq); break;
-      case PAIR_HOOKE: k_step<PAIR_HOOKE><<<blocks, 128, 0, stream>>>(P, seq); break;
-      default: k_step<PAIR_NONE><<<blocks, 128, 0, stream>>>(P, seq); break;
+      case PAIR_HERTZFIX_HISTORY:
+        if (tl) k_step<PAIR_HERTZFIX_HISTORY, true><<<blocks, 128, 0, stream>>>(P, seq);
+        else k_step<PAIR_HERTZFIX_HISTORY, false><<<blocks, 128, 0, stream>>>(P, seq);
+        break;
+      case PAIR_HOOKE_HISTORY:
+        if (tl) k_step<PAIR_HOOKE_HISTORY, true><<<blocks, 128, 0, stream>>>(P, seq);
+        else k_step<PAIR_HOOKE_HISTORY, false><<<blocks, 128, 0, stream>>>(P, seq);
+        break;
+      case PAIR_HOOKE:
+        if (tl) k_step<PAIR_HOOKE, true><<<blocks, 128, 0, stream>>>(P, seq);
+        else k_step<PAIR_HOOKE, false><<<blocks, 128, 0, stream>>>(P, seq);
+        break;
+      default:
+        if (tl) k_step<PAIR_NONE, true><<<blocks, 128, 0, stream>>>(P, seq);
+        else k_step<PAIR_NONE, false><<<blocks, 128, 0, stream>>>(P, seq);
+        break;
     }
     launches++;
   }

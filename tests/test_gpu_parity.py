@@ -66,7 +66,7 @@ def test_neighbour_lists_bit_exact_at_build(oracle_mod, name):
     re_, _, _ = engine_rows(e, "gran")
     (ro,) = sort_rows(ro); (re_,) = sort_rows(re_)
     assert ro.shape == re_.shape and np.array_equal(ro, re_)
-    assert len(ro) > 0
+    assert len(ro) > 0 or "lubricate" in case["script"]   # the dilute lubrication case has no granular neighbours
     assert e.stat("gran_pairs") == o.stat("gran_pairs")
     if "cohesive" in case["script"]:
         rt, _, _ = directed_from_oracle(o, "half")
@@ -116,7 +116,12 @@ def test_trajectory_parity(oracle_mod, name):
     rg, tg, sg = engine_rows(e, "gran")
     ro, to, so = sort_rows(ro, to, so); rg, tg, sg = sort_rows(rg, tg, sg)
     assert np.array_equal(ro, rg)
-    if to is not None:
+    if "lubricate" in case["script"]:
+        rt, _, _ = directed_from_oracle(o, "full")
+        rq, _, _ = engine_rows(e, "type")
+        (rt,) = sort_rows(rt); (rq,) = sort_rows(rq)
+        assert len(rt) > 0 and np.array_equal(rt, rq)
+    if to is not None and len(to):
         assert np.array_equal(to, tg)
         if np.abs(so).max() > 0:
             assert rel_err(sg, so) < 1e-5
