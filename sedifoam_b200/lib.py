@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
 
 
 def library_path():
-    return os.path.join(_HERE, "libsedi_b200.so")
+    return os.environ.get("SEDI_B200_LIB", os.path.join(_HERE, "libsedi_b200.so"))
 
 
 def build_library(verbose=False):
