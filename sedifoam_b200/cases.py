@@ -195,3 +195,25 @@ def uniform_fields(case, gamma=None):
     gradp = np.tile(case["rhob"] * np.asarray(case["g"], np.float64), (C, 1))
     gam = np.zeros(C) if gamma is None else gamma
     return Uf, gam, gradp
+
+
+def write_lammps_files(case, directory):
+    """the same case as LAMMPS files: a `read_data` file (id type diameter density x y z) and an
+    in.lammps in the style of the shipped cases.  Returns the script path."""
+    import os
+    data = os.path.join(directory, "IC.in")
+    lo, hi = case["box_lo"], case["box_hi"]
+    with open(data, "w") as f:
+        f.write("LAMMPS data file\n\n%d atoms\n%d atom types\n\n" % (len(case["tag"]), case["ntypes"]))
+        for k, ax in enumerate("xyz"):
+            f.write("%.17g %.17g %slo %shi\n" % (lo[k], hi[k], ax, ax))
+        f.write("\nAtoms\n\n")
+        for i in range(len(case["tag"])):
+            f.write("%d %d %.17g %.17g %.17g %.17g %.17g\n" % (case["tag"][i], case["type"][i], case["diam"][i], case["rho"][i],
+                                                              case["x"][i, 0], case["x"][i, 1], case["x"][i, 2]))
+    script = os.path.join(directory, "in.lammps")
+    with open(script, "w") as f:
+        f.write("atom_style sphere\natom_modify map array\nboundary %s\nnewton off\ncommunicate single vel yes\n" % " ".join(case["periodic"]))
+        f.write("read_data %s\n" % data)
+        f.write(case["script"])
+    return script

@@ -24,6 +24,8 @@
 #include <vector>
 
 #include "../../include/sedi_b200.h"
+#include "../../include/lammps_shim/lammps.h"
+#include "../../include/lammps_shim/input.h"
 #include "lmp_script.hpp"
 #include "sedi_device.cuh"
 #include "sedi_neigh.cuh"
@@ -1018,15 +1020,25 @@ class Engine {
 // C-ABI
 // =====================================================================================================================
 using sedi::Engine;
+
+// The handle that crosses the boundary is a LAMMPS_NS::LAMMPS* exactly as in the reference (softParticleCloud.H:71
+// holds `LAMMPS* lmp_` and passes it as the `void *` of library.h): include/lammps_shim/lammps.h.
+namespace LAMMPS_NS {
+LAMMPS::LAMMPS(int, char **, MPI_Comm communicator) : input(new Input(this)), engine(new Engine()), world(communicator) {}
+LAMMPS::~LAMMPS() { delete (Engine *)engine; delete input; }
+char *Input::one(const char *line) { ((Engine *)lmp->engine)->command(line); return NULL; }
+void Input::file(const char *path) { ((Engine *)lmp->engine)->file(path); }
+}  // namespace LAMMPS_NS
+
 static inline Engine *E(void *p) {
-  if (!p) sedi::fatal("NULL engine handle passed to libsedi_b200");
-  return (Engine *)p;
+  if (!p) sedi::fatal("NULL LAMMPS handle passed to libsedi_b200");
+  return (Engine *)((LAMMPS_NS::LAMMPS *)p)->engine;
 }
 
 extern "C" {
 
-void lammps_open(int, char **, MPI_Comm, void **ptr) { *ptr = (void *)new Engine(); }
-void lammps_close(void *ptr) { delete (Engine *)ptr; }
+void lammps_open(int argc, char **argv, MPI_Comm comm, void **ptr) { *ptr = (void *)new LAMMPS_NS::LAMMPS(argc, argv, comm); }
+void lammps_close(void *ptr) { delete (LAMMPS_NS::LAMMPS *)ptr; }
 void lammps_file(void *ptr, char *path) { E(ptr)->file(path); }
 char *lammps_command(void *ptr, char *line) { E(ptr)->command(line); return NULL; }
 void lammps_sync(void *ptr) { Engine *e = E(ptr); if (e->dev_ready) { CK(cudaSetDevice(e->device)); CK(cudaStreamSynchronize(e->stream)); } e->comm.barrier(); }
