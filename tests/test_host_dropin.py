@@ -47,7 +47,7 @@ def test_foam_side_compiles_and_reads_the_script(driver, tmp_path):
 
 @pytest.mark.gpu
 def test_put_step_get_sequence_matches_oracle(driver, tmp_path, oracle_mod):
-    case = cases.fluidized_bed(dims=(8, 9, 8))
+    case = cases.fluidized_bed(dims=(8, 9, 8), vjit=0.0)   # a read_data file carries no velocities
     script = cases.write_lammps_files(case, str(tmp_path))
     acc = (0.5, 3.0, -0.25)
     out = _run(driver, [script, 3, 50, "host"] + list(acc))
@@ -70,7 +70,7 @@ def test_put_step_get_sequence_matches_oracle(driver, tmp_path, oracle_mod):
 @pytest.mark.gpu
 def test_enhanced_cloud_mirror(driver, tmp_path):
     """evolve() + calcTcFields() through include/sedi_cloud.hpp against the same sequence through the ctypes binding"""
-    case = cases.fluidized_bed(dims=(8, 9, 8))
+    case = cases.fluidized_bed(dims=(8, 9, 8), vjit=0.0)
     script = cases.write_lammps_files(case, str(tmp_path))
     env = {"MESH_X0": case["mesh_lo"][0], "MESH_Y0": case["mesh_lo"][1], "MESH_Z0": case["mesh_lo"][2],
            "MESH_X1": case["mesh_hi"][0], "MESH_Y1": case["mesh_hi"][1], "MESH_Z1": case["mesh_hi"][2],
