@@ -121,6 +121,14 @@ void sedi_step(void *ptr, int n);
  * lammpsFoam run, torch.distributed in bench.py); procgrid may be NULL (taken from the script / factorised). */
 int sedi_comm_unique_id(void *out, int cap); /* returns the id size in bytes, 0 when NCCL is unavailable */
 int sedi_comm_init(void *ptr, int rank, int nranks, const void *nccl_unique_id, int id_bytes, const int *procgrid);
+int sedi_comm_rank(void *ptr);
+/* which: 0 ghost refreshes issued, 1 border rows sent per refresh, 2 ghost rows, 3 neighbour links, 4 arrivals at the last rebuild */
+long long sedi_comm_stat(void *ptr, int which);
+/* host-only decomposition logic: LAMMPS-style processor grid, owner rank of a position, neighbour links of a brick
+ * (peers[26], offsets[26][3], shifts[26][3]; returns the link count) */
+void sedi_decomp_grid(int nranks, const double *boxlen, int *grid);
+int sedi_decomp_owner(const double *x, const double *boxlo, const double *boxhi, const int *grid);
+int sedi_decomp_links(int rank, const int *grid, const int *periodic, const double *prd, int *peers, int *offsets, double *shifts);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,7 @@ package is the thin ctypes binding used by the tests and by ``bench.py``; it mir
 raises immediately.
 """
 from .lib import Lammps, build_library, library_path, load_library, EXPORTED_SYMBOLS  # noqa: F401
+from .lib import decomp_grid, decomp_owner, decomp_links  # noqa: F401
 from .lib import DRAG_ERGUN_WENYU, DRAG_SYAMLAL_OBRIEN, FORCE_DRAG, FORCE_PGRAD, FORCE_BUOY, FORCE_ADDEDMASS, FORCE_LIFT  # noqa: F401
 
 __all__ = ["Lammps", "build_library", "library_path", "load_library", "EXPORTED_SYMBOLS"]

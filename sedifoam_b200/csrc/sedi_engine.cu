@@ -31,6 +31,7 @@
 #include "sedi_neigh.cuh"
 #include "sedi_step.cuh"
 #include "sedi_couple.cuh"
+#include "sedi_halo.cuh"
 #include "sedi_comm.cuh"
 
 #define CK(call)                                                                                              \
@@ -165,6 +166,8 @@ __global__ void k_fill_double(double *p, size_t n, double v) {
   if (i < n) p[i] = v;
 }
 
+class Engine;
+static void g_comm_engine_set(Engine *e);
 static const int NPLANES_BASE = 6;  // f, tq, fdrag, dudt, vold, uold (x3 each)
 
 class Engine {
@@ -178,7 +181,8 @@ class Engine {
   double prof_ms;
   long long prof_steps;
   // particle rows
-  int n, nlocal, npad, maxtag;
+  int n, nlocal, nghost, npad, maxtag;   // n = nlocal + nghost rows; npad = capacity of the per-row arrays
+  Buf<int> leave;                        // migration flags (multi-GPU)
   Buf<D4> posr[2], velm[2], omgt[2];
   int cur;
   Plane2 f[3], tq[3], fdrag[3], dudt[3], vold[3], uold[3], xhold[3];
@@ -226,7 +230,7 @@ class Engine {
 
   Engine()
       : device(0), dev_ready(false), loaded(false), setup_done(false), params_dirty(true), cell_valid(false), stream(0), n(0),
-        nlocal(0), npad(0), maxtag(0), cur(0), icur(0), ecur(0), cutneighmax(0), dt_init(0), lub_R0(0), lub_RT0(0), lub_RS0(0),
+        nlocal(0), nghost(0), npad(0), maxtag(0), cur(0), icur(0), ecur(0), cutneighmax(0), dt_init(0), lub_R0(0), lub_RT0(0), lub_RS0(0),
         beta_pair(0), nbuilds(0), pair_evals(0), steps_done(0), launches(0), list_gran_dir(0), list_type_dir(0), list_gran_img(0),
         list_type_img(0), chunk(16), last_step_ms(0), count_in_kernel(false), have_mesh(false), ncells(0), have_DDtU(false),
         have_curlU(false), have_gradp(false), drag_model(0), force_flags(SEDI_FORCE_DRAG | SEDI_FORCE_PGRAD), nub(1e-6), rhob(1000.0),
@@ -268,6 +272,7 @@ class Engine {
 
   // ---- device bring-up: no CPU fallback -------------------------------------------------------------------
   void need_device() {
+    g_comm_engine_set(this);
     if (dev_ready) { CK(cudaSetDevice(device)); return; }
     int cnt = 0;
     cudaError_t e = cudaGetDeviceCount(&cnt);
@@ -305,6 +310,7 @@ class Engine {
   void alloc_rows(int rows) {
     npad = ((rows + 127) / 128) * 128;
     if (npad < 128) npad = 128;
+    leave.ensure(npad);
     for (int k = 0; k < 2; k++) { posr[k].ensure(npad); velm[k].ensure(npad); omgt[k].ensure(npad); wmask[k].ensure(npad); foam[k].ensure(npad); }
     Plane2 *groups[] = {f, tq, fdrag, dudt, vold, uold, xhold};
     for (size_t g = 0; g < sizeof(groups) / sizeof(groups[0]); g++)
@@ -325,23 +331,48 @@ class Engine {
     if (cfg().nwalls > MAX_WALLS) fatal("Too many wall fixes");
     if (cfg().ntypes > MAX_TYPES) fatal("Too many atom types for the device cut-off table");
     if ((int)cfg().fixes.size() > MAX_FIXES) fatal("Too many fixes");
-    nlocal = (int)a.size();
-    n = nlocal;
-    if (n > (int)NB_IDX_MASK) fatal("Too many particles per GPU for the 25-bit neighbour index");
-    alloc_rows(n);
-    std::vector<D4> hp(n), hv(n), hw(n);
+    // every rank reads the whole atom table (as LAMMPS' read_data does) and keeps the atoms of its own brick
+    std::vector<D4> hp, hv, hw;
     maxtag = 0;
-    for (int i = 0; i < n; i++) {
-      hp[i].x = a.x[3 * i]; hp[i].y = a.x[3 * i + 1]; hp[i].z = a.x[3 * i + 2]; hp[i].w = a.radius[i];
-      hv[i].x = a.v[3 * i]; hv[i].y = a.v[3 * i + 1]; hv[i].z = a.v[3 * i + 2]; hv[i].w = a.rmass[i];
-      hw[i].x = a.omega[3 * i]; hw[i].y = a.omega[3 * i + 1]; hw[i].z = a.omega[3 * i + 2];
+    for (size_t i = 0; i < a.size(); i++) {
       if (a.tag[i] < 0) fatal("Negative atom tag");
+      maxtag = std::max(maxtag, a.tag[i]);
+      if (comm.nranks > 1) {
+        double xw[3] = {a.x[3 * i], a.x[3 * i + 1], a.x[3 * i + 2]};
+        for (int d = 0; d < 3; d++) if (cfg().periodic[d]) {
+          const double lo = cfg().boxlo[d], hi = cfg().boxhi[d], prd = hi - lo;
+          if (xw[d] < lo) xw[d] += prd;
+          if (xw[d] >= hi) { xw[d] -= prd; xw[d] = std::max(xw[d], lo); }
+        }
+        if (!comm.owns(cfg(), xw)) continue;
+      }
+      D4 p, v, w;
+      p.x = a.x[3 * i]; p.y = a.x[3 * i + 1]; p.z = a.x[3 * i + 2]; p.w = a.radius[i];
+      v.x = a.v[3 * i]; v.y = a.v[3 * i + 1]; v.z = a.v[3 * i + 2]; v.w = a.rmass[i];
+      w.x = a.omega[3 * i]; w.y = a.omega[3 * i + 1]; w.z = a.omega[3 * i + 2];
       if (script.mask[i] > 0xFFFF) fatal("Too many groups for the 16-bit device mask");
       const unsigned long long b = pack_bits(a.tag[i], script.mask[i], a.type[i], 0);
       long long sb = (long long)b;
-      memcpy(&hw[i].w, &sb, 8);
-      maxtag = std::max(maxtag, a.tag[i]);
+      memcpy(&w.w, &sb, 8);
+      hp.push_back(p); hv.push_back(v); hw.push_back(w);
     }
+    {
+      double mt = (double)maxtag;
+      comm.allreduce_max_host(&mt, 1);
+      maxtag = (int)mt;
+    }
+    nlocal = (int)hp.size();
+    nghost = 0;
+    n = nlocal;
+    if (n > (int)NB_IDX_MASK / 2) fatal("Too many particles per GPU for the 25-bit neighbour index");
+    // capacity: owned rows + (multi-GPU) ghost shell and migration slack
+    int rows = n;
+    if (comm.nranks > 1) {
+      const char *e = getenv("SEDI_ROW_SLACK");
+      const double slack = e ? atof(e) : 0.6;
+      rows = (int)(n * (1.0 + slack)) + 65536;
+    }
+    alloc_rows(rows);
     cur = 0; icur = 0; ecur = 0;
     ell[0].valid = ell[1].valid = false;
     if (n) {
@@ -358,6 +389,7 @@ class Engine {
     }
     tag2idx.ensure((size_t)maxtag + 2);
     CK(cudaMemsetAsync(tag2idx.p, 0xFF, tag2idx.cap * sizeof(int), stream));
+    CK(cudaMemsetAsync(leave.p, 0, leave.cap * sizeof(int), stream));
     CK(cudaStreamSynchronize(stream));  // host vectors go out of scope
     loaded = true; setup_done = false; cell_valid = false;
   }
@@ -426,8 +458,9 @@ class Engine {
       grow *= 1.3;
     }
     bin.n = n;
-    cellcount.ensure((size_t)total + 1); cellstart.ensure((size_t)total + 1); cellfill.ensure((size_t)total + 1);
-    blocksum.ensure((size_t)cdiv(total + 1, SCAN_ITEMS) + 1);
+    cellcount.ensure((size_t)total + 2); cellstart.ensure((size_t)total + 2); cellfill.ensure((size_t)total + 2);
+    blocksum.ensure((size_t)cdiv(total + 2, SCAN_ITEMS) + 1);
+    if (comm.nranks > 1) comm.setup_decomp(*this);
   }
 
   long long ncells_bin() const { return (long long)bin.nb[0] * bin.nb[1] * bin.nb[2]; }
@@ -488,7 +521,7 @@ class Engine {
   void fill_launch(StepParams &P, int mode, int in, long long ntimestep) {
     P = base;
     P.mode = mode; P.ntimestep = ntimestep;
-    P.n = n;
+    P.n = nlocal;
     Ell &L = ell[ecur];
     P.npad = L.npad; P.nn = L.nn.p; P.nbr = L.nbr.p; P.shear = L.shear.p; P.tmask = L.tmask.p;
     P.posr_in = posr[in].p; P.velm_in = velm[in].p; P.omgt_in = omgt[in].p;
@@ -517,7 +550,7 @@ class Engine {
   void launch_step(int mode, int in, long long ntimestep, int seq) {
     StepParams P;
     fill_launch(P, mode, in, ntimestep);
-    const int blocks = cdiv(n, 128);
+    const int blocks = cdiv(nlocal, 128);
     if (!blocks) return;
     const bool tl = P.has_cohesive || P.lub_enabled;
     switch (cfg().pair) {
@@ -544,7 +577,7 @@ class Engine {
   void launch_initial(int in, int seq) {
     StepParams P;
     fill_launch(P, MODE_FUSED, in, cfg().ntimestep);
-    const int blocks = cdiv(n, 256);
+    const int blocks = cdiv(nlocal, 256);
     if (!blocks) return;
     k_initial_integrate<<<blocks, 256, 0, stream>>>(P, seq);
     launches++;
@@ -553,70 +586,101 @@ class Engine {
   // ---- neighbour rebuild (EXTERNAL Verlet: pre_exchange history save, pbc, exchange, borders, Neighbor::build) ---
   void rebuild() {
     need_device();
-    if (comm.nranks > 1) comm.exchange_and_borders(*this);
-    bin.n = n;
-    const long long nc = ncells_bin();
-    const int T = 256;
-    CK(cudaMemsetAsync(cellcount.p, 0, (size_t)(nc + 1) * sizeof(int), stream));
-    CK(cudaMemsetAsync(cellfill.p, 0, (size_t)(nc + 1) * sizeof(int), stream));
     const SimConfig &c = cfg();
-    if (n) {
-      k_wrap_bin<<<cdiv(n, T), T, 0, stream>>>(posr[cur].p, omgt[cur].p, n, bin, c.boxhi[0], c.boxhi[1], c.boxhi[2], c.boxhi[0] - c.boxlo[0],
-                                               c.boxhi[1] - c.boxlo[1], c.boxhi[2] - c.boxlo[2], cellid.p, cellcount.p,
-                                               c.periodic[0], c.periodic[1], c.periodic[2], c.boxlo[0], c.boxlo[1], c.boxlo[2]);
+    const int T = 256;
+    const int n_old = nlocal + nghost;  // rows that are valid in quads[cur] (ghost rows are dropped by the sort)
+    int narr = 0;
+    if (comm.nranks > 1) narr = comm.migrate(*this);  // leavers flagged in leave[], arrivals appended at rows >= n_old
+    const int n_tmp = n_old + narr;
+    const long long nc = ncells_bin();
+    const int trash = (int)nc;                         // cell id of rows that leave the sort (ghosts, migrated-away)
+    CK(cudaMemsetAsync(cellcount.p, 0, (size_t)(nc + 2) * sizeof(int), stream));
+    CK(cudaMemsetAsync(cellfill.p, 0, (size_t)(nc + 2) * sizeof(int), stream));
+    if (n_tmp) {
+      k_wrap_bin<<<cdiv(n_tmp, T), T, 0, stream>>>(posr[cur].p, omgt[cur].p, n_tmp, bin, c.boxhi[0], c.boxhi[1], c.boxhi[2], c.boxhi[0] - c.boxlo[0],
+                                                   c.boxhi[1] - c.boxlo[1], c.boxhi[2] - c.boxlo[2], cellid.p, cellcount.p,
+                                                   c.periodic[0], c.periodic[1], c.periodic[2], c.boxlo[0], c.boxlo[1], c.boxlo[2],
+                                                   comm.nranks > 1 ? leave.p : (const int *)0, trash, comm.nranks > 1 ? 0 : 1);
     }
-    const int nscan = (int)(nc + 1);
+    const int nscan = (int)(nc + 2);
     const int nblk = cdiv(nscan, SCAN_ITEMS);
     k_scan_local<<<nblk, 1024, 0, stream>>>(cellcount.p, cellstart.p, nscan, blocksum.p);
     k_scan_sums<<<1, 1024, 0, stream>>>(blocksum.p, nblk);
     k_scan_add<<<cdiv(nscan, T), T, 0, stream>>>(cellstart.p, nscan, blocksum.p, 0);
     launches += 4;
-    if (n) {
-      k_bin_scatter<<<cdiv(n, T), T, 0, stream>>>(cellid.p, n, cellstart.p, cellfill.p, order.p);
-      k_cell_sort<<<cdiv(nc, T), T, 0, stream>>>(cellstart.p, (int)nc, n, order.p, omgt[cur].p);
+    int nlocal_new = n_tmp;
+    if (comm.nranks > 1) {  // kept rows = start of the trash cell
+      CK(cudaMemcpyAsync(h_ctrl.p + 4, cellstart.p + nc, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      nlocal_new = h_ctrl.p[4];
+    }
+    if (n_tmp) {
+      k_bin_scatter<<<cdiv(n_tmp, T), T, 0, stream>>>(cellid.p, n_tmp, cellstart.p, cellfill.p, order.p);
+      k_cell_sort<<<cdiv(nc, T), T, 0, stream>>>(cellstart.p, (int)nc, nlocal_new, order.p, omgt[cur].p);
+      launches += 2;
+    }
+    if (nlocal_new) {
       // physical re-ordering into cell order: quads cur -> cur^1, planes get() -> alt()
-      k_permute_quads<<<cdiv(n, T), T, 0, stream>>>(order.p, n, posr[cur].p, velm[cur].p, omgt[cur].p, posr[cur ^ 1].p, velm[cur ^ 1].p,
-                                                    omgt[cur ^ 1].p, xhold[0].get(), xhold[1].get(), xhold[2].get(), tag2idx.p, maxtag,
-                                                    wmask[icur].p, wmask[icur ^ 1].p, foam[icur].p, foam[icur ^ 1].p);
+      k_permute_quads<<<cdiv(nlocal_new, T), T, 0, stream>>>(order.p, nlocal_new, posr[cur].p, velm[cur].p, omgt[cur].p, posr[cur ^ 1].p,
+                                                             velm[cur ^ 1].p, omgt[cur ^ 1].p, xhold[0].get(), xhold[1].get(), xhold[2].get(),
+                                                             tag2idx.p, maxtag, wmask[icur].p, wmask[icur ^ 1].p, foam[icur].p, foam[icur ^ 1].p);
       PlaneList L;
       L.nplanes = 0;
       Plane2 *groups[] = {f, tq, fdrag, dudt, vold, uold};
       for (int g = 0; g < NPLANES_BASE; g++) for (int d = 0; d < 3; d++) { L.src[L.nplanes] = groups[g][d].get(); L.dst[L.nplanes] = groups[g][d].alt(); L.nplanes++; }
       for (int w = 0; w < c.nwalls; w++) for (int d = 0; d < 3; d++) { L.src[L.nplanes] = wshear[w][d].get(); L.dst[L.nplanes] = wshear[w][d].alt(); L.nplanes++; }
-      k_permute_planes<<<cdiv(n, T), T, 0, stream>>>(order.p, n, L);
+      k_permute_planes<<<cdiv(nlocal_new, T), T, 0, stream>>>(order.p, nlocal_new, L);
+      launches += 2;
+    }
+    {
+      Plane2 *groups[] = {f, tq, fdrag, dudt, vold, uold};
       for (int g = 0; g < NPLANES_BASE; g++) for (int d = 0; d < 3; d++) groups[g][d].cur ^= 1;
       for (int w = 0; w < c.nwalls; w++) for (int d = 0; d < 3; d++) wshear[w][d].cur ^= 1;
-      launches += 4;
     }
     const int oldq = cur;
     cur ^= 1; icur ^= 1;
+    nlocal = nlocal_new; nghost = 0; n = nlocal;
+    if (comm.nranks > 1) {
+      CK(cudaMemsetAsync(leave.p, 0, (size_t)npad * sizeof(int), stream));
+      comm.borders(*this);  // ghost rows [nlocal, nlocal + nghost) of the new buffers, binned by cell
+      n = nlocal + nghost;
+    }
+    bin.n = n;
     // directed ELL list + history re-attachment
     Ell &Lo = ell[ecur], &Ln = ell[ecur ^ 1];
+    const int npad_ell = std::max(128, ((nlocal + 127) / 128) * 128);
     BuildParams B;
     memset(&B, 0, sizeof(B));
-    B.n = n; B.want_gran = (c.pair != PAIR_NONE); B.want_type = want_type_list() ? 1 : 0; B.ntypes = c.ntypes;
+    B.n = nlocal; B.want_gran = (c.pair != PAIR_NONE); B.want_type = want_type_list() ? 1 : 0; B.ntypes = c.ntypes;
     B.posr = posr[cur].p; B.omgt = omgt[cur].p; B.cellstart = cellstart.p;
     for (int d = 0; d < 3; d++) { B.nb[d] = bin.nb[d]; B.periodic[d] = bin.periodic[d]; B.lo[d] = bin.lo[d]; B.inv[d] = bin.inv[d]; B.prd[d] = c.boxhi[d] - c.boxlo[d]; }
     B.skin = c.skin;
     memcpy(B.cutneighsq, cutneighsq, sizeof(cutneighsq));
-    B.have_old = Lo.valid ? 1 : 0; B.npad_old = Lo.npad; B.oldidx = order.p;
-    B.nbr_old = Lo.nbr.p; B.nn_old = Lo.nn.p; B.tmask_old = Lo.tmask.p; B.shear_old = Lo.shear.p; B.omgt_old = omgt[oldq].p;
+    B.have_old = (Lo.valid || narr > 0) ? 1 : 0; B.npad_old = Lo.npad; B.oldidx = order.p;
+    B.nbr_old = Lo.nbr.p; B.nn_old = Lo.valid ? Lo.nn.p : (const int *)0; B.tmask_old = Lo.tmask.p; B.shear_old = Lo.shear.p; B.omgt_old = omgt[oldq].p;
+    B.n_old = Lo.valid ? n_old : 0;
+    B.nlocal_rows = nlocal;
+    if (comm.nranks > 1) {
+      B.gcellstart = comm.d_gstart; B.gorder = comm.d_gorder;
+      if (narr > 0) { B.arr_nh = comm.d_arr_nh; B.arr_tag = comm.d_arr_tag; B.arr_shear = comm.d_arr_shear; if (!Lo.valid) B.n_old = n_old; }
+    }
     B.maxcount = ctrl.p + 3; B.npairs = counters.p;
     if (Ln.cap < 8) Ln.cap = std::max(Lo.cap, 0);
     for (int attempt = 0; attempt < 3; attempt++) {
-      Ln.npad = npad;
-      Ln.nn.ensure(npad); Ln.tmask.ensure(npad);
-      if (Ln.cap > 0) { Ln.nbr.ensure((size_t)Ln.cap * npad); Ln.shear.ensure((size_t)Ln.cap * npad); }
+      Ln.npad = npad_ell;
+      Ln.nn.ensure(npad_ell); Ln.tmask.ensure(npad_ell);
+      if (Ln.cap > 0) { Ln.nbr.ensure((size_t)Ln.cap * npad_ell); Ln.shear.ensure((size_t)Ln.cap * npad_ell); }
       B.npad = Ln.npad; B.cap = Ln.cap; B.nbr = Ln.nbr.p; B.nn = Ln.nn.p; B.tmask = Ln.tmask.p; B.shear = Ln.shear.p;
       CK(cudaMemsetAsync(ctrl.p + 3, 0, sizeof(int), stream));
       CK(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned long long), stream));
-      if (n) k_build_list<<<cdiv(n, 128), 128, 0, stream>>>(B);
+      if (nlocal) k_build_list<<<cdiv(nlocal, 128), 128, 0, stream>>>(B);
       launches++;
       CK(cudaMemcpyAsync(h_ctrl.p, ctrl.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
       CK(cudaMemcpyAsync(h_counters.p, counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
       CK(cudaStreamSynchronize(stream));
       CK(cudaGetLastError());
-      const int maxrow = h_ctrl.p[3];
+      int maxrow = h_ctrl.p[3];
+      if (comm.nranks > 1) { double m = maxrow; comm.allreduce_max_host(&m, 1); maxrow = (int)m; }  // same capacity decision on every rank
       if (maxrow <= Ln.cap) break;
       if (maxrow > MAX_SLOTS) fatal("Neighbour row longer than 64 entries: reduce the skin / cut-off (contact-history mask is 64 bits)");
       Ln.cap = std::min(MAX_SLOTS, ((maxrow + 2 + 3) / 4) * 4);
@@ -680,12 +744,14 @@ class Engine {
       CK(cudaMemsetAsync(ctrl.p, 0, 2 * sizeof(int), stream));
       const int K = (int)std::min<long long>(remaining, chunk);
       int seq = 0, in = cur, nk = 0;
-      if (pending_initial) { launch_initial(in, ++seq); in ^= 1; nk++; }
+      const bool mg = comm.nranks > 1;
+      if (pending_initial) { launch_initial(in, ++seq); in ^= 1; nk++; if (mg) comm.forward(*this, in, true); }
       if (prof_on) CK(cudaEventRecord(evk0, stream));
       for (int s = 0; s < K; s++) {
         const bool last = (remaining - s == 1);
         launch_step(last ? MODE_LAST : MODE_FUSED, in, cfg().ntimestep + s + 1, ++seq);
         in ^= 1;
+        if (mg && !last) comm.forward(*this, in, true);  // ghost x, v, omega of the new positions + rebuild consensus
       }
       if (prof_on) CK(cudaEventRecord(evk1, stream));
       CK(cudaMemcpyAsync(h_ctrl.p, ctrl.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -802,6 +868,7 @@ class Engine {
     if (!setup_done) setup();
     need_device();
     Ell &L = ell[ecur];
+    const int n = nlocal;
     std::vector<int> hn(n), rs(n + 1, 0);
     if (n) CK(cudaMemcpyAsync(hn.data(), L.nn.p, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
@@ -884,7 +951,7 @@ class Engine {
     if (!have_mesh) fatal("sedi_locate: call sedi_mesh_box first");
     if (!loaded) load_atoms();
     need_device();
-    if (n) k_locate_cells<<<cdiv(n, 256), 256, 0, stream>>>(posr[cur].p, n, mesh, cell.p);
+    if (nlocal) k_locate_cells<<<cdiv(nlocal, 256), 256, 0, stream>>>(posr[cur].p, nlocal, mesh, cell.p);
     launches++;
     cell_valid = true;
   }
@@ -1015,6 +1082,7 @@ class Engine {
 }  // namespace sedi
 
 #include "sedi_comm_impl.cuh"
+namespace sedi { static void g_comm_engine_set(Engine *e) { g_comm_engine = e; } }
 
 // =====================================================================================================================
 // C-ABI
@@ -1178,5 +1246,18 @@ int sedi_comm_init(void *ptr, int rank, int nranks, const void *nccl_unique_id, 
   return E(ptr)->comm.init(*E(ptr), rank, nranks, nccl_unique_id, id_bytes, procgrid);
 }
 int sedi_comm_unique_id(void *out, int cap) { return sedi::Comm::unique_id(out, cap); }
+int sedi_comm_rank(void *ptr) { return E(ptr)->comm.rank; }
+long long sedi_comm_stat(void *ptr, int which) {
+  Engine *e = E(ptr);
+  switch (which) { case 0: return e->comm.halo_calls; case 1: return e->comm.total_send; case 2: return e->comm.total_recv; case 3: return (long long)e->comm.links.size(); case 4: return e->comm.narr_last; default: return -1; }
+}
+/* pure host logic of the brick decomposition (no GPU, no NCCL): used by the CPU tests */
+void sedi_decomp_grid(int nranks, const double *boxlen, int *grid) { sedi::decomp_auto_grid(nranks, boxlen, grid); }
+int sedi_decomp_owner(const double *x, const double *boxlo, const double *boxhi, const int *grid) { return sedi::decomp_owner(x, boxlo, boxhi, grid); }
+int sedi_decomp_links(int rank, const int *grid, const int *periodic, const double *prd, int *peers, int *offsets, double *shifts) {
+  std::vector<sedi::LinkHost> l = sedi::decomp_links(rank, grid, periodic, prd);
+  for (size_t k = 0; k < l.size(); k++) { peers[k] = l[k].peer; for (int d = 0; d < 3; d++) { offsets[3 * k + d] = l[k].off[d]; shifts[3 * k + d] = l[k].shift[d]; } }
+  return (int)l.size();
+}
 
 }  // extern "C"

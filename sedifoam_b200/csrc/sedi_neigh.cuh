@@ -37,6 +37,11 @@ struct BuildParams {
   const unsigned long long *tmask_old;
   const D4 *shear_old;
   const D4 *omgt_old;
+  int nlocal_rows;               // first ghost row (ghost partners are reached through gorder)
+  const int *gcellstart, *gorder;  // ghost rows binned by cell (null on a single GPU)
+  int n_old;                     // rows of the old arrays; oldidx >= n_old marks a particle that migrated in
+  const int *arr_nh, *arr_tag;   // history carried by migrated particles
+  const D4 *arr_shear;
   int *maxcount;                 // [0] max row length found
   unsigned long long *npairs;    // directed entries: [0] granular, [1] type list, [2] granular periodic-image, [3] type periodic-image
 };
@@ -50,12 +55,18 @@ __device__ __forceinline__ int bin_coord(double x, double lo, double inv, int nb
 // B describes the bins (which cover the local sub-domain plus its ghost shell on a multi-GPU run).
 __global__ void k_wrap_bin(D4 *posr, const D4 *omgt, int n, BinParams B, double hi0, double hi1, double hi2, double prd0,
                            double prd1, double prd2, int *cellid, int *cellcount, int per0, int per1, int per2, double blo0,
-                           double blo1, double blo2) {
+                           double blo1, double blo2, const int *leave, int trash_cell, int do_wrap) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   D4 p = posr[i];
   const unsigned long long b = (unsigned long long)__double_as_longlong(omgt[i].w);
-  if (!(bits_flags(b) & PFLAG_GHOST)) {
+  const bool ghost = (bits_flags(b) & PFLAG_GHOST) != 0;
+  if (trash_cell >= 0 && (ghost || (leave && leave[i]))) {  // stale ghost rows and migrated-away rows drop out of the sort
+    cellid[i] = trash_cell;
+    atomicAdd(&cellcount[trash_cell], 1);
+    return;
+  }
+  if (!ghost && do_wrap) {
     bool ch = false;
     if (per0) { if (p.x < blo0) { p.x += prd0; ch = true; } if (p.x >= hi0) { p.x -= prd0; p.x = fmax(p.x, blo0); ch = true; } }
     if (per1) { if (p.y < blo1) { p.y += prd1; ch = true; } if (p.y >= hi1) { p.y -= prd1; p.y = fmax(p.y, blo1); ch = true; } }
@@ -187,10 +198,55 @@ __global__ void __launch_bounds__(128) k_build_list(const __grid_constant__ Buil
       const int cx = bin_coord(pi.x, B.lo[0], B.inv[0], B.nb[0]);
       const int cy = bin_coord(pi.y, B.lo[1], B.inv[1], B.nb[1]);
       const int cz = bin_coord(pi.z, B.lo[2], B.inv[2], B.nb[2]);
-      const int orow = B.have_old ? B.oldidx[i] : -1;
+      const int orow_raw = B.have_old ? B.oldidx[i] : -1;
+      const int arrk = (orow_raw >= B.n_old && B.arr_nh) ? orow_raw - B.n_old : -1;  // migrated in at this rebuild
+      const int orow = (B.nn_old && orow_raw >= 0 && orow_raw < B.n_old) ? orow_raw : -1;
       const int nno = (orow >= 0) ? B.nn_old[orow] : 0;
       const unsigned long long tmo = (orow >= 0) ? B.tmask_old[orow] : 0ull;
+      const int narrh = (arrk >= 0) ? B.arr_nh[arrk] : 0;
       unsigned long long tm = 0ull;
+      auto visit = [&](const int j, const int img, const int ix, const int iy, const int iz) {
+        if (j == i && img == NB_IMG_NONE) return;
+        D4 pj = B.posr[j];
+        if (img != NB_IMG_NONE) { pj.x = pj.x + ix * B.prd[0]; pj.y = pj.y + iy * B.prd[1]; pj.z = pj.z + iz * B.prd[2]; }
+        const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
+        const double rsq = delx * delx + dely * dely + delz * delz;
+        const double radsum = radi + pj.w;
+        unsigned flags = 0;
+        if (B.want_gran) { const double cs = (radsum + B.skin) * (radsum + B.skin); if (rsq <= cs) flags |= NB_FLAG_GRAN; }
+        if (B.want_type) {
+          const int tj = bits_type((unsigned long long)__double_as_longlong(B.omgt[j].w));
+          if (rsq <= B.cutneighsq[ti * (MAX_TYPES + 1) + tj]) flags |= NB_FLAG_TYPE;
+        }
+        if (!flags) return;
+        // LAMMPS stores an owned-ghost pair in both owners' lists; a periodic image inside one GPU is the same thing
+        const bool isimg = (img != NB_IMG_NONE) || (j >= B.nlocal_rows);
+        if (flags & NB_FLAG_GRAN) { ng++; if (isimg) ngi++; }
+        if (flags & NB_FLAG_TYPE) { nt++; if (isimg) nti++; }
+        if (cnt < B.cap) {
+          const size_t slot = (size_t)cnt * B.npad + i;
+          B.nbr[slot] = (unsigned)j | ((unsigned)img << NB_IMG_SHIFT) | flags;
+          if ((flags & NB_FLAG_GRAN) && rsq < radsum * radsum) {
+            const int tagj = bits_tag((unsigned long long)__double_as_longlong(B.omgt[j].w));
+            if (tmo) {
+              for (int so = 0; so < nno; so++) {
+                if (!((tmo >> so) & 1ull)) continue;
+                const size_t oslot = (size_t)so * B.npad_old + orow;
+                const int jo = (int)(B.nbr_old[oslot] & NB_IDX_MASK);
+                if (bits_tag((unsigned long long)__double_as_longlong(B.omgt_old[jo].w)) == tagj) {
+                  B.shear[slot] = B.shear_old[oslot];
+                  tm |= (1ull << cnt);
+                  break;
+                }
+              }
+            }
+            for (int m = 0; m < narrh; m++) {
+              if (B.arr_tag[arrk * 16 + m] == tagj) { B.shear[slot] = B.arr_shear[arrk * 16 + m]; tm |= (1ull << cnt); break; }
+            }
+          }
+        }
+        cnt++;
+      };
       for (int dz = -1; dz <= 1; dz++) {
         int bz = cz + dz, iz = 0;
         if (bz < 0) { if (!B.periodic[2]) continue; bz += B.nb[2]; iz = -1; }
@@ -204,42 +260,12 @@ __global__ void __launch_bounds__(128) k_build_list(const __grid_constant__ Buil
             if (bx < 0) { if (!B.periodic[0]) continue; bx += B.nb[0]; ix = -1; }
             else if (bx >= B.nb[0]) { if (!B.periodic[0]) continue; bx -= B.nb[0]; ix = 1; }
             const int c = bx + B.nb[0] * (by + B.nb[1] * bz);
-            const int js = B.cellstart[c], je = B.cellstart[c + 1];
             const int img = (ix + 1) + 3 * (iy + 1) + 9 * (iz + 1);
-            for (int j = js; j < je; j++) {
-              if (j == i && img == NB_IMG_NONE) continue;
-              D4 pj = B.posr[j];
-              if (img != NB_IMG_NONE) { pj.x = pj.x + ix * B.prd[0]; pj.y = pj.y + iy * B.prd[1]; pj.z = pj.z + iz * B.prd[2]; }
-              const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
-              const double rsq = delx * delx + dely * dely + delz * delz;
-              const double radsum = radi + pj.w;
-              unsigned flags = 0;
-              if (B.want_gran) { const double cs = (radsum + B.skin) * (radsum + B.skin); if (rsq <= cs) flags |= NB_FLAG_GRAN; }
-              if (B.want_type) {
-                const int tj = bits_type((unsigned long long)__double_as_longlong(B.omgt[j].w));
-                if (rsq <= B.cutneighsq[ti * (MAX_TYPES + 1) + tj]) flags |= NB_FLAG_TYPE;
-              }
-              if (!flags) continue;
-              if (flags & NB_FLAG_GRAN) { ng++; if (img != NB_IMG_NONE) ngi++; }
-              if (flags & NB_FLAG_TYPE) { nt++; if (img != NB_IMG_NONE) nti++; }
-              if (cnt < B.cap) {
-                const size_t slot = (size_t)cnt * B.npad + i;
-                B.nbr[slot] = (unsigned)j | ((unsigned)img << NB_IMG_SHIFT) | flags;
-                if ((flags & NB_FLAG_GRAN) && B.have_old && rsq < radsum * radsum && tmo) {
-                  const int tagj = bits_tag((unsigned long long)__double_as_longlong(B.omgt[j].w));
-                  for (int so = 0; so < nno; so++) {
-                    if (!((tmo >> so) & 1ull)) continue;
-                    const size_t oslot = (size_t)so * B.npad_old + orow;
-                    const int jo = (int)(B.nbr_old[oslot] & NB_IDX_MASK);
-                    if (bits_tag((unsigned long long)__double_as_longlong(B.omgt_old[jo].w)) == tagj) {
-                      B.shear[slot] = B.shear_old[oslot];
-                      tm |= (1ull << cnt);
-                      break;
-                    }
-                  }
-                }
-              }
-              cnt++;
+            const int js = B.cellstart[c], je = B.cellstart[c + 1];
+            for (int j = js; j < je; j++) visit(j, img, ix, iy, iz);
+            if (B.gcellstart) {
+              const int gs = B.gcellstart[c], ge = B.gcellstart[c + 1];
+              for (int k = gs; k < ge; k++) visit(B.nlocal_rows + B.gorder[k], img, ix, iy, iz);
             }
           }
         }

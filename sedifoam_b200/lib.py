@@ -25,7 +25,8 @@ EXPORTED_SYMBOLS = [
     "sedi_synchronize", "sedi_stream", "sedi_last_step_ms", "sedi_timer_start", "sedi_timer_stop_ms", "sedi_profile",
     "sedi_get_profile", "sedi_mesh_box", "sedi_mesh_ncells", "sedi_coupling_config",
     "sedi_put_cell_fields", "sedi_locate", "sedi_compute_fluid_force", "sedi_scatter_alpha_u", "sedi_calc_tc",
-    "sedi_enable_diag", "sedi_get_coupling_diag", "sedi_step", "sedi_comm_init", "sedi_comm_unique_id",
+    "sedi_enable_diag", "sedi_get_coupling_diag", "sedi_step", "sedi_comm_init", "sedi_comm_unique_id", "sedi_comm_rank", "sedi_comm_stat",
+    "sedi_decomp_grid", "sedi_decomp_owner", "sedi_decomp_links",
 ]
 
 
@@ -114,6 +115,11 @@ def load_library():
         "sedi_step": (None, [vp, i]),
         "sedi_comm_init": (i, [vp, i, i, vp, i, vp]),
         "sedi_comm_unique_id": (i, [vp, i]),
+        "sedi_comm_rank": (i, [vp]),
+        "sedi_comm_stat": (ll, [vp, i]),
+        "sedi_decomp_grid": (None, [i, vp, vp]),
+        "sedi_decomp_owner": (i, [vp, vp, vp, vp]),
+        "sedi_decomp_links": (i, [i, vp, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -372,3 +378,41 @@ class Lammps:
 
     def sedi_step(self, n):
         self.lib.sedi_step(self.h, int(n))
+
+    # ---- multi-GPU ---------------------------------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """ncclUniqueId bytes (call on rank 0, broadcast to the others)"""
+        buf = (C.c_char * 256)()
+        nb = load_library().sedi_comm_unique_id(C.cast(buf, C.c_void_p), 256)
+        if nb <= 0:
+            raise RuntimeError("NCCL is not available to libsedi_b200.so")
+        return bytes(buf[:nb])
+
+    def comm_init(self, rank, nranks, uid, procgrid=None):
+        pg = None if procgrid is None else _i32(procgrid)
+        b = C.create_string_buffer(uid, len(uid))
+        self.lib.sedi_comm_init(self.h, int(rank), int(nranks), C.cast(b, C.c_void_p), len(uid), _vp(pg))
+
+    def comm_stat(self, name):
+        return int(self.lib.sedi_comm_stat(self.h, {"halo_calls": 0, "send_rows": 1, "ghost_rows": 2, "links": 3, "arrivals": 4}[name]))
+
+
+def decomp_grid(nranks, boxlen):
+    g = np.zeros(3, np.int32)
+    bl = _f64(boxlen)
+    load_library().sedi_decomp_grid(int(nranks), _vp(bl), _vp(g))
+    return g
+
+
+def decomp_owner(x, boxlo, boxhi, grid):
+    lib = load_library()
+    x = _f64(x).reshape(-1, 3); lo = _f64(boxlo); hi = _f64(boxhi); g = _i32(grid)
+    return np.array([lib.sedi_decomp_owner(_vp(x[k]), _vp(lo), _vp(hi), _vp(g)) for k in range(len(x))], np.int32)
+
+
+def decomp_links(rank, grid, periodic, prd):
+    peers = np.zeros(26, np.int32); offs = np.zeros((26, 3), np.int32); sh = np.zeros((26, 3))
+    g = _i32(grid); per = _i32(periodic); p = _f64(prd)
+    n = load_library().sedi_decomp_links(int(rank), _vp(g), _vp(per), _vp(p), _vp(peers), _vp(offs), _vp(sh))
+    return peers[:n], offs[:n], sh[:n]
