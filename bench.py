@@ -166,7 +166,7 @@ def main():
     config = {"workload": "configs[2]: %d-particle fluidized bed per GPU, gran/hertzFix/history + wall/granFix + fdrag(ErgunWenYu), "
                           "%d DEM sub-steps per coupling step" % (int(np.prod(dims)), S),
               "particles_per_gpu": int(np.prod(dims)), "substeps_per_step": S, "dt_dem": 2e-6, "skin_over_d": 0.25,
-              "decomposition": "1 GPU" if world == 1 else "%d bricks" % world}
+              "decomposition": "1 GPU" if world == 1 else "%d bricks, NCCL ghost halo every sub-step" % world}
 
     if args.impl == "reference":
         if rank != 0:
@@ -224,10 +224,22 @@ def main():
         return float(t.item())
 
     log("generating case")
-    case = cases.fluidized_bed(dims=dims, seed=cases.SEED + rank)
+    # weak scaling: every GPU owns one `dims` brick of a bed that grows in x and z (the bed's free surface stays in y)
+    pg = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 1, 2), 8: (4, 1, 2)}.get(world)
+    if pg is None:
+        print("bench.py: --gpus must be 1, 2, 4 or 8", file=sys.stderr)
+        return 2
+    cx, cz = rank % pg[0], rank // (pg[0] * pg[1])
+    gdims = (dims[0] * pg[0], dims[1], dims[2] * pg[2])
+    block = (cx * dims[0], (cx + 1) * dims[0], 0, dims[1], cz * dims[2], (cz + 1) * dims[2])
+    case = cases.fluidized_bed(dims=gdims, seed=cases.SEED + rank, block=block if world > 1 else None)
     n = len(case["tag"])
     eng = sb.Lammps(device=local_rank)
     cases.apply(case, eng)
+    if world > 1:
+        uid = [sb.Lammps.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.comm_init(rank, world, uid[0], pg)
     eng.mesh_box(case["mesh_lo"], case["mesh_hi"], case["mesh_n"])
     eng.coupling_config(sb.DRAG_ERGUN_WENYU, sb.FORCE_DRAG | sb.FORCE_PGRAD, case["nub"], case["rhob"], case["g"], S * case["dt"])
     Uf, gamma, gradp = cases.uniform_fields(case)
@@ -261,7 +273,7 @@ def main():
     eng.synchronize(); barrier()
     wall = time.perf_counter() - t0
     ms = allmax(max(ms_dev, 0.0))
-    evals = eng.stat("pair_evals"); launches = eng.stat("launches"); nbuilds = eng.stat("nbuilds")
+    evals = eng.stat("pair_evals_unique"); launches = eng.stat("launches"); nbuilds = eng.stat("nbuilds")
     ksteps, kms = eng.get_profile()
     eng.profile(False)
     pairs_now = eng.stat("gran_pairs")
@@ -269,15 +281,16 @@ def main():
     value = tot_evals / (ms * 1e-3) / 1e6
 
     # ---- e2e through the reference boundary with host buffers
-    fd = np.zeros((n, 3)); tags = case["tag"].copy()
-    xh = np.zeros((n, 3)); vh = np.zeros((n, 3)); foam = np.zeros(n, np.int32); lmp = np.zeros(n, np.int32); tg = np.zeros(n, np.int32)
-    m = case["rho"] * np.pi / 6.0 * case["diam"] ** 3
-    fd[:, 1] = 0.3 * 9.8 * m
+    m1 = float(case["rho"][0] * np.pi / 6.0 * case["diam"][0] ** 3)
+    state = {"loc": eng.get_local_info()}
 
     def e2e_step():
-        eng.put_local_info(fd, tags, foam_cpu=foam)
+        loc = state["loc"]                      # host arrays of the previous step (tags of the particles this rank owns)
+        nl = len(loc["tag"])
+        fd = np.zeros((nl, 3)); fd[:, 1] = 0.3 * 9.8 * m1    # the host-side fluid force for exactly those particles
+        eng.put_local_info(fd, loc["tag"], foam_cpu=loc["foamCpuId"])
         eng.step(S)
-        eng.get_local_info(xh, vh, foam, lmp, tg)
+        state["loc"] = eng.get_local_info()     # x, v, ids back on the host
 
     e2e_step()
     eng.reset_stats()
@@ -289,10 +302,10 @@ def main():
     e2e_s = allmax(time.perf_counter() - t1)
     barrier()
     log("e2e region done: %.3f s" % e2e_s)
-    e2e_evals = allsum(float(eng.stat("pair_evals")))
+    e2e_evals = allsum(float(eng.stat("pair_evals_unique")))
     e2e_value = e2e_evals / e2e_s / 1e6
-    h2d = n * (24 + 4 + 4)
-    d2h = n * (24 + 24 + 4 + 4)
+    h2d = int(allsum(float(n))) * (24 + 4 + 4)
+    d2h = int(allsum(float(n))) * (24 + 24 + 4 + 4)
     if rank == 0:
         sampler.stop()
 
@@ -324,7 +337,7 @@ def main():
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
 
     if rank == 0:
-        config.update({"pairs_per_particle": pairs_now / n, "neighbor_rebuilds_in_timed_region": nbuilds,
+        config.update({"pairs_per_particle": pairs_now / n, "ghost_rows_rank0": eng.stat("nghost"), "neighbor_rebuilds_in_timed_region": nbuilds,
                        "l2": "per-step working set (2x96 B state + list + history > 300 MB at 1e6 particles) exceeds the 126 MB L2; no flush needed",
                        "solid_fraction": float(np.pi / 6 / (1 - 2e-3) ** 3)})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,

@@ -70,7 +70,9 @@ long long sedi_get_pairs(void *ptr, int *tag_i, int *tag_j, unsigned *meta, int 
 void sedi_get_wall_shear(void *ptr, int wall, double *shear /* [n][3], device order */);
 void sedi_force_rebuild(void *ptr);
 /* which: 0 neighbour rebuilds, 1 undirected granular pair evaluations, 2 DEM steps, 3 directed granular entries,
- *        4 directed type-list entries, 5 ELL row capacity, 6 kernel launches issued, 7 local particle count */
+ *        4 directed type-list entries, 5 ELL row capacity, 6 kernel launches issued, 7 local particle count,
+ *        8 undirected granular list size as LAMMPS counts it (owned-ghost pairs stored by both owners), 9 ghost rows,
+ *        10 pair evaluations counted once per undirected pair system-wide (directed entries / 2, summed over steps) */
 long long sedi_get_stat(void *ptr, int which);
 void sedi_reset_stats(void *ptr);
 void sedi_synchronize(void *ptr);

@@ -11,22 +11,26 @@ import numpy as np
 SEED = 20261017
 
 
-def lattice(dims, spacing, origin, jitter, rng):
+def lattice(dims, spacing, origin, jitter, rng, block=None):
+    """simple-cubic lattice sites; block = (i0, i1, j0, j1, k0, k1) restricts to a sub-lattice of the global one
+    (multi-GPU: every rank generates only its own brick).  Returns positions and global 1-based lattice tags."""
     nx, ny, nz = dims
-    ix, iy, iz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    i0, i1, j0, j1, k0, k1 = (0, nx, 0, ny, 0, nz) if block is None else block
+    ix, iy, iz = np.meshgrid(np.arange(i0, i1), np.arange(j0, j1), np.arange(k0, k1), indexing="ij")
+    tags = (ix.ravel().astype(np.int64) * ny + iy.ravel()) * nz + iz.ravel() + 1
     x = np.stack([ix.ravel(), iy.ravel(), iz.ravel()], axis=1).astype(np.float64)
     x = np.asarray(origin, np.float64) + (x + 0.5) * np.asarray(spacing, np.float64)
     if jitter:
         x += rng.uniform(-jitter, jitter, size=x.shape)
-    return x
+    return x, tags.astype(np.int32)
 
 
-def _base(x, d, rho, box_lo, box_hi, periodic, script, mesh_cell, typ=None, v=None, ntypes=1, extra=None):
+def _base(x, d, rho, box_lo, box_hi, periodic, script, mesh_cell, typ=None, v=None, ntypes=1, extra=None, tags=None):
     n = len(x)
     d = np.full(n, d, np.float64) if np.isscalar(d) else np.asarray(d, np.float64)
     case = dict(
         box_lo=np.asarray(box_lo, np.float64), box_hi=np.asarray(box_hi, np.float64), periodic=periodic, ntypes=ntypes,
-        tag=np.arange(1, n + 1, dtype=np.int32), type=np.ones(n, np.int32) if typ is None else np.asarray(typ, np.int32),
+        tag=np.arange(1, n + 1, dtype=np.int32) if tags is None else tags, type=np.ones(n, np.int32) if typ is None else np.asarray(typ, np.int32),
         diam=d, rho=np.full(n, rho, np.float64), x=np.ascontiguousarray(x), v=np.zeros((n, 3)) if v is None else v,
         script=script,
     )
@@ -51,7 +55,7 @@ def apply(case, sim):
 
 
 def fluidized_bed(dims=(100, 100, 100), d=5.0e-4, rho=2650.0, overlap=2.0e-3, skin_frac=0.25, dt=2.0e-6, kn=1.0e7, e=0.9,
-                  mu=0.4, head=0.5, seed=SEED, jitter_frac=1.0e-3, vjit=1.0e-3):
+                  mu=0.4, head=0.5, seed=SEED, jitter_frac=1.0e-3, vjit=1.0e-3, block=None):
     """configs[2]: dense bed -- jittered simple-cubic lattice with every particle in (slightly pre-compressed,
     overlap*d) contact with its 6 lattice neighbours and the walls, solid fraction pi/6/(1-overlap)^3 = 0.527 -- in a
     box with granular walls on all sides and free head-room on top; Hertz-Mindlin pair + wall/granFix + gravity +
@@ -62,7 +66,7 @@ def fluidized_bed(dims=(100, 100, 100), d=5.0e-4, rho=2650.0, overlap=2.0e-3, sk
     lo = np.zeros(3)
     hi = ext.copy()
     hi[1] = ext[1] * (1.0 + head)
-    x = lattice(dims, (a, a, a), lo, jitter_frac * d, rng)
+    x, tags = lattice(dims, (a, a, a), lo, jitter_frac * d, rng, block)
     v = rng.uniform(-vjit, vjit, size=x.shape)
     script = f"""
 neighbor {skin_frac * d:.9g} bin
@@ -77,7 +81,7 @@ fix xw all wall/granFix {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 xplane {lo[0]:.17g
 fix yw all wall/granFix {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 yplane {lo[1]:.17g} {hi[1]:.17g}
 fix zw all wall/granFix {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 zplane {lo[2]:.17g} {hi[2]:.17g}
 """
-    return _base(x, d, rho, lo, hi, ("f", "f", "f"), script, 4.0 * d, v=v,
+    return _base(x, d, rho, lo, hi, ("f", "f", "f"), script, 4.0 * d, v=v, tags=tags,
                  extra=dict(name="fluidized_bed", Uf=(0.0, 0.02, 0.0), g=(0.0, -9.8, 0.0), dt=dt, substeps=100))
 
 
@@ -89,7 +93,7 @@ def sediment_column(dims=(36, 103, 27), d=5.0e-4, rho=2650.0, phi=0.30, skin_fra
     ext = np.array(dims, np.float64) * a
     lo = np.zeros(3)
     hi = ext.copy()
-    x = lattice(dims, (a, a, a), lo, jitter_frac * d, rng)
+    x, _ = lattice(dims, (a, a, a), lo, jitter_frac * d, rng)
     script = f"""
 neighbor {skin_frac * d:.9g} bin
 neigh_modify delay 0
@@ -113,7 +117,7 @@ def cohesive_shear_bed(dims=(40, 20, 40), d=5.0e-5, rho=2650.0, phi=0.55, dt=2.0
     ext = np.array(dims, np.float64) * a
     lo = np.zeros(3)
     hi = ext.copy()
-    x = lattice(dims, (a, a, a), lo, jitter_frac * d, rng)
+    x, _ = lattice(dims, (a, a, a), lo, jitter_frac * d, rng)
     smax = 1.0e-6
     skin = max(0.25 * d, 2.0 * smax)
     script = f"""
@@ -147,7 +151,7 @@ def poly_lubricated(dims=(20, 20, 20), dmin=3.0e-4, dmax=7.0e-4, rho=2650.0, phi
     ext = np.array(dims, np.float64) * a
     lo = np.zeros(3)
     hi = ext.copy()
-    x = lattice(dims, (a, a, a), lo, 0.02 * dmin, rng)
+    x, _ = lattice(dims, (a, a, a), lo, 0.02 * dmin, rng)
     v = rng.uniform(-vjit, vjit, size=x.shape)
     skin = 0.1 * dmin
     script = f"""

@@ -206,6 +206,7 @@ class Engine {
   double beta_pair;
   StepParams base;
   // stats
+  long long pair_evals_unique;
   long long nbuilds, pair_evals, steps_done, launches, list_gran_dir, list_type_dir, list_gran_img, list_type_img;
   int chunk;
   double last_step_ms;
@@ -231,7 +232,7 @@ class Engine {
   Engine()
       : device(0), dev_ready(false), loaded(false), setup_done(false), params_dirty(true), cell_valid(false), stream(0), n(0),
         nlocal(0), nghost(0), npad(0), maxtag(0), cur(0), icur(0), ecur(0), cutneighmax(0), dt_init(0), lub_R0(0), lub_RT0(0), lub_RS0(0),
-        beta_pair(0), nbuilds(0), pair_evals(0), steps_done(0), launches(0), list_gran_dir(0), list_type_dir(0), list_gran_img(0),
+        beta_pair(0), pair_evals_unique(0), nbuilds(0), pair_evals(0), steps_done(0), launches(0), list_gran_dir(0), list_type_dir(0), list_gran_img(0),
         list_type_img(0), chunk(16), last_step_ms(0), count_in_kernel(false), have_mesh(false), ncells(0), have_DDtU(false),
         have_curlU(false), have_gradp(false), drag_model(0), force_flags(SEDI_FORCE_DRAG | SEDI_FORCE_PGRAD), nub(1e-6), rhob(1000.0),
         deltaT(1.0), want_diag(false), prof_on(false), prof_ms(0), prof_steps(0) {
@@ -766,6 +767,7 @@ class Engine {
       if (h_ctrl.p[2]) fatal("Device-side error flag raised during the DEM step");
       if ((nk + done) & 1) cur ^= 1;
       pair_evals += (long long)done * list_pairs_undirected();
+      pair_evals_unique += (long long)done * list_gran_dir;  // halves: every undirected pair has two directed entries system-wide
       steps_done += done;
       remaining -= done;
       cfg().ntimestep += done;
@@ -1201,10 +1203,11 @@ long long sedi_get_stat(void *ptr, int which) {
     case 7: return e->nlocal;
     case 8: return e->list_pairs_undirected();
     case 9: return e->n - e->nlocal;
+    case 10: return e->pair_evals_unique / 2;
     default: return -1;
   }
 }
-void sedi_reset_stats(void *ptr) { Engine *e = E(ptr); e->nbuilds = e->pair_evals = e->steps_done = e->launches = 0; }
+void sedi_reset_stats(void *ptr) { Engine *e = E(ptr); e->nbuilds = e->pair_evals = e->steps_done = e->launches = e->pair_evals_unique = 0; }
 void sedi_synchronize(void *ptr) { Engine *e = E(ptr); if (e->dev_ready) { CK(cudaSetDevice(e->device)); CK(cudaStreamSynchronize(e->stream)); } }
 void *sedi_stream(void *ptr) { Engine *e = E(ptr); e->need_device(); return (void *)e->stream; }
 double sedi_last_step_ms(void *ptr) { return E(ptr)->last_step_ms; }

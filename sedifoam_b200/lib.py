@@ -139,7 +139,7 @@ def _i32(a):
 
 
 _STATS = {"nbuilds": 0, "pair_evals": 1, "steps": 2, "gran_entries": 3, "type_entries": 4, "ell_cap": 5, "launches": 6,
-          "nlocal": 7, "gran_pairs": 8, "nghost": 9}
+          "nlocal": 7, "gran_pairs": 8, "nghost": 9, "pair_evals_unique": 10}
 
 
 class Lammps:
