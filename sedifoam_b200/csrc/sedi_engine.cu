@@ -551,25 +551,26 @@ class Engine {
   void launch_step(int mode, int in, long long ntimestep, int seq) {
     StepParams P;
     fill_launch(P, mode, in, ntimestep);
-    const int blocks = cdiv(nlocal, 128);
+    const int KT = SEDI_KSTEP_THREADS;
+    const int blocks = cdiv(nlocal, KT);
     if (!blocks) return;
     const bool tl = P.has_cohesive || P.lub_enabled;
     switch (cfg().pair) {
       case PAIR_HERTZFIX_HISTORY:
-        if (tl) k_step<PAIR_HERTZFIX_HISTORY, true><<<blocks, 128, 0, stream>>>(P, seq);
-        else k_step<PAIR_HERTZFIX_HISTORY, false><<<blocks, 128, 0, stream>>>(P, seq);
+        if (tl) k_step<PAIR_HERTZFIX_HISTORY, true><<<blocks, KT, 0, stream>>>(P, seq);
+        else k_step<PAIR_HERTZFIX_HISTORY, false><<<blocks, KT, 0, stream>>>(P, seq);
         break;
       case PAIR_HOOKE_HISTORY:
-        if (tl) k_step<PAIR_HOOKE_HISTORY, true><<<blocks, 128, 0, stream>>>(P, seq);
-        else k_step<PAIR_HOOKE_HISTORY, false><<<blocks, 128, 0, stream>>>(P, seq);
+        if (tl) k_step<PAIR_HOOKE_HISTORY, true><<<blocks, KT, 0, stream>>>(P, seq);
+        else k_step<PAIR_HOOKE_HISTORY, false><<<blocks, KT, 0, stream>>>(P, seq);
         break;
       case PAIR_HOOKE:
-        if (tl) k_step<PAIR_HOOKE, true><<<blocks, 128, 0, stream>>>(P, seq);
-        else k_step<PAIR_HOOKE, false><<<blocks, 128, 0, stream>>>(P, seq);
+        if (tl) k_step<PAIR_HOOKE, true><<<blocks, KT, 0, stream>>>(P, seq);
+        else k_step<PAIR_HOOKE, false><<<blocks, KT, 0, stream>>>(P, seq);
         break;
       default:
-        if (tl) k_step<PAIR_NONE, true><<<blocks, 128, 0, stream>>>(P, seq);
-        else k_step<PAIR_NONE, false><<<blocks, 128, 0, stream>>>(P, seq);
+        if (tl) k_step<PAIR_NONE, true><<<blocks, KT, 0, stream>>>(P, seq);
+        else k_step<PAIR_NONE, false><<<blocks, KT, 0, stream>>>(P, seq);
         break;
     }
     launches++;
@@ -666,7 +667,7 @@ class Engine {
       if (narr > 0) { B.arr_nh = comm.d_arr_nh; B.arr_tag = comm.d_arr_tag; B.arr_shear = comm.d_arr_shear; if (!Lo.valid) B.n_old = n_old; }
     }
     B.maxcount = ctrl.p + 3; B.npairs = counters.p;
-    if (Ln.cap < 8) Ln.cap = std::max(Lo.cap, 0);
+    if (Ln.cap < 8) Ln.cap = std::max(Lo.cap, 8);   // k_step reads the first eight list words of every row unconditionally
     for (int attempt = 0; attempt < 3; attempt++) {
       Ln.npad = npad_ell;
       Ln.nn.ensure(npad_ell); Ln.tmask.ensure(npad_ell);
@@ -684,7 +685,7 @@ class Engine {
       if (comm.nranks > 1) { double m = maxrow; comm.allreduce_max_host(&m, 1); maxrow = (int)m; }  // same capacity decision on every rank
       if (maxrow <= Ln.cap) break;
       if (maxrow > MAX_SLOTS) fatal("Neighbour row longer than 64 entries: reduce the skin / cut-off (contact-history mask is 64 bits)");
-      Ln.cap = std::min(MAX_SLOTS, ((maxrow + 2 + 3) / 4) * 4);
+      Ln.cap = std::max(8, std::min(MAX_SLOTS, ((maxrow + 2 + 3) / 4) * 4));
       if (attempt == 2) fatal("Neighbour list capacity did not converge");
     }
     list_gran_dir = (long long)h_counters.p[0]; list_type_dir = (long long)h_counters.p[1];
