@@ -667,7 +667,7 @@ class Engine {
       if (narr > 0) { B.arr_nh = comm.d_arr_nh; B.arr_tag = comm.d_arr_tag; B.arr_shear = comm.d_arr_shear; if (!Lo.valid) B.n_old = n_old; }
     }
     B.maxcount = ctrl.p + 3; B.npairs = counters.p;
-    if (Ln.cap < 8) Ln.cap = std::max(Lo.cap, 8);   // k_step reads the first eight list words of every row unconditionally
+    if (Ln.cap < 12) Ln.cap = std::max(Lo.cap, 12);   // k_step reads the first nine list words of every row unconditionally
     for (int attempt = 0; attempt < 3; attempt++) {
       Ln.npad = npad_ell;
       Ln.nn.ensure(npad_ell); Ln.tmask.ensure(npad_ell);
@@ -685,7 +685,7 @@ class Engine {
       if (comm.nranks > 1) { double m = maxrow; comm.allreduce_max_host(&m, 1); maxrow = (int)m; }  // same capacity decision on every rank
       if (maxrow <= Ln.cap) break;
       if (maxrow > MAX_SLOTS) fatal("Neighbour row longer than 64 entries: reduce the skin / cut-off (contact-history mask is 64 bits)");
-      Ln.cap = std::max(8, std::min(MAX_SLOTS, ((maxrow + 2 + 3) / 4) * 4));
+      Ln.cap = std::max(12, std::min(MAX_SLOTS, ((maxrow + 2 + 3) / 4) * 4));
       if (attempt == 2) fatal("Neighbour list capacity did not converge");
     }
     list_gran_dir = (long long)h_counters.p[0]; list_type_dir = (long long)h_counters.p[1];
