@@ -166,7 +166,7 @@ def main():
     config = {"workload": "configs[2]: %d-particle fluidized bed per GPU, gran/hertzFix/history + wall/granFix + fdrag(ErgunWenYu), "
                           "%d DEM sub-steps per coupling step" % (int(np.prod(dims)), S),
               "particles_per_gpu": int(np.prod(dims)), "substeps_per_step": S, "dt_dem": 2e-6, "skin_over_d": 0.25,
-              "decomposition": "1 GPU" if world == 1 else "%d bricks, NCCL ghost halo every sub-step" % world}
+              "decomposition": "1 GPU" if world == 1 else "%d bricks, ghost halo every sub-step" % world}
 
     if args.impl == "reference":
         if rank != 0:
@@ -337,7 +337,8 @@ def main():
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
 
     if rank == 0:
-        config.update({"pairs_per_particle": pairs_now / n, "ghost_rows_rank0": eng.stat("nghost"), "neighbor_rebuilds_in_timed_region": nbuilds,
+        config.update({"pairs_per_particle": pairs_now / n, "ghost_rows_rank0": eng.stat("nghost"),
+                       "halo": ("NVLink peer-memory push (CUDA IPC) + signal barrier" if eng.comm_stat("p2p") else "NCCL send/recv") if world > 1 else "none", "neighbor_rebuilds_in_timed_region": nbuilds,
                        "l2": "per-step working set (2x96 B state + list + history > 300 MB at 1e6 particles) exceeds the 126 MB L2; no flush needed",
                        "solid_fraction": float(np.pi / 6 / (1 - 2e-3) ** 3)})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,

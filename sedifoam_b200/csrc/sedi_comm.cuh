@@ -86,6 +86,15 @@ struct Comm {
   int *d_gcellid, *d_gcount, *d_gstart, *d_gfill, *d_gorder; size_t cap_g, cap_gcells;
   int narr_last;
   long long halo_calls;
+  // NVLink peer-memory halo (CUDA IPC): the neighbours' particle arrays and every rank's signal array mapped here
+  bool p2p;                       // true once the peer mappings are in place (SEDI_HALO=nccl keeps the NCCL path)
+  unsigned long long *d_sig;      // my signal array [64]
+  void *peer_base[64][7];         // per rank: posr[0], posr[1], velm[0], velm[1], omgt[0], omgt[1], sig (opened IPC mappings)
+  void *exported[7];              // the local pointers the current mappings were made from
+  std::vector<int> rstart;        // per link: first ghost row of my segment in the peer's arrays
+  unsigned epoch;
+  void setup_peer(Engine &e);
+  void close_peer();
   Comm();
 
   double sublo(const SimConfig &c, int d, double shell) const {

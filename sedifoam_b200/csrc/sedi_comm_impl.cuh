@@ -61,7 +61,8 @@ inline Comm::Comm()
     : rank(0), nranks(1), nccl_lib(0), nccl_comm(0), total_send(0), total_recv(0), d_small(0), h_small(0), d_sendrows(0), cap_sendrows(0),
       d_blockcnt(0), d_blockoff(0), d_blocksum(0), cap_block(0), d_sendbuf(0), d_recvbuf(0), cap_sendbuf(0), cap_recvbuf(0), d_migrows(0),
       d_migsend(0), d_migrecv(0), cap_mig(0), migcap(0), migrec(0), d_arr_nh(0), d_arr_tag(0), d_arr_shear(0), cap_arr(0), d_gcellid(0),
-      d_gcount(0), d_gstart(0), d_gfill(0), d_gorder(0), cap_g(0), cap_gcells(0), narr_last(0), halo_calls(0) {
+      d_gcount(0), d_gstart(0), d_gfill(0), d_gorder(0), cap_g(0), cap_gcells(0), narr_last(0), halo_calls(0), p2p(false), d_sig(0), epoch(0) {
+  memset(peer_base, 0, sizeof(peer_base)); memset(exported, 0, sizeof(exported));
   grid[0] = grid[1] = grid[2] = 1; coord[0] = coord[1] = coord[2] = 0;
   memset(&dev, 0, sizeof(dev));
 }
@@ -100,6 +101,10 @@ inline int Comm::init(Engine &e, int rank_, int nranks_, const void *uid, int ui
 }
 
 inline void Comm::destroy() {
+  if (nccl_comm && nranks > 1) barrier();   // nobody unmaps / frees while a peer may still push into this rank
+  close_peer();
+  if (nccl_comm && nranks > 1) barrier();
+  if (d_sig) { cudaFree(d_sig); d_sig = 0; }
   if (nccl_comm) { nccl_dyn::CommDestroy((ncclComm_t)nccl_comm); nccl_comm = 0; }
   void *ptrs[] = {d_small, d_sendrows, d_blockcnt, d_blockoff, d_blocksum, d_sendbuf, d_recvbuf, d_migrows, d_migsend, d_migrecv, d_arr_nh,
                   d_arr_tag, d_arr_shear, d_gcellid, d_gcount, d_gstart, d_gfill, d_gorder};
@@ -183,6 +188,59 @@ inline void Comm::setup_decomp(Engine &e) {
     CK(cudaMalloc((void **)&d_gstart, cap_gcells * sizeof(int)));
     CK(cudaMalloc((void **)&d_gfill, cap_gcells * sizeof(int)));
   }
+  rstart.assign(dev.nlinks, 0);
+  setup_peer(e);
+}
+
+inline void Comm::close_peer() {
+  for (int r = 0; r < 64; r++) for (int k = 0; k < 7; k++) if (peer_base[r][k] && r != rank) { cudaIpcCloseMemHandle(peer_base[r][k]); peer_base[r][k] = 0; }
+  p2p = false;
+}
+
+// map the neighbours' particle arrays and all signal arrays into this process (cudaIpc*), once per (re)load
+inline void Comm::setup_peer(Engine &e) {
+  const char *mode = getenv("SEDI_HALO");
+  if (mode && !strcmp(mode, "nccl")) { p2p = false; return; }
+  if (nranks > 64) { p2p = false; return; }
+  if (!d_sig) { CK(cudaMalloc((void **)&d_sig, 64 * sizeof(unsigned long long))); CK(cudaMemset(d_sig, 0, 64 * sizeof(unsigned long long))); epoch = 0; }
+  void *mine[7] = {e.posr[0].p, e.posr[1].p, e.velm[0].p, e.velm[1].p, e.omgt[0].p, e.omgt[1].p, d_sig};
+  bool same = p2p;
+  for (int k = 0; k < 7; k++) if (mine[k] != exported[k]) same = false;
+  // every rank must take the same branch: agree through a max-reduction
+  double chg = same ? 0.0 : 1.0;
+  allreduce_max_host(&chg, 1);
+  if (chg == 0.0) return;
+  close_peer();
+  struct Pack { cudaIpcMemHandle_t h[7]; };
+  Pack my;
+  int ok = 1;
+  for (int k = 0; k < 7; k++) if (cudaIpcGetMemHandle(&my.h[k], mine[k]) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  Pack *d_all;
+  std::vector<Pack> all(nranks);
+  CK(cudaMalloc((void **)&d_all, (size_t)(nranks + 1) * sizeof(Pack)));
+  CK(cudaMemcpyAsync(d_all + nranks, &my, sizeof(Pack), cudaMemcpyHostToDevice, e.stream));
+  NK(nccl_dyn::AllGather(d_all + nranks, d_all, sizeof(Pack), ncclChar, (ncclComm_t)nccl_comm, e.stream));
+  CK(cudaMemcpyAsync(all.data(), d_all, (size_t)nranks * sizeof(Pack), cudaMemcpyDeviceToHost, e.stream));
+  CK(cudaStreamSynchronize(e.stream));
+  CK(cudaFree(d_all));
+  std::vector<char> need(nranks, 0);
+  for (size_t L = 0; L < links.size(); L++) need[links[L].peer] = 1;
+  for (int r = 0; r < nranks && ok; r++) {
+    if (r == rank) { for (int k = 0; k < 7; k++) peer_base[r][k] = mine[k]; continue; }
+    for (int k = 0; k < 7 && ok; k++) {
+      if (k < 6 && !need[r]) continue;   // particle arrays only of link peers; the signal array of everybody
+      if (cudaIpcOpenMemHandle(&peer_base[r][k], all[r].h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); peer_base[r][k] = 0; ok = 0; }
+    }
+  }
+  double okd = ok ? 1.0 : 0.0, neg = -okd;
+  allreduce_max_host(&neg, 1);          // min over ranks
+  if (neg != -1.0) {
+    if (rank == 0) fprintf(stderr, "libsedi_b200: CUDA IPC peer mapping unavailable, ghost halo falls back to NCCL send/recv\n");
+    close_peer();
+    return;
+  }
+  for (int k = 0; k < 7; k++) exported[k] = mine[k];
+  p2p = true;
 }
 
 static inline int link_with_offset(const std::vector<LinkHost> &links, int ox, int oy, int oz) {
@@ -330,6 +388,14 @@ inline void Comm::borders(Engine &e) {
   if (nl + total_recv > (int)NB_IDX_MASK) fatal("too many rows for the 25-bit neighbour index");
   grow_raw(d_recvbuf, cap_recvbuf, 3 * (size_t)total_recv + 3);
   e.nghost = total_recv;
+  if (p2p) {  // tell every peer where, in my arrays, the ghost segment it fills starts
+    for (int L = 0; L < NL; L++) h_small[L] = nl + recvbase[L];
+    CK(cudaMemcpyAsync(d_cnt, h_small, 32 * sizeof(int), cudaMemcpyHostToDevice, e.stream));
+    exchange_counts(*this, e, d_cnt, d_rcnt);
+    CK(cudaMemcpyAsync(h_small + 32, d_rcnt, 32 * sizeof(int), cudaMemcpyDeviceToHost, e.stream));
+    CK(cudaStreamSynchronize(e.stream));
+    for (int L = 0; L < NL; L++) rstart[L] = h_small[32 + L];
+  }
   forward(e, e.cur, false);
   // bin the ghost rows (index lists, no physical re-ordering)
   const long long nc = e.ncells_bin();
@@ -359,6 +425,28 @@ inline void Comm::borders(Engine &e) {
 // ---- Comm::forward_comm(): ghost x, v, omega every sub-step, plus the rebuild-flag consensus ---------------------------
 inline void Comm::forward(Engine &e, int buf, bool with_flag) {
   const int T = 256, NL = dev.nlinks;
+  if (p2p) {
+    PushTable H;
+    memset(&H, 0, sizeof(H));
+    H.nlinks = NL;
+    for (int L = 0; L < NL; L++) {
+      H.base[L] = sendbase[L]; H.rstart[L] = rstart[L];
+      for (int d = 0; d < 3; d++) H.shift[L][d] = links[L].shift[d];
+      const int pr = links[L].peer;
+      H.rposr[L] = (D4 *)peer_base[pr][0 + buf]; H.rvelm[L] = (D4 *)peer_base[pr][2 + buf]; H.romgt[L] = (D4 *)peer_base[pr][4 + buf];
+    }
+    H.base[NL] = total_send;
+    if (total_send) k_halo_push<<<cdiv(total_send, T), T, 0, e.stream>>>(e.posr[buf].p, e.velm[buf].p, e.omgt[buf].p, d_sendrows, H);
+    SignalTable S;
+    memset(&S, 0, sizeof(S));
+    S.nranks = nranks; S.me = rank;
+    for (int r = 0; r < nranks; r++) S.rsig[r] = (unsigned long long *)peer_base[r][6];
+    epoch++;
+    k_halo_signal_wait<<<1, 64, 0, e.stream>>>(S, d_sig, epoch, e.ctrl.p, with_flag ? 1 : 0);
+    e.launches += 2;
+    halo_calls++;
+    return;
+  }
   HaloTable H;
   memset(&H, 0, sizeof(H));
   H.nlinks = NL;

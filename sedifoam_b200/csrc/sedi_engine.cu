@@ -250,6 +250,7 @@ class Engine {
   ~Engine() {
     if (!dev_ready) return;
     cudaSetDevice(device);
+    g_comm_engine_set(this);
     cudaStreamSynchronize(stream);
     // device memory is released with the process; explicit frees keep long-lived hosts clean
     for (int k = 0; k < 2; k++) { posr[k].release(); velm[k].release(); omgt[k].release(); wmask[k].release(); foam[k].release();

@@ -193,6 +193,56 @@ __global__ void k_halo_pack(const D4 *posr, const D4 *velm, const D4 *omgt, cons
   out[3 * (size_t)e] = p; out[3 * (size_t)e + 1] = v; out[3 * (size_t)e + 2] = w;
 }
 
+// ---- fused pack + send over NVLink peer memory -----------------------------------------------------------------------
+// The ghost rows of every neighbour brick are mapped into this process (CUDA IPC); the border rows are written
+// straight into them (posr + shift, velm, omgt | GHOST), no staging buffer, no NCCL call, no unpack kernel.
+struct PushTable {
+  int nlinks;
+  int base[MAX_LINKS + 1];
+  int rstart[MAX_LINKS];       // first ghost row, in the peer's arrays, of the segment this link fills
+  double shift[MAX_LINKS][3];
+  D4 *rposr[MAX_LINKS], *rvelm[MAX_LINKS], *romgt[MAX_LINKS];   // the peer's arrays of the buffer being written
+};
+__global__ void k_halo_push(const D4 *posr, const D4 *velm, const D4 *omgt, const int *sendrows, const __grid_constant__ PushTable H) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= H.base[H.nlinks]) return;
+  int L = 0;
+  while (L + 1 < H.nlinks && e >= H.base[L + 1]) L++;
+  const int i = sendrows[e];
+  D4 p = posr[i], v = velm[i], w = omgt[i];
+  p.x = p.x + H.shift[L][0]; p.y = p.y + H.shift[L][1]; p.z = p.z + H.shift[L][2];
+  unsigned long long b = (unsigned long long)__double_as_longlong(w.w);
+  b |= ((unsigned long long)PFLAG_GHOST) << 56;
+  w.w = __longlong_as_double((long long)b);
+  const int r = H.rstart[L] + (e - H.base[L]);
+  H.rposr[L][r] = p; H.rvelm[L][r] = v; H.romgt[L][r] = w;
+  __threadfence_system();
+}
+
+// all-ranks barrier + rebuild-flag consensus through peer memory: rank r's slot [me] of every rank's signal array
+// receives (epoch << 32 | my flag); then every rank waits until all its slots carry this epoch and takes the max flag.
+struct SignalTable { int nranks, me; unsigned long long *rsig[64]; };
+__global__ void k_halo_signal_wait(const __grid_constant__ SignalTable S, volatile unsigned long long *mysig, unsigned epoch, int *ctrl, int with_flag) {
+  __shared__ int sflag[64];
+  const int r = threadIdx.x;
+  if (r < S.nranks) {
+    const unsigned fl = with_flag ? (unsigned)ctrl[0] : 0u;
+    __threadfence_system();
+    *((volatile unsigned long long *)&S.rsig[r][S.me]) = ((unsigned long long)epoch << 32) | fl;
+    __threadfence_system();
+    unsigned long long v;
+    do { v = mysig[r]; } while ((unsigned)(v >> 32) < epoch);
+    sflag[r] = (int)(unsigned)(v & 0xffffffffull);
+  }
+  __syncthreads();
+  if (r == 0 && with_flag) {
+    int m = 0;
+    for (int k = 0; k < S.nranks; k++) m = max(m, sflag[k]);
+    ctrl[0] = m;
+  }
+  __threadfence_system();
+}
+
 // receiver side: records -> ghost rows [row0, row0 + nghost)
 __global__ void k_halo_unpack(const D4 *in, int nghost, int row0, D4 *posr, D4 *velm, D4 *omgt) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;

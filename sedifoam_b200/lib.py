@@ -395,7 +395,7 @@ class Lammps:
         self.lib.sedi_comm_init(self.h, int(rank), int(nranks), C.cast(b, C.c_void_p), len(uid), _vp(pg))
 
     def comm_stat(self, name):
-        return int(self.lib.sedi_comm_stat(self.h, {"halo_calls": 0, "send_rows": 1, "ghost_rows": 2, "links": 3, "arrivals": 4}[name]))
+        return int(self.lib.sedi_comm_stat(self.h, {"halo_calls": 0, "send_rows": 1, "ghost_rows": 2, "links": 3, "arrivals": 4, "p2p": 5}[name]))
 
 
 def decomp_grid(nranks, boxlen):

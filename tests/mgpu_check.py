@@ -53,7 +53,7 @@ def main():
         eng.step(nsteps - nsteps // 2)
         st = eng.atoms()
         stats = dict(nlocal=eng.get_local_n(), nbuilds=eng.stat("nbuilds"), pair_evals=eng.stat("pair_evals"), ghosts=eng.comm_stat("ghost_rows"),
-                     links=eng.comm_stat("links"), halo=eng.comm_stat("halo_calls"), gran_entries=eng.stat("gran_entries"))
+                     links=eng.comm_stat("links"), halo=eng.comm_stat("halo_calls"), p2p=eng.comm_stat("p2p"), gran_entries=eng.stat("gran_entries"))
         gathered = [None] * world
         dist.all_gather_object(gathered, dict(tag=st["tag"], x=st["x"], v=st["v"], omega=st["omega"], stats=stats, dom=eng.get_local_domain(),
                                               nglobal=eng.get_global_n()))
@@ -85,9 +85,9 @@ def main():
             nb = [g["stats"]["nbuilds"] for g in gathered]
             pe = sum(g["stats"]["pair_evals"] for g in gathered)
             good = good and all(b == o.stat("nbuilds") for b in nb) and all(g["nglobal"] == n for g in gathered)
-            print("[mgpu %s] ranks=%d n=%d nlocal=%s ghosts=%s links=%s rebuilds=%s (oracle %d) halo_calls=%d err x=%.2e v=%.2e w=%.2e pair_evals=%d (oracle %d) -> %s"
+            print("[mgpu %s] ranks=%d n=%d nlocal=%s ghosts=%s links=%s rebuilds=%s (oracle %d) halo_calls=%d p2p=%d err x=%.2e v=%.2e w=%.2e pair_evals=%d (oracle %d) -> %s"
                   % (name, world, n, [g["stats"]["nlocal"] for g in gathered], [g["stats"]["ghosts"] for g in gathered],
-                     [g["stats"]["links"] for g in gathered], nb, o.stat("nbuilds"), gathered[0]["stats"]["halo"], ex, ev, ew, pe,
+                     [g["stats"]["links"] for g in gathered], nb, o.stat("nbuilds"), gathered[0]["stats"]["halo"], gathered[0]["stats"]["p2p"], ex, ev, ew, pe,
                      o.stat("pair_evals"), "OK" if good else "FAIL"), flush=True)
             ok = ok and good
         eng.close()
