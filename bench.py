@@ -151,7 +151,7 @@ def main():
         faulthandler.dump_traceback_later(float(os.environ["SEDI_BENCH_TRACE"]), repeat=True, file=sys.stderr)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--dims", default=None, help="override the bed lattice, e.g. 50x50x50 (testing only)")
@@ -282,15 +282,28 @@ def main():
 
     # ---- e2e through the reference boundary with host buffers
     m1 = float(case["rho"][0] * np.pi / 6.0 * case["diam"][0] ** 3)
-    state = {"loc": eng.get_local_info()}
+    # the host side of the boundary: page-locked arrays, allocated once (an OpenFOAM host would keep its particle lists
+    # in such buffers); sized with slack because brick ownership changes by migration
+    ncap = int(n * 1.3) + 4096
+
+    def pinned(shape, dtype):
+        return torch.empty(shape, dtype=dtype).pin_memory().numpy()
+
+    hb = {"fd": pinned((ncap, 3), torch.float64), "x": pinned((ncap, 3), torch.float64), "v": pinned((ncap, 3), torch.float64),
+          "tag": pinned((ncap,), torch.int32), "foam": pinned((ncap,), torch.int32), "lmp": np.zeros(ncap, np.int32)}
+    first = eng.get_local_info()
+    state = {"n": len(first["tag"])}
+    hb["tag"][:state["n"]] = first["tag"]; hb["foam"][:state["n"]] = first["foamCpuId"]
 
     def e2e_step():
-        loc = state["loc"]                      # host arrays of the previous step (tags of the particles this rank owns)
-        nl = len(loc["tag"])
-        fd = np.zeros((nl, 3)); fd[:, 1] = 0.3 * 9.8 * m1    # the host-side fluid force for exactly those particles
-        eng.put_local_info(fd, loc["tag"], foam_cpu=loc["foamCpuId"])
+        nl = state["n"]                            # particles this rank owned after the previous step
+        fd = hb["fd"][:nl]
+        fd[:, 0] = 0.0; fd[:, 1] = 0.3 * 9.8 * m1; fd[:, 2] = 0.0     # the host-side fluid force for exactly those particles
+        eng.put_local_info(fd, hb["tag"][:nl], foam_cpu=hb["foam"][:nl])
         eng.step(S)
-        state["loc"] = eng.get_local_info()     # x, v, ids back on the host
+        nl = eng.get_local_n()
+        eng.get_local_info(hb["x"][:nl], hb["v"][:nl], hb["foam"][:nl], hb["lmp"][:nl], hb["tag"][:nl])   # x, v, ids back on the host
+        state["n"] = nl
 
     e2e_step()
     eng.reset_stats()

@@ -788,6 +788,11 @@ class Engine {
   }
 
   // ---- C-ABI data movement ---------------------------------------------------------------------------------------
+  static bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  }
   void put_local(int nin, const double *fd, const int *foamin, const int *tagin) {
     if (!loaded) load_atoms();
     need_device();
@@ -797,14 +802,15 @@ class Engine {
     }
     if (!nin) return;
     if (!setup_done) setup();  // tag2idx is filled by the first build
-    h_stage_a.ensure(3 * (size_t)nin); h_stage_i.ensure(nin); h_stage_j.ensure(nin);
     d_stage_a.ensure(3 * (size_t)nin); d_stage_i.ensure(nin); d_stage_j.ensure(nin);
-    memcpy(h_stage_a.p, fd, 3 * (size_t)nin * sizeof(double));
-    memcpy(h_stage_i.p, tagin, nin * sizeof(int));
-    if (foamin) memcpy(h_stage_j.p, foamin, nin * sizeof(int));
-    CK(cudaMemcpyAsync(d_stage_a.p, h_stage_a.p, 3 * (size_t)nin * sizeof(double), cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(d_stage_i.p, h_stage_i.p, nin * sizeof(int), cudaMemcpyHostToDevice, stream));
-    if (foamin) CK(cudaMemcpyAsync(d_stage_j.p, h_stage_j.p, nin * sizeof(int), cudaMemcpyHostToDevice, stream));
+    // caller arrays that are already page-locked go straight to the copy engine; pageable ones are staged
+    const void *src_a = fd, *src_i = tagin, *src_j = foamin;
+    if (!is_pinned(fd)) { h_stage_a.ensure(3 * (size_t)nin); memcpy(h_stage_a.p, fd, 3 * (size_t)nin * sizeof(double)); src_a = h_stage_a.p; }
+    if (!is_pinned(tagin)) { h_stage_i.ensure(nin); memcpy(h_stage_i.p, tagin, nin * sizeof(int)); src_i = h_stage_i.p; }
+    if (foamin && !is_pinned(foamin)) { h_stage_j.ensure(nin); memcpy(h_stage_j.p, foamin, nin * sizeof(int)); src_j = h_stage_j.p; }
+    CK(cudaMemcpyAsync(d_stage_a.p, src_a, 3 * (size_t)nin * sizeof(double), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(d_stage_i.p, src_i, nin * sizeof(int), cudaMemcpyHostToDevice, stream));
+    if (foamin) CK(cudaMemcpyAsync(d_stage_j.p, src_j, nin * sizeof(int), cudaMemcpyHostToDevice, stream));
     k_put_fdrag<<<cdiv(nin, 256), 256, 0, stream>>>(nin, d_stage_a.p, d_stage_i.p, foamin ? d_stage_j.p : 0, tag2idx.p, maxtag,
                                                     fdrag[0].get(), fdrag[1].get(), fdrag[2].get(), foam[icur].p, ctrl.p + 2);
     launches++;
@@ -818,20 +824,25 @@ class Engine {
     need_device();
     const int m = nlocal;
     if (!m) return;
-    h_stage_a.ensure(3 * (size_t)m); h_stage_b.ensure(3 * (size_t)m); h_stage_i.ensure(m); h_stage_j.ensure(m);
     d_stage_a.ensure(3 * (size_t)m); d_stage_b.ensure(3 * (size_t)m); d_stage_i.ensure(m); d_stage_j.ensure(m);
     k_pack_local<<<cdiv(m, 256), 256, 0, stream>>>(posr[cur].p, velm[cur].p, omgt[cur].p, foam[icur].p, m, d_stage_a.p, d_stage_b.p,
                                                    d_stage_i.p, d_stage_j.p);
     launches++;
-    CK(cudaMemcpyAsync(h_stage_a.p, d_stage_a.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
-    CK(cudaMemcpyAsync(h_stage_b.p, d_stage_b.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
-    CK(cudaMemcpyAsync(h_stage_i.p, d_stage_i.p, m * sizeof(int), cudaMemcpyDeviceToHost, stream));
-    CK(cudaMemcpyAsync(h_stage_j.p, d_stage_j.p, m * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    // page-locked caller arrays receive the DMA directly; pageable ones go through the pinned staging buffers
+    const bool px = x && is_pinned(x), pv = v && is_pinned(v), pt = tag && is_pinned(tag), pf = foamid && is_pinned(foamid);
+    if (x && !px) h_stage_a.ensure(3 * (size_t)m);
+    if (v && !pv) h_stage_b.ensure(3 * (size_t)m);
+    if (tag && !pt) h_stage_i.ensure(m);
+    if (foamid && !pf) h_stage_j.ensure(m);
+    if (x) CK(cudaMemcpyAsync(px ? (void *)x : (void *)h_stage_a.p, d_stage_a.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (v) CK(cudaMemcpyAsync(pv ? (void *)v : (void *)h_stage_b.p, d_stage_b.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (tag) CK(cudaMemcpyAsync(pt ? (void *)tag : (void *)h_stage_i.p, d_stage_i.p, m * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (foamid) CK(cudaMemcpyAsync(pf ? (void *)foamid : (void *)h_stage_j.p, d_stage_j.p, m * sizeof(int), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    if (x) memcpy(x, h_stage_a.p, 3 * (size_t)m * sizeof(double));
-    if (v) memcpy(v, h_stage_b.p, 3 * (size_t)m * sizeof(double));
-    if (tag) memcpy(tag, h_stage_i.p, m * sizeof(int));
-    if (foamid) memcpy(foamid, h_stage_j.p, m * sizeof(int));
+    if (x && !px) memcpy(x, h_stage_a.p, 3 * (size_t)m * sizeof(double));
+    if (v && !pv) memcpy(v, h_stage_b.p, 3 * (size_t)m * sizeof(double));
+    if (tag && !pt) memcpy(tag, h_stage_i.p, m * sizeof(int));
+    if (foamid && !pf) memcpy(foamid, h_stage_j.p, m * sizeof(int));
     if (lmpid) for (int i = 0; i < m; i++) lmpid[i] = comm.rank;
   }
 

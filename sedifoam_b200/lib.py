@@ -220,7 +220,7 @@ class Lammps:
         fdrag = _f64(fdrag, (n, 3))
         tags = _i32(tags)
         foam_cpu = np.zeros(n, np.int32) if foam_cpu is None else _i32(foam_cpu)
-        DuDt = np.zeros((n, 3)) if DuDt is None else _f64(DuDt, (n, 3))
+        DuDt = None if DuDt is None else _f64(DuDt, (n, 3))   # ignored by the reference too (library.cpp:314-367)
         self.lib.lammps_put_local_info(self.h, n, _vp(fdrag), _vp(DuDt), _vp(foam_cpu), _vp(tags))
 
     def step(self, n):
