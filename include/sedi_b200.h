@@ -111,6 +111,17 @@ void sedi_compute_fluid_force(void *ptr);
 void sedi_scatter_alpha_u(void *ptr, double *gamma, double *Ue);
 /* calcTcFields: Asrc[C][3] ; Omega[C] is identically zero in the reference (enhancedCloud.C:391) */
 void sedi_calc_tc(void *ptr, double *Asrc, double *Omega);
+/* diffusion smoothing of the Eulerian particle fields (enhancedCloud::smoothField, enhancedCloud.C:790-907):
+ * bandwidth = diffusionBandWidth, steps = diffusionSteps, Ddiag = diagonal of smoothDirection (NULL = identity),
+ * flags = which fields are smoothed inside the sedi_* calls (names of constant/cloudProperties, :573-576) */
+#define SEDI_SMOOTH_UF_BIT 1
+#define SEDI_SMOOTH_UP_BIT 2
+#define SEDI_SMOOTH_DRAG_BIT 4
+#define SEDI_SMOOTH_ALPHA_BIT 8
+void sedi_smooth_config(void *ptr, double bandwidth, int steps, const double *Ddiag, int flags);
+void sedi_smooth_uf(void *ptr);                                  /* Uf (1-gamma) -> smooth -> / (1-gamma), :675-690 */
+void sedi_smooth_field(void *ptr, double *field, int ncomp);    /* smooth a host cell field in place (ncomp 1 or 3) */
+int sedi_smooth_last_iters(void *ptr);                           /* PCG iterations of the last solve */
 void sedi_enable_diag(void *ptr, int on); /* keep Uri/|Uri|/alpha/Jd per particle at the next sedi_compute_fluid_force */
 /* diagnostics of the last sedi_compute_fluid_force, device order: cell[n], Uri[n][3], magUri[n], alpha[n], Jd[n],
  * F[n][3]; any pointer may be NULL */

@@ -9,7 +9,8 @@
 //
 // Differences to the reference that a drop-in must know (all documented in DESIGN.md):
 //   * the mesh is a single-block uniform blockMesh box (every shipped case); cell = i + nx (j + ny k);
-//   * diffusion smoothing (smoothField, enhancedCloud.C:790-907) is not applied here;
+//   * diffusion smoothing (smoothField, enhancedCloud.C:790-907) runs on the GPU inside the sedi_* calls when
+//     diffusionBandWidth > 0 (Jacobi-PCG on the box mesh; only the diagonal of smoothDirection acts);
 //   * Omega() is identically zero, as in the reference (enhancedCloud.C:391).
 #ifndef SEDI_CLOUD_HPP
 #define SEDI_CLOUD_HPP
@@ -25,9 +26,16 @@ struct CloudProperties {          // constant/cloudProperties + transportPropert
   double g[3];
   bool particleDrag, particlePressureGrad, particleBuoyancy, particleAddedMass, particleLift;
   double nub, rhob;
+  double diffusionBandWidth;      // 0 = pure PCM, no smoothing (cases/.../expWachem_PCM)
+  int diffusionSteps;
+  double smoothDirection[3];      // diagonal of the tensor (enhancedCloud.C:578-583)
+  bool UfSmooth, UpSmooth, dragSmooth, alphaSmooth;   // defaults true (enhancedCloud.C:573-576)
   CloudProperties()
       : dragModel("ErgunWenYu"), subCycles(1), particleDrag(true), particlePressureGrad(true), particleBuoyancy(false),
-        particleAddedMass(false), particleLift(false), nub(1e-6), rhob(1000.0) { g[0] = g[1] = g[2] = 0.0; }
+        particleAddedMass(false), particleLift(false), nub(1e-6), rhob(1000.0), diffusionBandWidth(0.0), diffusionSteps(0),
+        UfSmooth(true), UpSmooth(true), dragSmooth(true), alphaSmooth(true) {
+    g[0] = g[1] = g[2] = 0.0; smoothDirection[0] = smoothDirection[1] = smoothDirection[2] = 1.0;
+  }
 };
 
 class enhancedCloud {
@@ -45,6 +53,12 @@ class enhancedCloud {
     if (cp.particleAddedMass) flags |= SEDI_FORCE_ADDEDMASS_BIT;
     if (cp.particleLift) flags |= SEDI_FORCE_LIFT_BIT;
     sedi_coupling_config(lmp_, model, flags, cp.nub, cp.rhob, cp.g, deltaT);
+    int sflags = 0;
+    if (cp.UfSmooth) sflags |= SEDI_SMOOTH_UF_BIT;
+    if (cp.UpSmooth) sflags |= SEDI_SMOOTH_UP_BIT;
+    if (cp.dragSmooth) sflags |= SEDI_SMOOTH_DRAG_BIT;
+    if (cp.alphaSmooth) sflags |= SEDI_SMOOTH_ALPHA_BIT;
+    sedi_smooth_config(lmp_, cp.diffusionBandWidth, cp.diffusionSteps, cp.smoothDirection, sflags);
     gamma_.assign(nCells_, 0.0); Ue_.assign(3 * (size_t)nCells_, 0.0);
     Asrc_.assign(3 * (size_t)nCells_, 0.0); Omega_.assign(nCells_, 0.0);
     // softParticleCloud::adjustLampTimestep (softParticleCloud.C:209-261): dtDEM := dtFluid / round(dtFluid / dtDEM)
@@ -61,6 +75,7 @@ class enhancedCloud {
   // fluid fields of the current time step (Ub, grad p, DDtUb, curl Ub): pointers to [C][3] doubles, NULL = absent
   void setFluidFields(const double *Ub, const double *gradp, const double *DDtUb, const double *curlUb) {
     sedi_put_cell_fields(lmp_, Ub, 0, gradp, DDtUb, curlUb);
+    sedi_smooth_uf(lmp_);   // UfSmoothed_ = Uf (1-gamma) -> smooth -> / (1-gamma)  (enhancedCloud.C:675-690); no-op when off
   }
 
   // enhancedCloud::evolve(), enhancedCloud.C:669-787

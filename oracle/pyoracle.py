@@ -218,3 +218,35 @@ def calc_tc(cell, d, U, Uf, gamma, cellV, model, nub, rhob, kind="port"):
     lib.ora_foam_calc_tc(len(cell), np.ascontiguousarray(cell, np.int32), c(d), c(U), c(Uf), c(gamma), Cn, c(cellV), model,
                          nub, rhob, Asrc, Omega)
     return Asrc, Omega
+
+
+def smooth_field(phi, ncell, dx, bandwidth, steps, Ddiag=(1.0, 1.0, 1.0)):
+    """enhancedCloud::smoothField restated (lammpsFoam/enhancedCloud.C:790-907, :564-568; SURVEY Appendix B5):
+    `steps` implicit-Euler steps of d_tau = (b^2/4)/steps of d(phi)/d(tau) = div(D grad phi), zeroGradient walls, on the
+    uniform box mesh; each step one sparse direct solve (scipy) -- the converged answer of OpenFOAM's PCG (tol 1e-10).
+    PARITY UNPINNED at bit level (no OpenFOAM here); pinned by conservation of sum(phi V) and the Gaussian limit."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    nx, ny, nz = [int(v) for v in ncell]
+    C = nx * ny * nz
+    dtau = (bandwidth * bandwidth / 4.0) / (steps + 1.0e-150)
+    w = [dtau * Ddiag[k] / (dx[k] * dx[k]) for k in range(3)]
+
+    def lap1(n):
+        e = np.ones(n)
+        L = sp.diags([e[:-1], -2 * e, e[:-1]], [-1, 0, 1], format="lil")
+        L[0, 0] = -1.0; L[n - 1, n - 1] = -1.0      # zeroGradient: the wall face carries no flux
+        if n == 1:
+            L[0, 0] = 0.0
+        return sp.csr_matrix(L)
+    Ix, Iy, Iz = sp.identity(nx), sp.identity(ny), sp.identity(nz)
+    # cell = i + nx (j + ny k): x fastest
+    Lx = sp.kron(Iz, sp.kron(Iy, lap1(nx))); Ly = sp.kron(Iz, sp.kron(lap1(ny), Ix)); Lz = sp.kron(lap1(nz), sp.kron(Iy, Ix))
+    A = sp.identity(C) - (w[0] * Lx + w[1] * Ly + w[2] * Lz)
+    lu = spl.splu(sp.csc_matrix(A))
+    out = np.array(phi, np.float64, copy=True)
+    flat = out.reshape(C, -1)
+    for _ in range(int(steps)):
+        for k in range(flat.shape[1]):
+            flat[:, k] = lu.solve(flat[:, k])
+    return out

@@ -31,6 +31,7 @@
 #include "sedi_neigh.cuh"
 #include "sedi_step.cuh"
 #include "sedi_couple.cuh"
+#include "sedi_smooth.cuh"
 #include "sedi_halo.cuh"
 #include "sedi_comm.cuh"
 
@@ -227,6 +228,11 @@ class Engine {
   double nub, rhob, gvec[3], deltaT;
   Buf<double> dg_Uri, dg_mag, dg_alpha, dg_Jd;
   bool want_diag;
+  // diffusion smoothing (enhancedCloud.C:564-583, 790-907)
+  double smooth_b, smooth_D[3];
+  int smooth_steps, smooth_flags, smooth_iters_last;
+  Buf<double> cg_r, cg_z, cg_p, cg_Ap, cg_partial, cg_s, cg_tmp;
+  Pinned<double> h_cg;
   Comm comm;
 
   Engine()
@@ -235,8 +241,9 @@ class Engine {
         beta_pair(0), pair_evals_unique(0), nbuilds(0), pair_evals(0), steps_done(0), launches(0), list_gran_dir(0), list_type_dir(0), list_gran_img(0),
         list_type_img(0), chunk(16), last_step_ms(0), count_in_kernel(false), have_mesh(false), ncells(0), have_DDtU(false),
         have_curlU(false), have_gradp(false), drag_model(0), force_flags(SEDI_FORCE_DRAG | SEDI_FORCE_PGRAD), nub(1e-6), rhob(1000.0),
-        deltaT(1.0), want_diag(false), prof_on(false), prof_ms(0), prof_steps(0) {
+        deltaT(1.0), want_diag(false), smooth_b(0.0), smooth_steps(0), smooth_flags(0), smooth_iters_last(0), prof_on(false), prof_ms(0), prof_steps(0) {
     gvec[0] = gvec[1] = gvec[2] = 0.0;
+    smooth_D[0] = smooth_D[1] = smooth_D[2] = 1.0;
     memset(&base, 0, sizeof(base));
     memset(&bin, 0, sizeof(bin));
     memset(&mesh, 0, sizeof(mesh));
@@ -264,6 +271,7 @@ class Engine {
     h_stage_a.release(); h_stage_b.release(); h_stage_i.release(); h_stage_j.release();
     cell.release(); Uf.release(); gamma.release(); gradp.release(); DDtU.release(); curlU.release(); cellV.release(); Ue.release(); Asrc.release();
     dg_Uri.release(); dg_mag.release(); dg_alpha.release(); dg_Jd.release();
+    cg_r.release(); cg_z.release(); cg_p.release(); cg_Ap.release(); cg_partial.release(); cg_s.release(); cg_tmp.release(); h_cg.release();
     comm.destroy();
     cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evk0); cudaEventDestroy(evk1);
     cudaEventDestroy(evt0); cudaEventDestroy(evt1);
@@ -992,6 +1000,70 @@ class Engine {
     launches++;
   }
 
+  // ---- smoothField: `diffusionSteps` implicit-Euler diffusion steps, each one SPD 7-point solve by Jacobi-PCG ------------
+  bool smoothing_on(int flag) const { return (smooth_flags & flag) && smooth_b > 0.0 && smooth_steps > 0; }
+  void dot_to(const double *a, int sa, int oa, const double *b, int sb, int ob, int nC, double *out) {
+    const int nb = std::min(1024, cdiv(nC, 256));
+    k_dot_partial<<<nb, 256, 0, stream>>>(a, sa, oa, b, sb, ob, nC, cg_partial.p);
+    k_dot_final<<<1, 256, 0, stream>>>(cg_partial.p, nb, out);
+    launches += 2;
+  }
+  void smooth_component(double *field, int stride, int off) {
+    const int C = ncells, T = 256;
+    cg_r.ensure(C); cg_z.ensure(C); cg_p.ensure(C); cg_Ap.ensure(C); cg_partial.ensure(1024); cg_s.ensure(8); h_cg.ensure(8);
+    SmoothGrid G;
+    G.nx = mesh.nc[0]; G.ny = mesh.nc[1]; G.nz = mesh.nc[2];
+    const double dtau = (smooth_b * smooth_b / 4) / (smooth_steps + 1.0e-150);   // enhancedCloud.C:564-565
+    G.wx = dtau * smooth_D[0] / (mesh.dx[0] * mesh.dx[0]); G.wy = dtau * smooth_D[1] / (mesh.dx[1] * mesh.dx[1]); G.wz = dtau * smooth_D[2] / (mesh.dx[2] * mesh.dx[2]);
+    const int nblk = cdiv(C, T);
+    for (int step = 0; step < smooth_steps; step++) {
+      // A x = b with b = field (also the initial guess); s = {rz, pAp, rz_new, rr, bb}
+      dot_to(field, stride, off, field, stride, off, C, cg_s.p + 4);
+      k_smooth_apply<<<nblk, T, 0, stream>>>(G, field, cg_Ap.p, stride, off);
+      k_cg_init<<<nblk, T, 0, stream>>>(G, field, stride, off, cg_Ap.p, cg_r.p, cg_z.p, cg_p.p, C);
+      dot_to(cg_r.p, 1, 0, cg_z.p, 1, 0, C, cg_s.p + 0);
+      dot_to(cg_r.p, 1, 0, cg_r.p, 1, 0, C, cg_s.p + 3);
+      launches += 2;
+      int it = 0;
+      for (; it < 500; it++) {
+        if ((it & 3) == 0) {  // convergence check: ||r|| <= 1e-12 ||b||
+          CK(cudaMemcpyAsync(h_cg.p, cg_s.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+          CK(cudaStreamSynchronize(stream));
+          if (!(h_cg.p[3] > 1.0e-24 * h_cg.p[4]) || h_cg.p[0] == 0.0) break;
+        }
+        k_smooth_apply<<<nblk, T, 0, stream>>>(G, cg_p.p, cg_Ap.p, 1, 0);
+        dot_to(cg_p.p, 1, 0, cg_Ap.p, 1, 0, C, cg_s.p + 1);
+        k_cg_step1<<<nblk, T, 0, stream>>>(field, stride, off, cg_r.p, cg_p.p, cg_Ap.p, cg_s.p, G, cg_z.p, C);
+        dot_to(cg_r.p, 1, 0, cg_z.p, 1, 0, C, cg_s.p + 2);
+        dot_to(cg_r.p, 1, 0, cg_r.p, 1, 0, C, cg_s.p + 3);
+        k_cg_step2<<<nblk, T, 0, stream>>>(cg_p.p, cg_z.p, cg_s.p, C);
+        k_cg_shift<<<1, 1, 0, stream>>>(cg_s.p);
+        launches += 4;
+      }
+      smooth_iters_last = it;
+    }
+  }
+  void smooth_device_field(double *f, int ncomp) { for (int k = 0; k < ncomp; k++) smooth_component(f, ncomp, k); }
+  // UfSmoothed = Uf (1-gamma) -> smooth -> / (1-gamma)   (enhancedCloud.C:675-690)
+  void smooth_uf() {
+    if (!have_mesh) fatal("sedi_smooth_uf: call sedi_mesh_box first");
+    need_device();
+    if (!smoothing_on(1)) return;
+    k_scale_one_minus_gamma<<<cdiv(ncells, 256), 256, 0, stream>>>(ncells, gamma.p, Uf.p, 3, 0);
+    smooth_device_field(Uf.p, 3);
+    k_scale_one_minus_gamma<<<cdiv(ncells, 256), 256, 0, stream>>>(ncells, gamma.p, Uf.p, 3, 1);
+    launches += 2;
+  }
+  void smooth_host_field(double *h, int ncomp) {  // test / host hook: smooth a host array in place
+    if (!have_mesh) fatal("sedi_smooth_field: call sedi_mesh_box first");
+    need_device();
+    cg_tmp.ensure((size_t)ncells * ncomp);
+    CK(cudaMemcpyAsync(cg_tmp.p, h, (size_t)ncells * ncomp * sizeof(double), cudaMemcpyHostToDevice, stream));
+    if (smooth_b > 0.0 && smooth_steps > 0) smooth_device_field(cg_tmp.p, ncomp);
+    CK(cudaMemcpyAsync(h, cg_tmp.p, (size_t)ncells * ncomp * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+  }
+
   void scatter_alpha_u(double *hgamma, double *hUe) {
     if (!setup_done) setup();
     if (!cell_valid) locate();
@@ -1000,7 +1072,14 @@ class Engine {
     CK(cudaMemsetAsync(Ue.p, 0, 3 * C * sizeof(double), stream));
     if (nlocal) k_scatter_alpha_u<<<cdiv(nlocal, 256), 256, 0, stream>>>(posr[cur].p, velm[cur].p, cell.p, nlocal, gamma.p, Ue.p);
     if (comm.nranks > 1) { comm.allreduce_sum_dev(gamma.p, C, stream); comm.allreduce_sum_dev(Ue.p, 3 * C, stream); }
-    k_finalize_alpha_u<<<cdiv(C, 256), 256, 0, stream>>>((int)C, cellV.p, gamma.p, Ue.p);
+    if (smoothing_on(8) || smoothing_on(2)) {  // enhancedCloud.C:932-962 with alphaSmooth / UpSmooth
+      k_alpha_u_divV<<<cdiv(C, 256), 256, 0, stream>>>((int)C, cellV.p, gamma.p, Ue.p);
+      if (smoothing_on(8)) smooth_device_field(gamma.p, 1);
+      if (smoothing_on(2)) smooth_device_field(Ue.p, 3);
+      k_alpha_u_divgamma<<<cdiv(C, 256), 256, 0, stream>>>((int)C, gamma.p, Ue.p);
+    } else {
+      k_finalize_alpha_u<<<cdiv(C, 256), 256, 0, stream>>>((int)C, cellV.p, gamma.p, Ue.p);
+    }
     launches += 2;
     if (hgamma) CK(cudaMemcpyAsync(hgamma, gamma.p, C * sizeof(double), cudaMemcpyDeviceToHost, stream));
     if (hUe) CK(cudaMemcpyAsync(hUe, Ue.p, 3 * C * sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -1015,7 +1094,13 @@ class Engine {
     if (nlocal)
       k_scatter_asrc<<<cdiv(nlocal, 256), 256, 0, stream>>>(posr[cur].p, velm[cur].p, cell.p, nlocal, Uf.p, gamma.p, cellV.p, drag_model, nub, rhob, Asrc.p);
     if (comm.nranks > 1) comm.allreduce_sum_dev(Asrc.p, 3 * C, stream);
-    k_finalize_asrc<<<cdiv(C, 256), 256, 0, stream>>>((int)C, gamma.p, Asrc.p);
+    if (smoothing_on(4)) {  // Asrc (1-gamma) -> smooth -> / (1-gamma)   (enhancedCloud.C:407-416, dragSmooth)
+      k_scale_one_minus_gamma<<<cdiv(C, 256), 256, 0, stream>>>((int)C, gamma.p, Asrc.p, 3, 0);
+      smooth_device_field(Asrc.p, 3);
+      k_scale_one_minus_gamma<<<cdiv(C, 256), 256, 0, stream>>>((int)C, gamma.p, Asrc.p, 3, 1);
+    } else {
+      k_finalize_asrc<<<cdiv(C, 256), 256, 0, stream>>>((int)C, gamma.p, Asrc.p);
+    }
     launches += 2;
     if (hAsrc) CK(cudaMemcpyAsync(hAsrc, Asrc.p, 3 * C * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
@@ -1252,6 +1337,14 @@ void sedi_locate(void *ptr) { Engine *e = E(ptr); if (!e->setup_done) e->setup()
 void sedi_compute_fluid_force(void *ptr) { E(ptr)->fluid_force(); }
 void sedi_scatter_alpha_u(void *ptr, double *gamma, double *Ue) { E(ptr)->scatter_alpha_u(gamma, Ue); }
 void sedi_calc_tc(void *ptr, double *Asrc, double *Omega) { E(ptr)->calc_tc(Asrc, Omega); }
+void sedi_smooth_config(void *ptr, double bandwidth, int steps, const double *Ddiag, int flags) {
+  Engine *e = E(ptr);
+  e->smooth_b = bandwidth; e->smooth_steps = steps; e->smooth_flags = flags;
+  for (int d = 0; d < 3; d++) e->smooth_D[d] = Ddiag ? Ddiag[d] : 1.0;
+}
+void sedi_smooth_uf(void *ptr) { E(ptr)->smooth_uf(); }
+void sedi_smooth_field(void *ptr, double *field, int ncomp) { E(ptr)->smooth_host_field(field, ncomp); }
+int sedi_smooth_last_iters(void *ptr) { return E(ptr)->smooth_iters_last; }
 void sedi_enable_diag(void *ptr, int on) { E(ptr)->want_diag = (on != 0); }
 void sedi_get_coupling_diag(void *ptr, int *cell, double *Uri, double *magUri, double *alphap, double *Jd, double *F) {
   E(ptr)->get_coupling_diag(cell, Uri, magUri, alphap, Jd, F);

@@ -26,7 +26,8 @@ EXPORTED_SYMBOLS = [
     "sedi_get_profile", "sedi_mesh_box", "sedi_mesh_ncells", "sedi_coupling_config",
     "sedi_put_cell_fields", "sedi_locate", "sedi_compute_fluid_force", "sedi_scatter_alpha_u", "sedi_calc_tc",
     "sedi_enable_diag", "sedi_get_coupling_diag", "sedi_step", "sedi_comm_init", "sedi_comm_unique_id", "sedi_comm_rank", "sedi_comm_stat",
-    "sedi_decomp_grid", "sedi_decomp_owner", "sedi_decomp_links",
+    "sedi_decomp_grid", "sedi_decomp_owner", "sedi_decomp_links", "sedi_smooth_config", "sedi_smooth_uf", "sedi_smooth_field",
+    "sedi_smooth_last_iters",
 ]
 
 
@@ -111,6 +112,10 @@ def load_library():
         "sedi_scatter_alpha_u": (None, [vp, vp, vp]),
         "sedi_calc_tc": (None, [vp, vp, vp]),
         "sedi_enable_diag": (None, [vp, i]),
+        "sedi_smooth_config": (None, [vp, d, i, vp, i]),
+        "sedi_smooth_uf": (None, [vp]),
+        "sedi_smooth_field": (None, [vp, vp, i]),
+        "sedi_smooth_last_iters": (i, [vp]),
         "sedi_get_coupling_diag": (None, [vp] + [vp] * 6),
         "sedi_step": (None, [vp, i]),
         "sedi_comm_init": (i, [vp, i, i, vp, i, vp]),
@@ -362,6 +367,22 @@ class Lammps:
         Omega = np.zeros(Cn) if Omega is None else Omega
         self.lib.sedi_calc_tc(self.h, _vp(Asrc), _vp(Omega))
         return Asrc, Omega
+
+    def smooth_config(self, bandwidth, steps, Ddiag=None, flags=15):
+        D = None if Ddiag is None else _f64(Ddiag)
+        self.lib.sedi_smooth_config(self.h, float(bandwidth), int(steps), _vp(D), int(flags))
+
+    def smooth_uf(self):
+        self.lib.sedi_smooth_uf(self.h)
+
+    def smooth_field(self, field):
+        f = np.ascontiguousarray(field, np.float64).copy()
+        ncomp = 1 if f.ndim == 1 else f.shape[1]
+        self.lib.sedi_smooth_field(self.h, _vp(f), ncomp)
+        return f
+
+    def smooth_last_iters(self):
+        return int(self.lib.sedi_smooth_last_iters(self.h))
 
     def enable_diag(self, on=True):
         self.lib.sedi_enable_diag(self.h, 1 if on else 0)

@@ -153,3 +153,58 @@ def test_single_sphere_golden_curve():
     for tt, vv in xiao:
         if tt > 2e-4:
             assert abs(np.interp(tt, t, vy) - vv) < 0.05 * 0.05
+
+
+def test_smoothing_matches_restated_solver(oracle_mod):
+    """diffusion smoothing (SURVEY 8f rank 2): PCG on the GPU against the sparse direct solve of the restatement;
+    conservation of sum(phi V) is the reference's own invariant (enhancedCloud.C:434-435, 975-976)"""
+    case = cases.fluidized_bed(dims=(10, 12, 9))
+    e = make_engine(case)
+    nc = np.array([7, 9, 5], np.int32)
+    e.mesh_box(case["mesh_lo"], case["mesh_hi"], nc)
+    dx = (case["mesh_hi"] - case["mesh_lo"]) / nc
+    rng = np.random.default_rng(4)
+    C = int(np.prod(nc))
+    for b, steps, D in ((2.0 * dx[0], 3, (1.0, 1.0, 1.0)), (4.0 * dx[1], 2, (1.0, 0.0, 2.5))):
+        e.smooth_config(b, steps, D)
+        phi = rng.uniform(0.0, 1.0, size=C); vec = rng.normal(size=(C, 3))
+        ref_s = oracle_mod.smooth_field(phi, nc, dx, b, steps, D)
+        ref_v = oracle_mod.smooth_field(vec, nc, dx, b, steps, D)
+        got_s = e.smooth_field(phi); got_v = e.smooth_field(vec)
+        assert rel_err(got_s, ref_s) < 1e-10 and rel_err(got_v, ref_v) < 1e-10
+        assert abs(got_s.sum() - phi.sum()) < 1e-10 * phi.sum()
+        assert np.abs(got_v.sum(axis=0) - vec.sum(axis=0)).max() < 1e-9 * np.abs(vec).sum()
+        assert got_s.std() < phi.std() and 0 < e.smooth_last_iters() < 200
+
+
+def test_scatter_with_smoothing_flags(oracle_mod):
+    """alphaSmooth / UpSmooth / dragSmooth wired into particleToEulerianField and calcTcFields in the reference's order"""
+    case = cases.fluidized_bed(dims=(12, 14, 12), vjit=0.05)
+    e = make_engine(case)
+    e.mesh_box(case["mesh_lo"], case["mesh_hi"], case["mesh_n"])
+    e.coupling_config(DRAG_ERGUN_WENYU, FORCE_DRAG | FORCE_PGRAD, case["nub"], case["rhob"], case["g"], 2e-4)
+    nc = case["mesh_n"]; dx = (case["mesh_hi"] - case["mesh_lo"]) / nc
+    b, steps = 2.0e-3, 2
+    st = e.atoms(); e.setup(); st = e.atoms()
+    cell = oracle_mod.cell_owner(st["x"], case["mesh_lo"], case["mesh_hi"], nc)
+    d = 2.0 * st["radius"]; C = int(np.prod(nc)); cellV = np.full(C, np.prod(dx))
+    # reference order (enhancedCloud.C:932-962): /V, smooth gamma, smooth Ue, then Ue /= gamma
+    g0, _ = oracle_mod.particle_to_eulerian(cell, d, st["v"], cellV)
+    mom = np.zeros((C, 3)); vol = np.pi / 6 * d ** 3
+    np.add.at(mom, cell[cell >= 0], (vol[:, None] * st["v"])[cell >= 0])
+    mom /= cellV[:, None]
+    g_ref = oracle_mod.smooth_field(g0, nc, dx, b, steps)
+    m_ref = oracle_mod.smooth_field(mom, nc, dx, b, steps)
+    Ue_ref = np.where(g_ref[:, None] > 1e-150, m_ref / np.maximum(g_ref[:, None], 1e-300), m_ref)
+    e.smooth_config(b, steps, None, 2 | 8)
+    g, Ue = e.scatter_alpha_u()
+    assert rel_err(g, g_ref) < 1e-9 and rel_err(Ue, Ue_ref) < 1e-8
+    assert abs(g.sum() / g0.sum() - 1.0) < 1e-10
+    # dragSmooth: Asrc (1-gamma) -> smooth -> / (1-gamma)
+    Uf = np.tile([0.0, 0.05, 0.0], (C, 1))
+    e.put_cell_fields(Uf, g_ref, None)
+    A0, _ = oracle_mod.calc_tc(cell, d, st["v"], Uf, g_ref, cellV, DRAG_ERGUN_WENYU, case["nub"], case["rhob"])
+    A_ref = oracle_mod.smooth_field(A0 * (1 - g_ref[:, None]), nc, dx, b, steps) / (1 - g_ref[:, None])
+    e.smooth_config(b, steps, None, 4)
+    A, _ = e.calc_tc()
+    assert rel_err(A, A_ref) < 1e-8

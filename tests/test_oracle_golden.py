@@ -47,3 +47,20 @@ def test_xiaocase3_velocity_curve(oracle_mod):
         if tt > 2e-4:
             assert abs(np.interp(tt, t, vy) - vv) < 0.05 * 0.05, (tt, vv)
     assert abs(vy[-1] - 0.05) < 1e-4
+
+
+def test_smoothing_restatement_known_answers(oracle_mod):
+    """smoothField restated (enhancedCloud.C:790-907): (1) conserves sum(phi V) -- the reference's own printed check
+    (:434-435, 975-976); (2) a point source spreads to a Gaussian of variance 2 tau = b^2/2 per direction
+    (documentation/diffusionEqn/diffusionEqn.tex:127-141: bandwidth b <-> tau = b^2/4); (3) smoothDirection with a zero
+    entry leaves that direction untouched."""
+    nc = np.array([21, 21, 21]); dx = np.array([1.0, 1.0, 1.0]); C = 21 ** 3
+    phi = np.zeros(C); phi[10 + 21 * (10 + 21 * 10)] = 1.0
+    out = oracle_mod.smooth_field(phi, nc, dx, 4.0, 8).reshape(21, 21, 21)   # [k][j][i]
+    assert abs(out.sum() - 1.0) < 1e-12
+    x = np.arange(21) - 10
+    for ax in range(3):
+        prof = out.sum(axis=tuple(a for a in range(3) if a != ax))
+        assert abs((prof * x ** 2).sum() - 8.0) < 0.1
+    out2 = oracle_mod.smooth_field(phi, nc, dx, 4.0, 8, (1.0, 0.0, 1.0)).reshape(21, 21, 21)
+    assert np.count_nonzero(out2.sum(axis=(0, 2)) > 1e-15) == 1   # nothing leaked along y (axis 1 of [k][j][i])
