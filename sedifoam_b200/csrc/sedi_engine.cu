@@ -1358,7 +1358,7 @@ int sedi_comm_unique_id(void *out, int cap) { return sedi::Comm::unique_id(out, 
 int sedi_comm_rank(void *ptr) { return E(ptr)->comm.rank; }
 long long sedi_comm_stat(void *ptr, int which) {
   Engine *e = E(ptr);
-  switch (which) { case 0: return e->comm.halo_calls; case 1: return e->comm.total_send; case 2: return e->comm.total_recv; case 3: return (long long)e->comm.links.size(); case 4: return e->comm.narr_last; default: return -1; }
+  switch (which) { case 0: return e->comm.halo_calls; case 1: return e->comm.total_send; case 2: return e->comm.total_recv; case 3: return (long long)e->comm.links.size(); case 4: return e->comm.narr_last; case 5: return e->comm.p2p ? 1 : 0; default: return -1; }
 }
 /* pure host logic of the brick decomposition (no GPU, no NCCL): used by the CPU tests */
 void sedi_decomp_grid(int nranks, const double *boxlen, int *grid) { sedi::decomp_auto_grid(nranks, boxlen, grid); }
