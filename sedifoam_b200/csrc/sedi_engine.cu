@@ -561,8 +561,7 @@ class Engine {
     StepParams P;
     fill_launch(P, mode, in, ntimestep);
     const int KT = SEDI_KSTEP_THREADS;
-    const int blocks = cdiv(nlocal, KT);
-    if (!blocks) return;
+    const int blocks = std::max(1, cdiv(nlocal, KT));   // an empty brick still counts its sub-steps (ctrl[1])
     const bool tl = P.has_cohesive || P.lub_enabled;
     switch (cfg().pair) {
       case PAIR_HERTZFIX_HISTORY:

@@ -208,3 +208,29 @@ def test_scatter_with_smoothing_flags(oracle_mod):
     e.smooth_config(b, steps, None, 4)
     A, _ = e.calc_tc()
     assert rel_err(A, A_ref) < 1e-8
+
+
+def test_create_and_delete_particles(oracle_mod):
+    """lammps_create_particle / lammps_delete_particle (library.cpp:406-621): counts, tags, masses with the reference's
+    pi literal, and the run continues with the new population"""
+    case = cases.fluidized_bed(dims=(5, 5, 5), vjit=0.0)
+    e = make_engine(case)
+    e.command("group active type 1")
+    e.step(20)
+    n0 = e.get_local_n()
+    top = case["box_hi"].copy()
+    pos = np.array([[0.5 * top[0], 0.9 * top[1], 0.5 * top[2]], [0.25 * top[0], 0.9 * top[1], 0.25 * top[2]]])
+    e.create_particle(pos, [1001.0, 1002.0], 4.0e-4, 2500.0, 1, (0.0, -0.1, 0.0))
+    assert e.get_local_n() == n0 + 2 and e.get_global_n() == n0 + 2
+    e.step(20)
+    st = e.atoms()
+    k = int(np.flatnonzero(st["tag"] == 1001)[0])
+    r = 2.0e-4
+    assert st["radius"][k] == r and st["rmass"][k] == 4.0 * 3.14159265358917323846 / 3.0 * r * r * r * 2500.0
+    assert st["v"][k, 1] < -0.1           # it has been falling under gravity
+    e.delete_particle([1002, int(case["tag"][0])])
+    assert e.get_local_n() == n0
+    e.step(20)
+    st = e.atoms()
+    assert 1002 not in st["tag"] and case["tag"][0] not in st["tag"] and 1001 in st["tag"]
+    assert np.isfinite(st["x"]).all()

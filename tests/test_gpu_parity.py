@@ -21,6 +21,11 @@ SCENARIOS = {
     "cohesive_opt0": (lambda: cases.cohesive_shear_bed(dims=(10, 8, 10), opt=0), 300),
     "lubricate_poly": (lambda: cases.poly_lubricated(dims=(10, 10, 10)), 200),
     "frozen_floor": (lambda: _frozen(cases.sediment_column(dims=(8, 12, 8), phi=0.50, jitter_frac=0.02)), 300),
+    # skin = d: rows of ~32 neighbours, mostly not touching (the skin of cases/example-cases/transport-bedload/in.lammps:12);
+    # exercises the look-ahead ring refill of k_step and the growth of the ELL capacity
+    "hertz_large_skin": (lambda: cases.fluidized_bed(dims=(9, 10, 9), skin_frac=1.0, vjit=0.05), 300),
+    # ragged rows: polydisperse radii, random positions from a dilute lattice with large jitter, periodic box
+    "hertz_polydisperse": (lambda: _poly(cases.sediment_column(dims=(9, 14, 9), phi=0.25, jitter_frac=0.3)), 400),
 }
 
 
@@ -40,6 +45,14 @@ def _frozen(case):
     case["ntypes"] = 2
     case["script"] = case["script"].replace("fix 1 all nve/sphere", "group bed type 2\ngroup mobile subtract all bed\nfix 1 mobile nve/sphere")
     case["script"] += "fix fz bed freeze\n"
+    return case
+
+
+def _poly(case):
+    rng = np.random.default_rng(23)
+    n = len(case["tag"])
+    case["diam"] = case["diam"] * rng.uniform(0.6, 1.0, size=n)
+    case["v"] = rng.normal(scale=0.2, size=(n, 3))
     return case
 
 
@@ -159,3 +172,27 @@ def test_step_split_invariance(oracle_mod):
     a, b = e1.atoms(), e2.atoms()
     for k in ("x", "v", "omega"):
         assert np.array_equal(a[k], b[k])
+
+
+def test_edge_cases_empty_single_and_lost_particle(oracle_mod):
+    """empty system, one particle, and a particle that leaves a non-periodic box (it stays owned, LAMMPS `lost ignore`
+    is not modelled: the reference inputs abort on lost atoms, thermo_modify lost error)"""
+    case = cases.fluidized_bed(dims=(2, 2, 2))
+    for k in ("tag", "type", "diam", "rho"):
+        case[k] = case[k][:0]
+    case["x"] = case["x"][:0]; case["v"] = case["v"][:0]
+    e = make_engine(case)
+    e.step(5)
+    assert e.get_local_n() == 0 and e.stat("pair_evals") == 0
+    e.mesh_box(case["mesh_lo"], case["mesh_hi"], case["mesh_n"])
+    g, Ue = e.scatter_alpha_u()
+    assert g.sum() == 0.0
+    e.close()
+    one = cases.fluidized_bed(dims=(1, 1, 1), vjit=0.0)
+    one["script"] = "\n".join(ln for ln in one["script"].splitlines() if "wall/granFix" not in ln)
+    one["v"][:] = (3.0, 0.0, 0.0)     # flies out of the box in x
+    o = make_oracle(oracle_mod, one); e = make_engine(one)
+    o.run(500); e.step(500)
+    a, b = o.atoms(), e.atoms()
+    assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["v"], b["v"])
+    assert b["x"][0, 0] > one["box_hi"][0]
