@@ -38,48 +38,72 @@ SUBSTEPS = 100               # DEM sub-steps per coupling step (shipped cases: d
 # --------------------------------------------------------------------------------------------------------------
 # CPU side: the reference's own objects (kind "reference") or the port, on the host cores
 # --------------------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    dims, nsteps, kind, seed = args
+_CPU = {}
+
+
+def _cpu_init(dims, kind, seed_base, counter):
+    """worker start-up (once): build this worker's sub-domain replica of the bed and run LAMMPS' setup on it"""
     from oracle import pyoracle
     from sedifoam_b200 import cases
-    case = cases.fluidized_bed(dims=dims, seed=seed)
+    with counter.get_lock():
+        r = counter.value
+        counter.value += 1
+    case = cases.fluidized_bed(dims=dims, seed=seed_base + r)
     o = pyoracle.Oracle(kind)
     cases.apply(case, o)
     o.setup()
     n = len(case["tag"])
     m = case["rho"] * np.pi / 6.0 * case["diam"] ** 3
     o.put_fdrag(np.tile([0.0, 9.8 * 0.3, 0.0], (n, 1)) * m[:, None], case["tag"])
+    _CPU["o"] = o
+    _CPU["n"] = n
+
+
+def _cpu_step(nsteps):
+    o = _CPU["o"]
     e0 = o.stat("pair_evals")
     t0 = time.perf_counter()
     o.run(nsteps)
     dt = time.perf_counter() - t0
-    return o.stat("pair_evals") - e0, dt, n
+    return o.stat("pair_evals") - e0, dt, _CPU["n"]
+
+
+class CpuArm:
+    """`cores` independent sub-domain replicas of the bed (1/cores of the particles each, no halo exchange), one per
+    host core: an upper bound for a `cores`-rank MPI run of the reference, which has no threading of its own.  The
+    force kernels are the reference's own sources (oracle/_ref) when that library is present, else the port."""
+
+    def __init__(self, cores, dims_total=BED_DIMS):
+        import multiprocessing as mp
+        from oracle import pyoracle
+        self.kind = "reference" if pyoracle.have_reference() else "port"
+        self.cores = cores
+        f = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[cores]
+        self.dims = tuple(max(2, dims_total[k] // f[k]) for k in range(3))
+        ctx = mp.get_context("spawn")
+        counter = ctx.Value("i", 0)
+        self.pool = ctx.Pool(cores, initializer=_cpu_init, initargs=(self.dims, self.kind, 20261017, counter))
+
+    def step(self, nsteps):
+        res = self.pool.map(_cpu_step, [nsteps] * self.cores, chunksize=1)
+        evals = sum(r[0] for r in res); tmax = max(r[1] for r in res); npart = sum(r[2] for r in res)
+        return dict(value=evals / tmax / 1e6, unit=UNIT, cores=self.cores, kind=self.kind,
+                    sample="%d particles (%d sub-domain replicas of %s, no halo), %d DEM sub-steps, %.1f s" %
+                           (npart, self.cores, "x".join(map(str, self.dims)), nsteps, tmax),
+                    seconds=tmax, pair_evals=evals)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 def cpu_throughput(nsteps, cores, dims_total=BED_DIMS):
-    """`cores` independent sub-domain replicas of the bed (1/cores of the particles each, no halo exchange): an upper
-    bound for a `cores`-rank MPI run of the reference, which has no threading of its own."""
-    import multiprocessing as mp
-    from oracle import pyoracle
-    kind = "reference" if pyoracle.have_reference() else "port"
-    if cores == 1:
-        dims = dims_total
-    else:
-        f = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[cores]
-        dims = tuple(max(2, dims_total[k] // f[k]) for k in range(3))
-    jobs = [(dims, nsteps, kind, 20261017 + r) for r in range(cores)]
-    if cores == 1:
-        res = [_cpu_worker(jobs[0])]
-    else:
-        with mp.get_context("spawn").Pool(cores) as pool:
-            res = pool.map(_cpu_worker, jobs)
-    evals = sum(r[0] for r in res)
-    tmax = max(r[1] for r in res)
-    npart = sum(r[2] for r in res)
-    return dict(value=evals / tmax / 1e6, unit=UNIT, cores=cores, kind=kind,
-                sample="%d particles (%d sub-domain replicas of %s, no halo), %d DEM sub-steps, %.1f s" %
-                       (npart, cores, "x".join(map(str, dims)), nsteps, tmax),
-                seconds=tmax, pair_evals=evals)
+    arm = CpuArm(cores, dims_total)
+    try:
+        arm.step(max(1, nsteps // 10))   # warm the caches / first-touch the arrays
+        return arm.step(nsteps)
+    finally:
+        arm.close()
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -177,12 +201,14 @@ def main():
         # each "step" of the reference arm is a bounded sample: `nsteps` DEM sub-steps of the same bed on all host cores
         vals = []
         t_all = time.perf_counter()
+        arm = CpuArm(cores, dims)
         for it in range(W + K):
-            r = cpu_throughput(nsteps, cores, dims)
+            r = arm.step(nsteps)
             if it >= W:
                 vals.append(r)
             if time.perf_counter() - t_all > 240 and len(vals) >= 1:
                 break
+        arm.close()
         v = float(np.mean([r["value"] for r in vals]))
         ms = float(np.mean([r["seconds"] for r in vals])) * 1e3
         line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": W, "ms_per_step": ms,
