@@ -64,3 +64,48 @@ def test_smoothing_restatement_known_answers(oracle_mod):
         assert abs((prof * x ** 2).sum() - 8.0) < 0.1
     out2 = oracle_mod.smooth_field(phi, nc, dx, 4.0, 8, (1.0, 0.0, 1.0)).reshape(21, 21, 21)
     assert np.count_nonzero(out2.sum(axis=(0, 2)) > 1e-15) == 1   # nothing leaked along y (axis 1 of [k][j][i])
+
+
+GOLD4 = os.path.join(HERE, "golden", "multiParticlesCollideDia")
+
+
+def check_four_spheres(rows):
+    """rows[n] = state sorted by tag after (n+1)*1000 DEM steps, against data/origin/p{1..4}.dat (LAMMPS `dump custom`
+    rows `id type diameter mass x y z vx vy vz`, 6 significant digits).  The fluid is prescribed quiescent here (no
+    PISO solver in this image), so the fluid entrained by the spheres in the real run is missing: the isolated spheres
+    1 and 4 settle 1.4 % slower than the golden terminal velocity; the pair 2/3, which starts overlapping and is
+    thrown apart along x, ends within 4 mm of the golden end points after 75 mm of travel."""
+    for p in range(4):
+        g = np.loadtxt(os.path.join(GOLD4, "p%d.dat" % (p + 1)))
+        assert g.shape == (21, 10)
+        vt = np.abs(g[:, 8]).max()
+        ex = max(np.abs(rows[n]["x"][p] - g[n + 1][4:7]).max() for n in range(20))
+        ev = max(np.abs(rows[n]["v"][p] - g[n + 1][7:10]).max() for n in range(20))
+        if p in (0, 3):
+            assert ev < 0.025 * vt and ex < 1.0e-3, (p, ex, ev)
+        else:
+            assert ex < 4.0e-3 and ev < 0.2 * vt, (p, ex, ev)
+        assert abs(rows[0]["radius"][p] * 2 - g[0][2]) < 1e-12 and abs(rows[0]["rmass"][p] / g[0][3] - 1) < 1e-5
+
+
+def test_four_spheres_golden_dump(oracle_mod):
+    case = cases.four_spheres_collide()
+    o = make_oracle(oracle_mod, case)
+    o.setup()
+    lo, hi, nc = case["mesh_lo"], case["mesh_hi"], case["mesh_n"]
+    C = int(np.prod(nc)); cellV = np.full(C, np.prod((hi - lo) / nc))
+    Uf, _, gradp = cases.uniform_fields(case)
+    radius = 0.5 * case["diam"]; rmass = case["rho"] * 4.0 * np.pi / 3.0 * radius ** 3
+    rows = []
+    for k in range(400):   # 200 fluid steps x subCycles 2 x 50 DEM steps
+        a = o.atoms()
+        cell = oracle_mod.cell_owner(a["x"], lo, hi, nc)
+        gam, _ = oracle_mod.particle_to_eulerian(cell, case["diam"], a["v"], cellV)
+        fr = oracle_mod.particle_force(cell, case["diam"], a["v"], a["v"], Uf, gam, gradp, None, None, oracle_mod.DRAG_SYAMLAL_OBRIEN,
+                                       oracle_mod.FORCE_DRAG | oracle_mod.FORCE_PGRAD, case["nub"], case["rhob"], np.zeros(3), 1e-3)
+        o.put_fdrag(fr["F"], a["tag"])
+        o.run(50)
+        if (k + 1) % 20 == 0:
+            a = o.atoms(); a["radius"] = radius; a["rmass"] = rmass
+            rows.append(a)
+    check_four_spheres(rows)
