@@ -71,6 +71,11 @@ struct StepParams {
   const unsigned *nbr;
   D4 *shear;                  // [slot * npad + i], .w unused
   unsigned long long *tmask;  // touching-slot mask per particle
+  // row-contiguous form of the list (k_step_rows): entries of row i are [off[i], off[i+1]), in ELL slot order
+  const int *off;
+  const unsigned *cnbr;        // list words, same encoding as nbr
+  const unsigned char *crow;   // owner row & 255 of every entry
+  double *hx, *hy, *hz;        // contact history planes, one value per directed entry
   double *f[3], *tq[3];       // stored force/torque (written by SETUP/LAST, read by the initial-integrate kernel)
   double *fdrag[3], *dudt[3], *vold[3];
   double *xhold[3];
@@ -105,6 +110,21 @@ struct BinParams {
   double lo[3], inv[3];  // bin = floor((x - lo) * inv)
   int nb[3];
   int periodic[3];
+  int tile[2];           // row order: x-major bins (tile = 1 x 1) or TX x TY bin tiles in the x-y plane, tile-major
 };
+
+// position of bin (bx, by, bz) in the sorted row order.  Plain: x-major.  Tiled: the bins of a TX x TY tile are
+// contiguous (x fastest inside the tile), tiles x-major, then z -- a block of consecutive rows is then a compact
+// x-y patch of the bed whose in-plane neighbours are mostly inside the same block.
+__host__ __device__ inline int cell_index(int bx, int by, int bz, const int nb[3], const int tile[2]) {
+  const int TX = tile[0], TY = tile[1];
+  if (TX <= 1 && TY <= 1) return bx + nb[0] * (by + nb[1] * bz);
+  const int ntx = (nb[0] + TX - 1) / TX, nty = (nb[1] + TY - 1) / TY;
+  return (((bz * nty + by / TY) * ntx + bx / TX) * TY + by % TY) * TX + bx % TX;
+}
+__host__ __device__ inline long long cell_count(const int nb[3], const int tile[2]) {
+  const int TX = tile[0] > 1 ? tile[0] : 1, TY = tile[1] > 1 ? tile[1] : 1;
+  return (long long)(((nb[0] + TX - 1) / TX) * TX) * (((nb[1] + TY - 1) / TY) * TY) * nb[2];
+}
 
 }  // namespace sedi

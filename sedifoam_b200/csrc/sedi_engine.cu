@@ -30,6 +30,7 @@
 #include "sedi_device.cuh"
 #include "sedi_neigh.cuh"
 #include "sedi_step.cuh"
+#include "sedi_rows.cuh"
 #include "sedi_couple.cuh"
 #include "sedi_smooth.cuh"
 #include "sedi_halo.cuh"
@@ -103,7 +104,15 @@ struct Ell {  // directed neighbour list + contact history, slot-major
   Buf<D4> shear;
   int npad, cap;
   bool valid;
-  Ell() : npad(0), cap(0), valid(false) {}
+  // row-contiguous form of the same list (k_step_rows): offsets, list words, owner-row byte, history planes
+  Buf<int> off;
+  Buf<unsigned> cnbr;
+  Buf<unsigned char> crow;
+  Buf<double> hx, hy, hz;
+  long long nentries;
+  bool rows_valid;     // the row form exists
+  bool hist_in_rows;   // the live contact history is in hx/hy/hz (the ELL quads are stale)
+  Ell() : npad(0), cap(0), valid(false), nentries(0), rows_valid(false), hist_in_rows(false) {}
 };
 
 // small pack / unpack kernels of the C-ABI boundary -------------------------------------------------------
@@ -210,6 +219,7 @@ class Engine {
   long long pair_evals_unique;
   long long nbuilds, pair_evals, steps_done, launches, list_gran_dir, list_type_dir, list_gran_img, list_type_img;
   int chunk;
+  bool use_rows;   // pair sweep on the ELL slot walk (default) or on the row-block kernel (SEDI_KSTEP_PATH=rows)
   double last_step_ms;
   bool count_in_kernel;
   // boundary staging
@@ -249,6 +259,9 @@ class Engine {
     memset(&mesh, 0, sizeof(mesh));
     const char *e = getenv("SEDI_CHUNK");
     if (e && atoi(e) > 0) chunk = atoi(e);
+    use_rows = false;
+    e = getenv("SEDI_KSTEP_PATH");
+    if (e && !strcmp(e, "rows")) use_rows = true;
     e = getenv("SEDI_DEVICE");
     if (e) device = atoi(e);
     else if ((e = getenv("LOCAL_RANK"))) device = atoi(e);
@@ -261,7 +274,8 @@ class Engine {
     cudaStreamSynchronize(stream);
     // device memory is released with the process; explicit frees keep long-lived hosts clean
     for (int k = 0; k < 2; k++) { posr[k].release(); velm[k].release(); omgt[k].release(); wmask[k].release(); foam[k].release();
-      ell[k].nbr.release(); ell[k].nn.release(); ell[k].tmask.release(); ell[k].shear.release(); }
+      ell[k].nbr.release(); ell[k].nn.release(); ell[k].tmask.release(); ell[k].shear.release();
+      ell[k].off.release(); ell[k].cnbr.release(); ell[k].crow.release(); ell[k].hx.release(); ell[k].hy.release(); ell[k].hz.release(); }
     Plane2 *groups[] = {f, tq, fdrag, dudt, vold, uold, xhold};
     for (size_t g = 0; g < sizeof(groups) / sizeof(groups[0]); g++) for (int d = 0; d < 3; d++) { groups[g][d].b[0].release(); groups[g][d].b[1].release(); }
     for (int w = 0; w < MAX_WALLS; w++) for (int d = 0; d < 3; d++) { wshear[w][d].b[0].release(); wshear[w][d].b[1].release(); }
@@ -384,7 +398,7 @@ class Engine {
     }
     alloc_rows(rows);
     cur = 0; icur = 0; ecur = 0;
-    ell[0].valid = ell[1].valid = false;
+    ell[0].valid = ell[1].valid = false; ell[0].rows_valid = ell[1].rows_valid = false; ell[0].hist_in_rows = ell[1].hist_in_rows = false;
     if (n) {
       CK(cudaMemcpyAsync(posr[0].p, hp.data(), n * sizeof(D4), cudaMemcpyHostToDevice, stream));
       CK(cudaMemcpyAsync(velm[0].p, hv.data(), n * sizeof(D4), cudaMemcpyHostToDevice, stream));
@@ -453,6 +467,11 @@ class Engine {
     // one bin >= the largest neighbour cut-off, 27-cell stencil; periodic dimensions are tiled exactly
     long long total = 1;
     double grow = 1.0;
+    bin.tile[0] = bin.tile[1] = 1;
+    if (const char *e = getenv("SEDI_BIN_TILE")) {   // "TXxTY": tile-major row order (see cell_index)
+      int tx = 1, ty = 1;
+      if (sscanf(e, "%dx%d", &tx, &ty) == 2 && tx >= 1 && ty >= 1 && tx <= 64 && ty <= 64) { bin.tile[0] = tx; bin.tile[1] = ty; }
+    }
     for (int pass = 0; pass < 40; pass++) {
       total = 1;
       for (int d = 0; d < 3; d++) {
@@ -467,13 +486,14 @@ class Engine {
       if (total <= (1ll << 26)) break;
       grow *= 1.3;
     }
+    total = cell_count(bin.nb, bin.tile);
     bin.n = n;
     cellcount.ensure((size_t)total + 2); cellstart.ensure((size_t)total + 2); cellfill.ensure((size_t)total + 2);
     blocksum.ensure((size_t)cdiv(total + 2, SCAN_ITEMS) + 1);
     if (comm.nranks > 1) comm.setup_decomp(*this);
   }
 
-  long long ncells_bin() const { return (long long)bin.nb[0] * bin.nb[1] * bin.nb[2]; }
+  long long ncells_bin() const { return cell_count(bin.nb, bin.tile); }
 
   void build_base_params() {
     StepParams &P = base;
@@ -534,6 +554,7 @@ class Engine {
     P.n = nlocal;
     Ell &L = ell[ecur];
     P.npad = L.npad; P.nn = L.nn.p; P.nbr = L.nbr.p; P.shear = L.shear.p; P.tmask = L.tmask.p;
+    P.off = L.off.p; P.cnbr = L.cnbr.p; P.crow = L.crow.p; P.hx = L.hx.p; P.hy = L.hy.p; P.hz = L.hz.p;
     P.posr_in = posr[in].p; P.velm_in = velm[in].p; P.omgt_in = omgt[in].p;
     P.posr_out = posr[in ^ 1].p; P.velm_out = velm[in ^ 1].p; P.omgt_out = omgt[in ^ 1].p;
     for (int d = 0; d < 3; d++) {
@@ -563,6 +584,18 @@ class Engine {
     const int KT = SEDI_KSTEP_THREADS;
     const int blocks = std::max(1, cdiv(nlocal, KT));   // an empty brick still counts its sub-steps (ctrl[1])
     const bool tl = P.has_cohesive || P.lub_enabled;
+    if (ell[ecur].rows_valid && !tl && cfg().pair != PAIR_NONE) {   // row-block kernel: one directed entry per thread
+      const int RT = SEDI_ROWS_THREADS;
+      const int rb = std::max(1, cdiv(nlocal, RT));
+      ell[ecur].hist_in_rows = true;   // from here on the live history is in the planes
+      switch (cfg().pair) {
+        case PAIR_HERTZFIX_HISTORY: k_step_rows<PAIR_HERTZFIX_HISTORY><<<rb, RT, 0, stream>>>(P, seq); break;
+        case PAIR_HOOKE_HISTORY: k_step_rows<PAIR_HOOKE_HISTORY><<<rb, RT, 0, stream>>>(P, seq); break;
+        default: k_step_rows<PAIR_HOOKE><<<rb, RT, 0, stream>>>(P, seq); break;
+      }
+      launches++;
+      return;
+    }
     switch (cfg().pair) {
       case PAIR_HERTZFIX_HISTORY:
         if (tl) k_step<PAIR_HERTZFIX_HISTORY, true><<<blocks, KT, 0, stream>>>(P, seq);
@@ -594,8 +627,46 @@ class Engine {
   }
 
   // ---- neighbour rebuild (EXTERNAL Verlet: pre_exchange history save, pbc, exchange, borders, Neighbor::build) ---
+  // bring the contact history back into the ELL quads (re-attachment at the next rebuild, migration packing and
+  // sedi_get_pairs read it there)
+  void rows_history_to_ell() {
+    Ell &L = ell[ecur];
+    if (!L.valid || !L.rows_valid || !L.hist_in_rows) return;
+    if (nlocal && L.nentries)
+      k_rows_history_to_ell<<<cdiv(nlocal, 128), 128, 0, stream>>>(nlocal, L.npad, L.nn.p, L.off.p, L.tmask.p, L.hx.p, L.hy.p, L.hz.p, L.shear.p);
+    launches++;
+    L.hist_in_rows = false;
+  }
+
+  // compact the fresh ELL list (and the history re-attached to it) into the row-contiguous form
+  void build_rows(Ell &L) {
+    L.rows_valid = false; L.hist_in_rows = false; L.nentries = 0;
+    const SimConfig &c = cfg();
+    if (!use_rows || c.pair == PAIR_NONE || want_type_list()) return;
+    const int T = 256;
+    const int nscan = nlocal + 1;
+    L.off.ensure((size_t)nscan + 1);
+    CK(cudaMemsetAsync(L.nn.p + nlocal, 0, sizeof(int), stream));   // nn has npad_ell + 1 slots
+    const int nblk = cdiv(nscan, SCAN_ITEMS);
+    blocksum.ensure((size_t)nblk + 1);
+    k_scan_local<<<nblk, 1024, 0, stream>>>(L.nn.p, L.off.p, nscan, blocksum.p);
+    k_scan_sums<<<1, 1024, 0, stream>>>(blocksum.p, nblk);
+    k_scan_add<<<cdiv(nscan, T), T, 0, stream>>>(L.off.p, nscan, blocksum.p, 0);
+    CK(cudaMemcpyAsync(h_ctrl.p + 5, L.off.p + nlocal, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    L.nentries = h_ctrl.p[5];
+    const size_t cap_e = (size_t)L.nentries + 256;
+    L.cnbr.ensure(cap_e); L.crow.ensure(cap_e); L.hx.ensure(cap_e); L.hy.ensure(cap_e); L.hz.ensure(cap_e);
+    if (nlocal)
+      k_rows_fill<<<cdiv(nlocal, 128), 128, 0, stream>>>(nlocal, L.npad, L.nn.p, L.off.p, L.nbr.p, L.shear.p, L.tmask.p, L.cnbr.p, L.crow.p,
+                                                         L.hx.p, L.hy.p, L.hz.p);
+    launches += 4;
+    L.rows_valid = true;
+  }
+
   void rebuild() {
     need_device();
+    rows_history_to_ell();
     const SimConfig &c = cfg();
     const int T = 256;
     const int n_old = nlocal + nghost;  // rows that are valid in quads[cur] (ghost rows are dropped by the sort)
@@ -663,7 +734,7 @@ class Engine {
     memset(&B, 0, sizeof(B));
     B.n = nlocal; B.want_gran = (c.pair != PAIR_NONE); B.want_type = want_type_list() ? 1 : 0; B.ntypes = c.ntypes;
     B.posr = posr[cur].p; B.omgt = omgt[cur].p; B.cellstart = cellstart.p;
-    for (int d = 0; d < 3; d++) { B.nb[d] = bin.nb[d]; B.periodic[d] = bin.periodic[d]; B.lo[d] = bin.lo[d]; B.inv[d] = bin.inv[d]; B.prd[d] = c.boxhi[d] - c.boxlo[d]; }
+    for (int d = 0; d < 3; d++) { B.nb[d] = bin.nb[d]; if (d < 2) B.tile[d] = bin.tile[d]; B.periodic[d] = bin.periodic[d]; B.lo[d] = bin.lo[d]; B.inv[d] = bin.inv[d]; B.prd[d] = c.boxhi[d] - c.boxlo[d]; }
     B.skin = c.skin;
     memcpy(B.cutneighsq, cutneighsq, sizeof(cutneighsq));
     B.have_old = (Lo.valid || narr > 0) ? 1 : 0; B.npad_old = Lo.npad; B.oldidx = order.p;
@@ -678,7 +749,7 @@ class Engine {
     if (Ln.cap < 12) Ln.cap = std::max(Lo.cap, 12);   // k_step reads the first nine list words of every row unconditionally
     for (int attempt = 0; attempt < 3; attempt++) {
       Ln.npad = npad_ell;
-      Ln.nn.ensure(npad_ell); Ln.tmask.ensure(npad_ell);
+      Ln.nn.ensure((size_t)npad_ell + 1); Ln.tmask.ensure(npad_ell);
       if (Ln.cap > 0) { Ln.nbr.ensure((size_t)Ln.cap * npad_ell); Ln.shear.ensure((size_t)Ln.cap * npad_ell); }
       B.npad = Ln.npad; B.cap = Ln.cap; B.nbr = Ln.nbr.p; B.nn = Ln.nn.p; B.tmask = Ln.tmask.p; B.shear = Ln.shear.p;
       CK(cudaMemsetAsync(ctrl.p + 3, 0, sizeof(int), stream));
@@ -698,7 +769,8 @@ class Engine {
     }
     list_gran_dir = (long long)h_counters.p[0]; list_type_dir = (long long)h_counters.p[1];
     list_gran_img = (long long)h_counters.p[2]; list_type_img = (long long)h_counters.p[3];
-    Ln.valid = true; Lo.valid = false;
+    Ln.valid = true; Lo.valid = false; Lo.rows_valid = false; Lo.hist_in_rows = false;
+    build_rows(Ln);
     ecur ^= 1;
     nbuilds++;
     cell_valid = false;
@@ -889,6 +961,7 @@ class Engine {
   long long get_pairs(int *ti, int *tj, unsigned *meta, int *touch, double *shear, long long capacity) {
     if (!setup_done) setup();
     need_device();
+    rows_history_to_ell();
     Ell &L = ell[ecur];
     const int n = nlocal;
     std::vector<int> hn(n), rs(n + 1, 0);

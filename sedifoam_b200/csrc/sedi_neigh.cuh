@@ -22,7 +22,7 @@ struct BuildParams {
   int want_gran, want_type, ntypes;
   const D4 *posr, *omgt;
   const int *cellstart;
-  int nb[3], periodic[3];
+  int nb[3], periodic[3], tile[2];
   double lo[3], inv[3], prd[3];
   double skin;
   double cutneighsq[(MAX_TYPES + 1) * (MAX_TYPES + 1)];
@@ -76,7 +76,7 @@ __global__ void k_wrap_bin(D4 *posr, const D4 *omgt, int n, BinParams B, double 
   const int cx = bin_coord(p.x, B.lo[0], B.inv[0], B.nb[0]);
   const int cy = bin_coord(p.y, B.lo[1], B.inv[1], B.nb[1]);
   const int cz = bin_coord(p.z, B.lo[2], B.inv[2], B.nb[2]);
-  const int c = cx + B.nb[0] * (cy + B.nb[1] * cz);
+  const int c = cell_index(cx, cy, cz, B.nb, B.tile);
   cellid[i] = c;
   atomicAdd(&cellcount[c], 1);
 }
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(128) k_build_list(const __grid_constant__ Buil
             int bx = cx + dx, ix = 0;
             if (bx < 0) { if (!B.periodic[0]) continue; bx += B.nb[0]; ix = -1; }
             else if (bx >= B.nb[0]) { if (!B.periodic[0]) continue; bx -= B.nb[0]; ix = 1; }
-            const int c = bx + B.nb[0] * (by + B.nb[1] * bz);
+            const int c = cell_index(bx, by, bz, B.nb, B.tile);
             const int img = (ix + 1) + 3 * (iy + 1) + 9 * (iz + 1);
             const int js = B.cellstart[c], je = B.cellstart[c + 1];
             for (int j = js; j < je; j++) visit(j, img, ix, iy, iz);
