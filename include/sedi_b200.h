@@ -98,11 +98,22 @@ int sedi_mesh_ncells(void *ptr);
 #define SEDI_FORCE_BUOY_BIT 4
 #define SEDI_FORCE_ADDEDMASS_BIT 8
 #define SEDI_FORCE_LIFT_BIT 16
+#define SEDI_FORCE_HISTORY_BIT 32   /* particleHistoryForce, enhancedCloud.C:197-234 (single GPU) */
+#define SEDI_FORCE_WALL_LUB_BIT 64  /* lubricationForce against the y = 0 wall, enhancedCloud.C:235-248 */
+#define SEDI_FORCE_INLET_BIT 128    /* inletForce inside inletBox, enhancedCloud.C:249-257 */
 void sedi_coupling_config(void *ptr, int drag_model, int force_flags, double nub, double rhob, const double *g,
                           double deltaT);
 /* host cell fields -> device (Uf, gradp, DDtU, curlU are [C][3]; gamma is [C]); NULL = leave unchanged / absent */
 void sedi_put_cell_fields(void *ptr, const double *Uf, const double *gamma, const double *gradp, const double *DDtU,
                           const double *curlU);
+/* runTime().timeIndex() seen by the next sedi_compute_fluid_force (it then advances by one per call); history force only */
+void sedi_coupling_time_index(void *ptr, int time_index);
+/* inletForce vector, inletBox (x1 x2 y1 y2 z1 z2 r1 r2 -), addParticleOption (1 box, 2 hollow cylinder) and
+ * addParticleBoxEccentricity of constant/cloudProperties (softParticleCloud.C:471, :1354-1415) */
+void sedi_coupling_inlet(void *ptr, const double *inlet_force, const double *inlet_box, int region_option,
+                         const double *eccentricity);
+/* history-force state per owned particle in sedi_get_state row order: sumDeltaFb[n][3], n0[n] (softParticle.H:104-107) */
+void sedi_get_history_state(void *ptr, double *sumDeltaFb, double *n0);
 /* locate particles in cells (cell owner index, int32, -1 = outside) */
 void sedi_locate(void *ptr);
 /* updateParticleUr + updateParticleAlpha + Jd + updateDragOnParticles: writes fix fdrag's per-atom force on device */

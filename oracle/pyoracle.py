@@ -58,6 +58,8 @@ def _load(kind):
     lib.ora_foam_particle_force.argtypes = [C.c_int, _ip, _dp, _dp, _dp, _dp, _dp, _dp, C.c_void_p, C.c_void_p,
                                             C.c_int, C.c_int, C.c_double, C.c_double, _dp, C.c_double,
                                             _dp, _dp, _dp, _dp, _dp, _dp]
+    lib.ora_foam_particle_force_extra.argtypes = [C.c_int, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_double,
+                                                  C.c_double, C.c_int, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp]
     lib.ora_foam_cell_owner.argtypes = [C.c_int, _dp, _dp, _dp, _ip, _ip]
     lib.ora_foam_particle_to_eulerian.argtypes = [C.c_int, _ip, _dp, _dp, C.c_int, _dp, _dp, _dp]
     lib.ora_foam_calc_tc.argtypes = [C.c_int, _ip, _dp, _dp, _dp, _dp, C.c_int, _dp, C.c_int, C.c_double, C.c_double, _dp, _dp]
@@ -190,6 +192,19 @@ def particle_force(cell, d, U, UOld, Uf, gamma, gradp, DDtU, curlU, model, flags
     lib.ora_foam_particle_force(n, np.ascontiguousarray(cell, np.int32), c(d), c(U), c(UOld), c(Uf), c(gamma), c(gradp),
                                 _ptr(DDtU), _ptr(curlU), model, flags, nub, rhob, c(g), deltaT, Uri, mag, al, Jd, F, DuDt)
     return dict(Uri=Uri, magUri=mag, alpha=al, Jd=Jd, F=F, DuDt=DuDt)
+
+
+def particle_force_extra(cell, x, d, mass, U, UOld, Uf, UfOld, flags, nub, rhob, deltaT, time_index, sumDeltaFb, n0, F,
+                         inlet_force=(0, 0, 0), inlet_box=(0,) * 9, region_option=0, ecc=(0, 0, 0), kind="port"):
+    """history (32) / wall-lubrication (64) / inlet (128) branches of updateDragOnParticles applied to F in place;
+    sumDeltaFb and n0 are the per-particle history state, updated in place"""
+    lib = _load(kind)
+    c = lambda a: np.ascontiguousarray(a, np.float64)
+    assert F.flags.c_contiguous and sumDeltaFb.flags.c_contiguous and n0.flags.c_contiguous
+    lib.ora_foam_particle_force_extra(len(cell), np.ascontiguousarray(cell, np.int32), c(x), c(d), c(mass), c(U), c(UOld), c(Uf), c(UfOld),
+                                      flags, nub, rhob, deltaT, time_index, sumDeltaFb, n0, c(inlet_force), c(inlet_box), region_option,
+                                      c(ecc), F)
+    return F
 
 
 def cell_owner(x, lo, hi, ncell, kind="port"):

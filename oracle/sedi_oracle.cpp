@@ -222,6 +222,84 @@ void ora_foam_particle_force(int n, const int *cell, const double *d, const doub
   }
 }
 
+// The remaining branches of updateDragOnParticles, applied ON TOP of ora_foam_particle_force's pDrag (the reference
+// evaluates them in this order inside the same loop body, enhancedCloud.C:197-257):
+//   history force   :197-234  reduced-order Basset model (Elghannay & Tafti 2016), per-particle state sumDeltaFb, n0
+//   wall lubrication :235-248  y = 0 wall, active for 1e-4 d < gap < 0.1 d
+//   inlet forcing   :249-257  REPLACES the force inside the inlet region (softParticleCloud::pointInRegion :1354-1415)
+// flags: 32 history, 64 lubrication, 128 inlet.  region_option = addParticleOption (1 box, 2 hollow cylinder).
+static double ora_g1n(double n) {  // enhancedCloud.C:1372-1384
+  if (n < 1) return 0.9279;
+  return 0.9279 * (2 * n - 1) / n * pow(n, -n / (2 * n - 1)) + 0.001531;
+}
+static bool ora_point_in_region(const double *pt, const double *box, int option, const double *ecc) {
+  const double x1 = box[0], x2 = box[1], y1 = box[2], y2 = box[3], z1 = box[4], z2 = box[5], r1 = box[6], r2 = box[7];
+  if (option == 1)
+    return (pt[0] - x1) * (pt[0] - x2) < ROOTVSMALL && (pt[1] - y1) * (pt[1] - y2) < ROOTVSMALL && (pt[2] - z1) * (pt[2] - z2) < ROOTVSMALL;
+  if (option == 2) {
+    const double a[3] = {x2 - x1, y2 - y1, z2 - z1};
+    const double h = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    const double b[3] = {pt[0] - x1, pt[1] - y1, pt[2] - z1};
+    const double dot = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+    const double be[3] = {b[0] - ecc[0], b[1] - ecc[1], b[2] - ecc[2]};
+    if (dot < 0.0 || dot > pow(h, 2)) return false;
+    const double dsq = (b[0] * b[0] + b[1] * b[1] + b[2] * b[2]) - dot * dot / pow(h, 2);
+    const double dsqE = (be[0] * be[0] + be[1] * be[1] + be[2] * be[2]) - dot * dot / pow(h, 2);
+    return dsqE > r1 * r1 && dsq < r2 * r2;
+  }
+  return false;
+}
+void ora_foam_particle_force_extra(int n, const int *cell, const double *x, const double *d, const double *mass, const double *U,
+                                   const double *UOld, const double *Uf, const double *UfOld, int flags, double nub, double rhob,
+                                   double deltaT, int timeIndex, double *sumDeltaFb, double *n0, const double *inletForce,
+                                   const double *inletBox, int region_option, const double *ecc, double *pDrag) {
+  for (int i = 0; i < n; i++) {
+    const int c = cell[i];
+    if (c < 0) continue;
+    double *F = &pDrag[3 * i];
+    if (flags & 32) {
+      const double tau_d = pow(d[i], 2) / nub;
+      double Uri[3], UriOld[3], mU = 0, mUo = 0;
+      for (int k = 0; k < 3; k++) { Uri[k] = Uf[3 * c + k] - U[3 * i + k]; UriOld[k] = UfOld[3 * c + k] - UOld[3 * i + k]; mU += Uri[k] * Uri[k]; mUo += UriOld[k] * UriOld[k]; }
+      const double ReP = sqrt(mU) * d[i] / nub, RePOld = sqrt(mUo) * d[i] / nub;
+      const double q = 0.632 / (ReP + ROOTVSMALL) + 0.087, qo = 0.632 / (RePOld + ROOTVSMALL) + 0.087;
+      const double tau_h = tau_d * (q * q), tau_h_old = tau_d * (qo * qo);
+      const double Cb = -1.5 * (d[i] * d[i]) * rhob * pow((3.1416 * nub), 0.5);
+      const double nTotal = timeIndex;
+      const double tau_t = deltaT * (nTotal - n0[i]);
+      double FH[3];
+      double *S = &sumDeltaFb[3 * i];
+      double dfb[3];
+      for (int k = 0; k < 3; k++) dfb[k] = Cb * ((U[3 * i + k] - UOld[3 * i + k]) / deltaT) / sqrt(deltaT);
+      if (tau_t < tau_h) {
+        const double dn = nTotal - n0[i];
+        for (int k = 0; k < 3; k++) S[k] = S[k] + dfb[k];
+        const double g = ora_g1n(dn);
+        for (int k = 0; k < 3; k++) FH[k] = g * S[k];
+      } else {
+        for (int k = 0; k < 3; k++) S[k] = tau_h / tau_h_old * S[k];
+        const double dn = tau_h / deltaT;
+        for (int k = 0; k < 3; k++) S[k] = (dn - 1) / dn * S[k];
+        n0[i] = nTotal - dn;
+        for (int k = 0; k < 3; k++) S[k] = S[k] + dfb[k];
+        const double g = ora_g1n(dn);
+        for (int k = 0; k < 3; k++) FH[k] = g * S[k];
+      }
+      for (int k = 0; k < 3; k++) F[k] += FH[k] * deltaT;
+    }
+    if (flags & 64) {
+      const double distMin = 0.0001 * d[i], distMax = 0.1 * d[i];
+      const double distWall = x[3 * i + 1] - 0.5 * d[i];
+      const double pVel = U[3 * i + 1];
+      if (distWall < distMax && distWall > distMin) F[1] += 6 * 3.1416 * nub * rhob * (-pVel) / distWall * (d[i] * d[i]) / 4.0;
+    }
+    if ((flags & 128) && sqrt(inletForce[0] * inletForce[0] + inletForce[1] * inletForce[1] + inletForce[2] * inletForce[2]) > 0) {
+      if (ora_point_in_region(&x[3 * i], inletBox, region_option, ecc))
+        for (int k = 0; k < 3; k++) F[k] = mass[i] * (inletForce[k] - U[3 * i + k]) / deltaT;
+    }
+  }
+}
+
 // Cell owner on a single-block axis-aligned uniform blockMesh: cell = i + nx (j + ny k)  (SURVEY 8a15, Appendix B2).
 // Points outside the block get -1 (the reference deletes such particles on the Foam side, softParticle.C:177-184).
 void ora_foam_cell_owner(int n, const double *x, const double *lo, const double *hi, const int *ncell, int *cell) {

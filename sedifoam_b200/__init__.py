@@ -9,5 +9,6 @@ raises immediately.
 from .lib import Lammps, build_library, library_path, load_library, EXPORTED_SYMBOLS  # noqa: F401
 from .lib import decomp_grid, decomp_owner, decomp_links  # noqa: F401
 from .lib import DRAG_ERGUN_WENYU, DRAG_SYAMLAL_OBRIEN, FORCE_DRAG, FORCE_PGRAD, FORCE_BUOY, FORCE_ADDEDMASS, FORCE_LIFT  # noqa: F401
+from .lib import FORCE_HISTORY, FORCE_WALL_LUB, FORCE_INLET  # noqa: F401
 
 __all__ = ["Lammps", "build_library", "library_path", "load_library", "EXPORTED_SYMBOLS"]

@@ -23,7 +23,33 @@ struct MeshBox {  // single-block uniform hex mesh: cell = i + nx (j + ny k)
 };
 
 enum { SEDI_DRAG_ERGUN_WENYU = 0, SEDI_DRAG_SYAMLAL_OBRIEN = 1 };
-enum { SEDI_FORCE_DRAG = 1, SEDI_FORCE_PGRAD = 2, SEDI_FORCE_BUOY = 4, SEDI_FORCE_ADDEDMASS = 8, SEDI_FORCE_LIFT = 16 };
+enum { SEDI_FORCE_DRAG = 1, SEDI_FORCE_PGRAD = 2, SEDI_FORCE_BUOY = 4, SEDI_FORCE_ADDEDMASS = 8, SEDI_FORCE_LIFT = 16,
+       SEDI_FORCE_HISTORY = 32, SEDI_FORCE_WALL_LUB = 64, SEDI_FORCE_INLET = 128 };
+
+// enhancedCloud::g1n (enhancedCloud.C:1372-1384)
+__device__ __forceinline__ double g1n(double n) {
+  if (n < 1) return 0.9279;
+  return 0.9279 * (2 * n - 1) / n * pow(n, -n / (2 * n - 1)) + 0.001531;
+}
+// softParticleCloud::pointInRegion (softParticleCloud.C:1354-1415): option 1 = box, option 2 = hollow cylinder
+// between the axis points (x1,y1,z1) and (x2,y2,z2) with radii r1 < r2 and an eccentric inner hole
+__device__ __forceinline__ bool point_in_region(double px, double py, double pz, const double *box, int option, const double *ecc) {
+  const double x1 = box[0], x2 = box[1], y1 = box[2], y2 = box[3], z1 = box[4], z2 = box[5], r1 = box[6], r2 = box[7];
+  if (option == 1)
+    return (px - x1) * (px - x2) < kROOTVSMALL && (py - y1) * (py - y2) < kROOTVSMALL && (pz - z1) * (pz - z2) < kROOTVSMALL;
+  if (option == 2) {
+    const double a0 = x2 - x1, a1 = y2 - y1, a2 = z2 - z1;
+    const double h = sqrt(a0 * a0 + a1 * a1 + a2 * a2);
+    const double b0 = px - x1, b1 = py - y1, b2 = pz - z1;
+    const double dot = a0 * b0 + a1 * b1 + a2 * b2;
+    const double e0 = b0 - ecc[0], e1 = b1 - ecc[1], e2 = b2 - ecc[2];
+    if (dot < 0.0 || dot > pow(h, 2.0)) return false;
+    const double dsq = (b0 * b0 + b1 * b1 + b2 * b2) - dot * dot / pow(h, 2.0);
+    const double dsqE = (e0 * e0 + e1 * e1 + e2 * e2) - dot * dot / pow(h, 2.0);
+    return dsqE > r1 * r1 && dsq < r2 * r2;
+  }
+  return false;
+}
 
 __device__ __forceinline__ double jd_closure(int model, double Ur, double alpha, double pd, double nuf, double rhof) {
   const double beta = fmax(1.0 - alpha, kROOTVSMALL);
@@ -64,6 +90,13 @@ struct ForceParams {
   double *fdrag[3], *dudt[3];                        // outputs: fix fdrag's per-atom arrays
   double *Uri, *magUri, *alphap, *Jd;                // optional diagnostics (interleaved / scalar), may be null
   double nub, rhob, g[3], deltaT;
+  // history force (enhancedCloud.C:197-234): previous fluid velocity field, per-particle sumDeltaFb / n0, fluid step index
+  const double *UfOld;
+  double *hsum[3], *hn0;
+  int timeIndex;
+  // inlet forcing (:249-257)
+  double inletForce[3], inletBox[9], inletEcc[3];
+  int inletOption;
 };
 
 __global__ void __launch_bounds__(256) k_particle_force(const __grid_constant__ ForceParams P) {
@@ -98,6 +131,48 @@ __global__ void __launch_bounds__(256) k_particle_force(const __grid_constant__ 
       const double coef = 1.6 * P.rhob * sqrt(P.nub) * (d * d);
       const double s = sqrt(magw + kROOTVSMALL);
       F0 += coef * (u1 * w2 - u2 * w1) / s; F1 += coef * (u2 * w0 - u0 * w2) / s; F2 += coef * (u0 * w1 - u1 * w0) / s;
+    }
+  }
+  if (c >= 0 && (P.flags & (SEDI_FORCE_HISTORY | SEDI_FORCE_WALL_LUB | SEDI_FORCE_INLET))) {
+    if (P.flags & SEDI_FORCE_HISTORY) {  // reduced-order Basset history force, Elghannay & Tafti 2016 (:197-234)
+      const double tau_d = pow(d, 2.0) / P.nub;
+      const double o0 = P.uold[0][i], o1 = P.uold[1][i], o2 = P.uold[2][i];
+      const double q0 = P.UfOld[3 * (size_t)c] - o0, q1 = P.UfOld[3 * (size_t)c + 1] - o1, q2 = P.UfOld[3 * (size_t)c + 2] - o2;
+      const double ReP = mag * d / P.nub, RePOld = sqrt(q0 * q0 + q1 * q1 + q2 * q2) * d / P.nub;
+      const double qa = 0.632 / (ReP + kROOTVSMALL) + 0.087, qb = 0.632 / (RePOld + kROOTVSMALL) + 0.087;
+      const double tau_h = tau_d * (qa * qa), tau_h_old = tau_d * (qb * qb);
+      const double Cb = -1.5 * (d * d) * P.rhob * pow((3.1416 * P.nub), 0.5);
+      const double nTotal = P.timeIndex;
+      double n0 = P.hn0[i];
+      const double tau_t = P.deltaT * (nTotal - n0);
+      const double sdt = sqrt(P.deltaT);
+      const double b0 = Cb * ((v.x - o0) / P.deltaT) / sdt, b1 = Cb * ((v.y - o1) / P.deltaT) / sdt, b2 = Cb * ((v.z - o2) / P.deltaT) / sdt;
+      double S0 = P.hsum[0][i], S1 = P.hsum[1][i], S2 = P.hsum[2][i], g;
+      if (tau_t < tau_h) {
+        const double dn = nTotal - n0;
+        S0 = S0 + b0; S1 = S1 + b1; S2 = S2 + b2;
+        g = g1n(dn);
+      } else {
+        S0 = tau_h / tau_h_old * S0; S1 = tau_h / tau_h_old * S1; S2 = tau_h / tau_h_old * S2;
+        const double dn = tau_h / P.deltaT;
+        S0 = (dn - 1) / dn * S0; S1 = (dn - 1) / dn * S1; S2 = (dn - 1) / dn * S2;
+        n0 = nTotal - dn;
+        S0 = S0 + b0; S1 = S1 + b1; S2 = S2 + b2;
+        g = g1n(dn);
+      }
+      P.hsum[0][i] = S0; P.hsum[1][i] = S1; P.hsum[2][i] = S2; P.hn0[i] = n0;
+      F0 += (g * S0) * P.deltaT; F1 += (g * S1) * P.deltaT; F2 += (g * S2) * P.deltaT;
+    }
+    if (P.flags & SEDI_FORCE_WALL_LUB) {  // lubrication against the y = 0 wall (:235-248)
+      const double distMin = 0.0001 * d, distMax = 0.1 * d;
+      const double distWall = x.y - 0.5 * d;
+      if (distWall < distMax && distWall > distMin) F1 += 6 * 3.1416 * P.nub * P.rhob * (-v.y) / distWall * (d * d) / 4.0;
+    }
+    if ((P.flags & SEDI_FORCE_INLET) &&
+        sqrt(P.inletForce[0] * P.inletForce[0] + P.inletForce[1] * P.inletForce[1] + P.inletForce[2] * P.inletForce[2]) > 0) {
+      if (point_in_region(x.x, x.y, x.z, P.inletBox, P.inletOption, P.inletEcc)) {  // replaces the force (:253)
+        F0 = v.w * (P.inletForce[0] - v.x) / P.deltaT; F1 = v.w * (P.inletForce[1] - v.y) / P.deltaT; F2 = v.w * (P.inletForce[2] - v.z) / P.deltaT;
+      }
     }
   }
   P.fdrag[0][i] = F0; P.fdrag[1][i] = F1; P.fdrag[2][i] = F2;

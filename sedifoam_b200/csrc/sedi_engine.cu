@@ -197,6 +197,13 @@ class Engine {
   int cur;
   Plane2 f[3], tq[3], fdrag[3], dudt[3], vold[3], uold[3], xhold[3];
   Plane2 wshear[MAX_WALLS][3];
+  Plane2 hist[4];            // history-force state: sumDeltaFb xyz, n0 (allocated when SEDI_FORCE_HISTORY is configured)
+  bool hist_alloc;
+  Buf<double> UfOld;         // fluid velocity field of the previous coupling step (UfSmoothed_.oldTime())
+  bool have_UfOld;
+  int time_index;            // runTime().timeIndex() of the next fluid_force call
+  double inlet_force[3], inlet_box[9], inlet_ecc[3];
+  int inlet_option;
   Buf<unsigned> wmask[2];
   Buf<int> foam[2];
   int icur;  // which of wmask/foam is live
@@ -233,7 +240,7 @@ class Engine {
   int ncells;
   Buf<int> cell;
   Buf<double> Uf, gamma, gradp, DDtU, curlU, cellV, Ue, Asrc;
-  bool have_DDtU, have_curlU, have_gradp;
+  bool have_DDtU, have_curlU, have_gradp, have_Uf;
   int drag_model, force_flags;
   double nub, rhob, gvec[3], deltaT;
   Buf<double> dg_Uri, dg_mag, dg_alpha, dg_Jd;
@@ -250,9 +257,10 @@ class Engine {
         nlocal(0), nghost(0), npad(0), maxtag(0), cur(0), icur(0), ecur(0), cutneighmax(0), dt_init(0), lub_R0(0), lub_RT0(0), lub_RS0(0),
         beta_pair(0), pair_evals_unique(0), nbuilds(0), pair_evals(0), steps_done(0), launches(0), list_gran_dir(0), list_type_dir(0), list_gran_img(0),
         list_type_img(0), chunk(16), last_step_ms(0), count_in_kernel(false), have_mesh(false), ncells(0), have_DDtU(false),
-        have_curlU(false), have_gradp(false), drag_model(0), force_flags(SEDI_FORCE_DRAG | SEDI_FORCE_PGRAD), nub(1e-6), rhob(1000.0),
-        deltaT(1.0), want_diag(false), smooth_b(0.0), smooth_steps(0), smooth_flags(0), smooth_iters_last(0), prof_on(false), prof_ms(0), prof_steps(0) {
+        have_curlU(false), have_gradp(false), have_Uf(false), drag_model(0), force_flags(SEDI_FORCE_DRAG | SEDI_FORCE_PGRAD), nub(1e-6), rhob(1000.0),
+        deltaT(1.0), hist_alloc(false), have_UfOld(false), time_index(0), inlet_option(0), want_diag(false), smooth_b(0.0), smooth_steps(0), smooth_flags(0), smooth_iters_last(0), prof_on(false), prof_ms(0), prof_steps(0) {
     gvec[0] = gvec[1] = gvec[2] = 0.0;
+    memset(inlet_force, 0, sizeof(inlet_force)); memset(inlet_box, 0, sizeof(inlet_box)); memset(inlet_ecc, 0, sizeof(inlet_ecc));
     smooth_D[0] = smooth_D[1] = smooth_D[2] = 1.0;
     memset(&base, 0, sizeof(base));
     memset(&bin, 0, sizeof(bin));
@@ -398,6 +406,7 @@ class Engine {
     }
     alloc_rows(rows);
     cur = 0; icur = 0; ecur = 0;
+    hist_alloc = false;   // history-force state restarts with the atom table (softParticle.C:63-64: n0 = 0, sumDeltaFb = 0)
     ell[0].valid = ell[1].valid = false; ell[0].rows_valid = ell[1].rows_valid = false; ell[0].hist_in_rows = ell[1].hist_in_rows = false;
     if (n) {
       CK(cudaMemcpyAsync(posr[0].p, hp.data(), n * sizeof(D4), cudaMemcpyHostToDevice, stream));
@@ -710,6 +719,7 @@ class Engine {
       Plane2 *groups[] = {f, tq, fdrag, dudt, vold, uold};
       for (int g = 0; g < NPLANES_BASE; g++) for (int d = 0; d < 3; d++) { L.src[L.nplanes] = groups[g][d].get(); L.dst[L.nplanes] = groups[g][d].alt(); L.nplanes++; }
       for (int w = 0; w < c.nwalls; w++) for (int d = 0; d < 3; d++) { L.src[L.nplanes] = wshear[w][d].get(); L.dst[L.nplanes] = wshear[w][d].alt(); L.nplanes++; }
+      if (hist_alloc) for (int d = 0; d < 4; d++) { L.src[L.nplanes] = hist[d].get(); L.dst[L.nplanes] = hist[d].alt(); L.nplanes++; }
       k_permute_planes<<<cdiv(nlocal_new, T), T, 0, stream>>>(order.p, nlocal_new, L);
       launches += 2;
     }
@@ -717,6 +727,7 @@ class Engine {
       Plane2 *groups[] = {f, tq, fdrag, dudt, vold, uold};
       for (int g = 0; g < NPLANES_BASE; g++) for (int d = 0; d < 3; d++) groups[g][d].cur ^= 1;
       for (int w = 0; w < c.nwalls; w++) for (int d = 0; d < 3; d++) wshear[w][d].cur ^= 1;
+      if (hist_alloc) for (int d = 0; d < 4; d++) hist[d].cur ^= 1;
     }
     const int oldq = cur;
     cur ^= 1; icur ^= 1;
@@ -1001,6 +1012,23 @@ class Engine {
     d.release();
   }
 
+  // history-force state in device row order (rows match sedi_get_state)
+  void get_history_state(double *sum, double *n0) {
+    need_device();
+    const int m = nlocal;
+    if (!m) return;
+    if (!hist_alloc) { if (sum) memset(sum, 0, 3 * (size_t)m * sizeof(double)); if (n0) memset(n0, 0, (size_t)m * sizeof(double)); return; }
+    Buf<double> d;
+    d.ensure(3 * (size_t)m);
+    if (sum) {
+      k_interleave3<<<cdiv(m, 256), 256, 0, stream>>>(hist[0].get(), hist[1].get(), hist[2].get(), m, d.p);
+      CK(cudaMemcpyAsync(sum, d.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    }
+    if (n0) CK(cudaMemcpyAsync(n0, hist[3].get(), (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    d.release();
+  }
+
   void set_omega(int m, const int *tag, const double *w) {
     if (!loaded) load_atoms();
     if (!setup_done) setup();
@@ -1034,7 +1062,11 @@ class Engine {
     if (!have_mesh) fatal("sedi_put_cell_fields: call sedi_mesh_box first");
     need_device();
     const size_t C = ncells;
-    if (hUf) CK(cudaMemcpyAsync(Uf.p, hUf, 3 * C * sizeof(double), cudaMemcpyHostToDevice, stream));
+    if (hUf && (force_flags & SEDI_FORCE_HISTORY)) {  // the field about to be replaced becomes UfSmoothed_.oldTime()
+      UfOld.ensure(3 * C);
+      if (have_Uf) { CK(cudaMemcpyAsync(UfOld.p, Uf.p, 3 * C * sizeof(double), cudaMemcpyDeviceToDevice, stream)); have_UfOld = true; }
+    }
+    if (hUf) { CK(cudaMemcpyAsync(Uf.p, hUf, 3 * C * sizeof(double), cudaMemcpyHostToDevice, stream)); have_Uf = true; }
     if (hgamma) CK(cudaMemcpyAsync(gamma.p, hgamma, C * sizeof(double), cudaMemcpyHostToDevice, stream));
     if (hgradp) CK(cudaMemcpyAsync(gradp.p, hgradp, 3 * C * sizeof(double), cudaMemcpyHostToDevice, stream));
     if (hDDtU) { CK(cudaMemcpyAsync(DDtU.p, hDDtU, 3 * C * sizeof(double), cudaMemcpyHostToDevice, stream)); have_DDtU = true; }
@@ -1056,6 +1088,18 @@ class Engine {
     if (!cell_valid) locate();
     if ((force_flags & SEDI_FORCE_ADDEDMASS) && !have_DDtU) fatal("added-mass force needs DDtU");
     if ((force_flags & SEDI_FORCE_LIFT) && !have_curlU) fatal("lift force needs curlU");
+    if (force_flags & SEDI_FORCE_HISTORY) {
+      if (comm.nranks > 1) fatal("particleHistoryForce: the per-particle history state does not migrate between GPUs yet (single GPU only)");
+      if (!hist_alloc) {  // softParticle starts with n0 = 0, sumDeltaFb = 0 (softParticle.C:63-64)
+        for (int d = 0; d < 4; d++) for (int b = 0; b < 2; b++) { hist[d].b[b].ensure(npad); CK(cudaMemsetAsync(hist[d].b[b].p, 0, (size_t)npad * sizeof(double), stream)); }
+        hist_alloc = true;
+      }
+      if (!have_UfOld) {  // first step: oldTime() == current field
+        UfOld.ensure(3 * (size_t)ncells);
+        CK(cudaMemcpyAsync(UfOld.p, Uf.p, 3 * (size_t)ncells * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+        have_UfOld = true;
+      }
+    }
     ForceParams P;
     memset(&P, 0, sizeof(P));
     P.n = nlocal; P.model = drag_model; P.flags = force_flags;
@@ -1068,6 +1112,12 @@ class Engine {
     }
     P.nub = nub; P.rhob = rhob; P.deltaT = deltaT;
     for (int d = 0; d < 3; d++) P.g[d] = gvec[d];
+    P.UfOld = UfOld.p; P.timeIndex = time_index;
+    if (hist_alloc) { for (int d = 0; d < 3; d++) P.hsum[d] = hist[d].get(); P.hn0 = hist[3].get(); }
+    for (int d = 0; d < 3; d++) { P.inletForce[d] = inlet_force[d]; P.inletEcc[d] = inlet_ecc[d]; }
+    for (int d = 0; d < 9; d++) P.inletBox[d] = inlet_box[d];
+    P.inletOption = inlet_option;
+    time_index++;
     if (nlocal) k_particle_force<<<cdiv(nlocal, 256), 256, 0, stream>>>(P);
     launches++;
   }
@@ -1203,7 +1253,7 @@ class Engine {
 
   // UOld = U before the particles are advanced (softParticleCloud.C:571-572); only the added-mass force reads it
   void save_uold_if_ready() {
-    if (!loaded || !setup_done || !(force_flags & SEDI_FORCE_ADDEDMASS) || !nlocal) return;
+    if (!loaded || !setup_done || !(force_flags & (SEDI_FORCE_ADDEDMASS | SEDI_FORCE_HISTORY)) || !nlocal) return;
     need_device();
     k_save_uold<<<cdiv(nlocal, 256), 256, 0, stream>>>(velm[cur].p, nlocal, uold[0].get(), uold[1].get(), uold[2].get());
     launches++;
@@ -1402,6 +1452,14 @@ void sedi_coupling_config(void *ptr, int drag_model, int force_flags, double nub
   e->drag_model = drag_model; e->force_flags = force_flags; e->nub = nub; e->rhob = rhob; e->deltaT = deltaT;
   for (int d = 0; d < 3; d++) e->gvec[d] = g ? g[d] : 0.0;
 }
+void sedi_coupling_time_index(void *ptr, int time_index) { E(ptr)->time_index = time_index; }
+void sedi_coupling_inlet(void *ptr, const double *inlet_force, const double *inlet_box, int region_option, const double *eccentricity) {
+  Engine *e = E(ptr);
+  for (int d = 0; d < 3; d++) { e->inlet_force[d] = inlet_force ? inlet_force[d] : 0.0; e->inlet_ecc[d] = eccentricity ? eccentricity[d] : 0.0; }
+  for (int d = 0; d < 9; d++) e->inlet_box[d] = inlet_box ? inlet_box[d] : 0.0;
+  e->inlet_option = region_option;
+}
+void sedi_get_history_state(void *ptr, double *sumDeltaFb, double *n0) { E(ptr)->get_history_state(sumDeltaFb, n0); }
 void sedi_put_cell_fields(void *ptr, const double *Uf, const double *gamma, const double *gradp, const double *DDtU, const double *curlU) {
   E(ptr)->put_cell_fields(Uf, gamma, gradp, DDtU, curlU);
 }

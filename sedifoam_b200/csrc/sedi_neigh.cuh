@@ -159,7 +159,7 @@ __global__ void k_cell_sort(const int *cellstart, int ncells, int ntot, int *ord
   }
 }
 
-struct PlaneList { int nplanes; const double *src[40]; double *dst[40]; };
+struct PlaneList { int nplanes; const double *src[48]; double *dst[48]; };
 
 // gather the three state quads into cell order; record xhold, the tag map and the old<->new index maps
 __global__ void k_permute_quads(const int *order, int n, const D4 *posr_s, const D4 *velm_s, const D4 *omgt_s, D4 *posr_d,

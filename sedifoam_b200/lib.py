@@ -10,6 +10,7 @@ _LIB = None
 
 DRAG_ERGUN_WENYU, DRAG_SYAMLAL_OBRIEN = 0, 1
 FORCE_DRAG, FORCE_PGRAD, FORCE_BUOY, FORCE_ADDEDMASS, FORCE_LIFT = 1, 2, 4, 8, 16
+FORCE_HISTORY, FORCE_WALL_LUB, FORCE_INLET = 32, 64, 128
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -24,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "sedi_get_state", "sedi_get_pairs", "sedi_get_wall_shear", "sedi_force_rebuild", "sedi_get_stat", "sedi_reset_stats",
     "sedi_synchronize", "sedi_stream", "sedi_last_step_ms", "sedi_timer_start", "sedi_timer_stop_ms", "sedi_profile",
     "sedi_get_profile", "sedi_mesh_box", "sedi_mesh_ncells", "sedi_coupling_config",
-    "sedi_put_cell_fields", "sedi_locate", "sedi_compute_fluid_force", "sedi_scatter_alpha_u", "sedi_calc_tc",
+    "sedi_put_cell_fields", "sedi_coupling_time_index", "sedi_coupling_inlet", "sedi_get_history_state", "sedi_locate", "sedi_compute_fluid_force", "sedi_scatter_alpha_u", "sedi_calc_tc",
     "sedi_enable_diag", "sedi_get_coupling_diag", "sedi_step", "sedi_comm_init", "sedi_comm_unique_id", "sedi_comm_rank", "sedi_comm_stat",
     "sedi_decomp_grid", "sedi_decomp_owner", "sedi_decomp_links", "sedi_smooth_config", "sedi_smooth_uf", "sedi_smooth_field",
     "sedi_smooth_last_iters",
@@ -107,6 +108,9 @@ def load_library():
         "sedi_mesh_ncells": (i, [vp]),
         "sedi_coupling_config": (None, [vp, i, i, d, d, vp, d]),
         "sedi_put_cell_fields": (None, [vp] + [vp] * 5),
+        "sedi_coupling_time_index": (None, [vp, i]),
+        "sedi_coupling_inlet": (None, [vp, vp, vp, i, vp]),
+        "sedi_get_history_state": (None, [vp, vp, vp]),
         "sedi_locate": (None, [vp]),
         "sedi_compute_fluid_force": (None, [vp]),
         "sedi_scatter_alpha_u": (None, [vp, vp, vp]),
@@ -337,6 +341,24 @@ class Lammps:
     def coupling_config(self, drag_model, force_flags, nub, rhob, g=(0, 0, 0), deltaT=1.0):
         g = _f64(g)
         self.lib.sedi_coupling_config(self.h, drag_model, force_flags, nub, rhob, _vp(g), deltaT)
+
+    def coupling_time_index(self, time_index):
+        self.lib.sedi_coupling_time_index(self.h, int(time_index))
+
+    def coupling_inlet(self, inlet_force, inlet_box, region_option=1, eccentricity=(0, 0, 0)):
+        box = np.zeros(9); box[:len(inlet_box)] = inlet_box
+        f = _f64(inlet_force); e = _f64(eccentricity)
+        self.lib.sedi_coupling_inlet(self.h, _vp(f), _vp(box), int(region_option), _vp(e))
+
+    def history_state(self):
+        """(sumDeltaFb[n][3], n0[n]) sorted by tag"""
+        n = self.get_local_n()
+        s = np.zeros((n, 3)); n0 = np.zeros(n)
+        self.lib.sedi_get_history_state(self.h, _vp(s), _vp(n0))
+        tag = np.zeros(n, np.int32)
+        self.lib.sedi_get_state(self.h, None, None, None, None, None, None, None, _vp(tag), None, None)
+        o = np.argsort(tag, kind="stable")
+        return s[o], n0[o]
 
     def put_cell_fields(self, Uf=None, gamma=None, gradp=None, DDtU=None, curlU=None):
         a = [None if f is None else _f64(f) for f in (Uf, gamma, gradp, DDtU, curlU)]

@@ -255,3 +255,58 @@ def test_four_spheres_golden_dump_gpu(oracle_mod):
         if (k + 1) % 20 == 0:
             rows.append(e.atoms())
     check_four_spheres(rows)
+
+
+def test_coupling_history_lubrication_inlet_terms(oracle_mod):
+    """the last three branches of updateDragOnParticles (enhancedCloud.C:197-257): reduced-order Basset history force
+    carried over four coupling steps (per-particle sumDeltaFb / n0 state, both regimes of the window), lubrication
+    against the y = 0 wall, and inlet forcing inside a box region -- against the restatement, in the reference's order"""
+    from sedifoam_b200 import FORCE_HISTORY, FORCE_WALL_LUB, FORCE_INLET
+    case = cases.fluidized_bed(dims=(10, 8, 9), vjit=0.05)
+    d0 = float(case["diam"][0])
+    case["x"] = case["x"].copy()
+    case["x"][:, 1] += 0.05 * d0                       # bottom layer: wall gap 0.049 d, inside the lubrication window
+    e = make_engine(case)
+    rng = np.random.default_rng(23)
+    flags = FORCE_DRAG | FORCE_PGRAD | FORCE_HISTORY | FORCE_WALL_LUB | FORCE_INLET
+    deltaT = 2.0e-3                                     # tau_h ~ 3 ms here: steps 3 and 4 run in the moving-window regime
+    nub, rhob = case["nub"], case["rhob"]
+    e.mesh_box(case["mesh_lo"], case["mesh_hi"], case["mesh_n"])
+    e.coupling_config(DRAG_ERGUN_WENYU, flags, nub, rhob, case["g"], deltaT)
+    ext = case["box_hi"] - case["box_lo"]
+    box = [case["box_lo"][0], case["box_lo"][0] + 0.3 * ext[0], case["box_lo"][1], case["box_hi"][1], case["box_lo"][2], case["box_hi"][2], 0, 0, 0]
+    inlet = (0.0, 0.01, 0.002)
+    e.coupling_inlet(inlet, box, 1)
+    e.coupling_time_index(1)
+    e.enable_diag(True)
+    n = len(case["tag"])
+    S = np.zeros((n, 3)); n0 = np.zeros(n)
+    e.setup()
+    v_prev = np.zeros((n, 3))                           # softParticle starts with UOld = 0 (softParticle.C:58)
+    Uf_prev = None
+    hit = {"lub": 0, "inlet": 0, "window": 0}
+    for k in range(4):
+        Uf, gamma, gradp, DDtU, curlU = _fields(case, rng)
+        e.put_cell_fields(Uf, gamma, gradp)
+        st = e.atoms()
+        e.compute_fluid_force()
+        dg = e.coupling_diag()
+        cell = oracle_mod.cell_owner(st["x"], case["mesh_lo"], case["mesh_hi"], case["mesh_n"])
+        assert np.array_equal(dg["cell"], cell)
+        dia = 2.0 * st["radius"]
+        ref = oracle_mod.particle_force(cell, dia, st["v"], v_prev, Uf, gamma, gradp, None, None, DRAG_ERGUN_WENYU,
+                                        flags & 31, nub, rhob, np.asarray(case["g"], float), deltaT)
+        F = np.ascontiguousarray(ref["F"])
+        n0_before = n0.copy()
+        oracle_mod.particle_force_extra(cell, st["x"], dia, st["rmass"], st["v"], v_prev, Uf, Uf if Uf_prev is None else Uf_prev,
+                                        flags, nub, rhob, deltaT, 1 + k, S, n0, F, inlet, box, 1)
+        assert rel_err(dg["F"], F) < 1e-11, (k, rel_err(dg["F"], F))
+        Sg, n0g = e.history_state()
+        assert rel_err(Sg, S) < 1e-11 and np.abs(n0g - n0).max() < 1e-9
+        gap = st["x"][:, 1] - 0.5 * dia
+        hit["lub"] += int(((gap < 0.1 * dia) & (gap > 1e-4 * dia)).sum())
+        hit["inlet"] += int((st["x"][:, 0] < box[1]).sum())
+        hit["window"] += int((n0 != n0_before).sum())
+        v_prev = st["v"]; Uf_prev = Uf
+        e.sedi_step(10)
+    assert hit["lub"] > 0 and hit["inlet"] > 0 and hit["window"] > 0   # every branch was exercised
