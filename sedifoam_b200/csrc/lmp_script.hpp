@@ -74,7 +74,24 @@ struct Group {
   int bit;
 };
 
+// `dump ID group custom N file field...` -- the golden-file format of the shipped cases
+// (e.g. cases/auto-testing/test-cases/multiParticlesCollideDia/in.lammps:31).  Text layout = EXTERNAL LAMMPS
+// DumpCustom: header items TIMESTEP / NUMBER OF ATOMS / BOX BOUNDS / ATOMS, one row per atom, "%d " for integer
+// fields and "%g " for doubles.  Rows are written in ascending id (`dump_modify sort id`).
+enum DumpField { DF_ID, DF_TYPE, DF_DIAMETER, DF_RADIUS, DF_MASS, DF_X, DF_Y, DF_Z, DF_VX, DF_VY, DF_VZ, DF_FX, DF_FY, DF_FZ,
+                 DF_OMEGAX, DF_OMEGAY, DF_OMEGAZ, DF_TQX, DF_TQY, DF_TQZ };
+struct DumpSpec {
+  std::string id, path, columns;
+  int groupbit;
+  long long every, last_written;
+  std::vector<int> fields;
+  FILE *fp;
+  DumpSpec() : groupbit(1), every(0), last_written(-1), fp(0) {}
+};
+
 struct SimConfig {
+  std::vector<DumpSpec> dumps;
+  std::string boundary_str[3];
   int periodic[3];
   double boxlo[3], boxhi[3];
   int have_box;
@@ -98,6 +115,7 @@ struct SimConfig {
     memset(&gran, 0, sizeof(gran)); memset(&lub, 0, sizeof(lub)); lub.flagHI = 1; lub.flagVF = 1;
     nwalls = 0; ntimestep = 0; freeze_group_bit = 0;
     Group g; g.name = "all"; g.bit = 1; groups.push_back(g);
+    for (int d = 0; d < 3; d++) boundary_str[d] = "pp";
   }
   int find_group(const std::string &n) const {
     for (size_t i = 0; i < groups.size(); i++) if (groups[i].name == n) return groups[i].bit;
@@ -339,6 +357,31 @@ class Script {
     }
   }
 
+  void apply_dump(const std::vector<std::string> &a) {
+    if (a.size() < 7) fatal("Illegal dump command");
+    if (a[3] != "custom") fatal("Only `dump ID group custom N file fields...` is supported");
+    DumpSpec d;
+    d.id = a[1];
+    d.groupbit = cfg.find_group(a[2]);
+    if (!d.groupbit) fatal("dump: unknown group", a[2].c_str());
+    d.every = atoll(a[4].c_str());
+    if (d.every <= 0) fatal("Illegal dump command: N must be positive");
+    d.path = a[5];
+    static const struct { const char *name; int f; } names[] = {
+        {"id", DF_ID}, {"tag", DF_ID}, {"type", DF_TYPE}, {"diameter", DF_DIAMETER}, {"radius", DF_RADIUS}, {"mass", DF_MASS},
+        {"x", DF_X}, {"y", DF_Y}, {"z", DF_Z}, {"vx", DF_VX}, {"vy", DF_VY}, {"vz", DF_VZ}, {"fx", DF_FX}, {"fy", DF_FY}, {"fz", DF_FZ},
+        {"omegax", DF_OMEGAX}, {"omegay", DF_OMEGAY}, {"omegaz", DF_OMEGAZ}, {"tqx", DF_TQX}, {"tqy", DF_TQY}, {"tqz", DF_TQZ}};
+    for (size_t k = 6; k < a.size(); k++) {
+      int f = -1;
+      for (size_t m = 0; m < sizeof(names) / sizeof(names[0]); m++) if (a[k] == names[m].name) f = names[m].f;
+      if (f < 0) fatal("dump custom: unsupported per-atom field", a[k].c_str());
+      d.fields.push_back(f);
+      d.columns += a[k] + " ";
+    }
+    for (size_t i = 0; i < cfg.dumps.size(); i++) if (cfg.dumps[i].id == d.id) fatal("Reuse of dump ID", d.id.c_str());
+    cfg.dumps.push_back(d);
+  }
+
   // Executes one script line.  Returns an action the engine must perform itself (run / nothing).
   ScriptAction one(const char *line) {
     ScriptAction act;
@@ -346,15 +389,22 @@ class Script {
     if (a.empty()) return act;
     const std::string &c = a[0];
     if (c == "atom_style") { if (a.size() < 2 || a[1] != "sphere") fatal("Only atom_style sphere is supported"); }
-    else if (c == "atom_modify" || c == "communicate" || c == "comm_modify" || c == "dump" || c == "thermo" ||
+    else if (c == "dump") apply_dump(a);
+    else if (c == "undump") {
+      for (size_t i = 0; i < cfg.dumps.size(); i++) if (a.size() > 1 && a[1] == cfg.dumps[i].id) {
+        if (cfg.dumps[i].fp) fclose(cfg.dumps[i].fp);
+        cfg.dumps.erase(cfg.dumps.begin() + i); break;
+      }
+    }
+    else if (c == "atom_modify" || c == "communicate" || c == "comm_modify" || c == "thermo" ||
              c == "thermo_style" || c == "thermo_modify" || c == "restart" || c == "dimension" || c == "echo" ||
-             c == "log" || c == "dump_modify" || c == "undump" || c == "compute" || c == "neigh_modify") {
+             c == "log" || c == "dump_modify" || c == "compute" || c == "neigh_modify") {
       // accepted, no effect on the hot path (neigh_modify delay 0 every 1 check yes is the only mode implemented)
     }
     else if (c == "units") { if (a.size() > 1 && a[1] != "lj") fatal("Only lj units are supported (reference inputs set none)"); }
     else if (c == "boundary") {
       if (a.size() != 4) fatal("Illegal boundary command");
-      for (int d = 0; d < 3; d++) cfg.periodic[d] = (a[d + 1][0] == 'p');
+      for (int d = 0; d < 3; d++) { cfg.periodic[d] = (a[d + 1][0] == 'p'); cfg.boundary_str[d] = a[d + 1].size() == 1 ? a[d + 1] + a[d + 1] : a[d + 1]; }
     }
     else if (c == "newton") { cfg.newton_pair = (a.size() > 1 && a[1] == "on"); }
     else if (c == "processors") {

@@ -276,6 +276,7 @@ class Engine {
   }
 
   ~Engine() {
+    for (size_t k = 0; k < script.cfg.dumps.size(); k++) if (script.cfg.dumps[k].fp) { fclose(script.cfg.dumps[k].fp); script.cfg.dumps[k].fp = 0; }
     if (!dev_ready) return;
     cudaSetDevice(device);
     g_comm_engine_set(this);
@@ -822,10 +823,86 @@ class Engine {
     launch_step(MODE_SETUP, cur, cfg().ntimestep, 0);
     pair_evals += list_pairs_undirected();
     setup_done = true;
+    if (!cfg().dumps.empty()) write_dumps();   // Output::setup writes the initial snapshot
   }
 
-  // ---- Verlet::run: n DEM sub-steps, chunked so that the host only synchronises every `chunk` launches ------------
+  // ---- `dump custom` (EXTERNAL LAMMPS DumpCustom text format) --------------------------------------
+  // Called when HBM holds an end-of-step state (after MODE_SETUP or MODE_LAST): x(n), v(n), f(n), torque(n).
+  void write_dumps() {
+    SimConfig &c = cfg();
+    bool due = false;
+    for (size_t k = 0; k < c.dumps.size(); k++) if (c.ntimestep % c.dumps[k].every == 0 && c.dumps[k].last_written != c.ntimestep) due = true;
+    if (!due || getenv("SEDI_NO_DUMP")) return;
+    const int m = nlocal;
+    std::vector<double> x(3 * (size_t)m), v(3 * (size_t)m), w(3 * (size_t)m), fo(3 * (size_t)m), to(3 * (size_t)m), r(m), ms(m);
+    std::vector<int> tg(m), ty(m), mk(m);
+    if (m) get_state(x.data(), v.data(), w.data(), fo.data(), to.data(), r.data(), ms.data(), tg.data(), ty.data(), mk.data());
+    std::vector<int> ord(m);
+    for (int i = 0; i < m; i++) ord[i] = i;
+    std::sort(ord.begin(), ord.end(), [&](int a, int b) { return tg[a] < tg[b]; });
+    for (size_t k = 0; k < c.dumps.size(); k++) {
+      DumpSpec &D = c.dumps[k];
+      if (c.ntimestep % D.every != 0 || D.last_written == c.ntimestep) continue;
+      if (!D.fp) {
+        std::string path = D.path;
+        const char *dir = getenv("SEDI_DUMP_DIR");
+        if (dir && path.size() && path[0] != '/') path = std::string(dir) + "/" + path;
+        if (comm.nranks > 1) { char suf[32]; snprintf(suf, sizeof(suf), ".%d", comm.rank); path += suf; }  // one file per GPU rank
+        D.fp = fopen(path.c_str(), "w");
+        if (!D.fp) fatal("Cannot open dump file", path.c_str());
+      }
+      long long cnt = 0;
+      for (int i = 0; i < m; i++) if (mk[i] & D.groupbit) cnt++;
+      fprintf(D.fp, "ITEM: TIMESTEP\n%lld\nITEM: NUMBER OF ATOMS\n%lld\n", c.ntimestep, cnt);
+      fprintf(D.fp, "ITEM: BOX BOUNDS %s %s %s\n", c.boundary_str[0].c_str(), c.boundary_str[1].c_str(), c.boundary_str[2].c_str());
+      for (int d = 0; d < 3; d++) fprintf(D.fp, "%g %g\n", c.boxlo[d], c.boxhi[d]);
+      fprintf(D.fp, "ITEM: ATOMS %s\n", D.columns.c_str());
+      for (int q = 0; q < m; q++) {
+        const int i = ord[q];
+        if (!(mk[i] & D.groupbit)) continue;
+        for (size_t f = 0; f < D.fields.size(); f++) {
+          switch (D.fields[f]) {
+            case DF_ID: fprintf(D.fp, "%d ", tg[i]); break;
+            case DF_TYPE: fprintf(D.fp, "%d ", ty[i]); break;
+            case DF_DIAMETER: fprintf(D.fp, "%g ", 2.0 * r[i]); break;
+            case DF_RADIUS: fprintf(D.fp, "%g ", r[i]); break;
+            case DF_MASS: fprintf(D.fp, "%g ", ms[i]); break;
+            case DF_X: case DF_Y: case DF_Z: fprintf(D.fp, "%g ", x[3 * (size_t)i + (D.fields[f] - DF_X)]); break;
+            case DF_VX: case DF_VY: case DF_VZ: fprintf(D.fp, "%g ", v[3 * (size_t)i + (D.fields[f] - DF_VX)]); break;
+            case DF_FX: case DF_FY: case DF_FZ: fprintf(D.fp, "%g ", fo[3 * (size_t)i + (D.fields[f] - DF_FX)]); break;
+            case DF_OMEGAX: case DF_OMEGAY: case DF_OMEGAZ: fprintf(D.fp, "%g ", w[3 * (size_t)i + (D.fields[f] - DF_OMEGAX)]); break;
+            default: fprintf(D.fp, "%g ", to[3 * (size_t)i + (D.fields[f] - DF_TQX)]); break;
+          }
+        }
+        fputc('\n', D.fp);
+      }
+      fflush(D.fp);
+      D.last_written = c.ntimestep;
+    }
+  }
+
+  // Verlet::run with Output::write at the dump steps: the sub-step sequence is cut at every dump boundary so that the
+  // snapshot is the reference's end-of-step state (the fused kernel otherwise holds x(n+1), v(n+1/2) between launches).
   void run(long long nsteps) {
+    if (!setup_done) setup();
+    if (nsteps <= 0) return;
+    long long remaining = nsteps;
+    while (remaining > 0) {
+      long long seg = remaining;
+      if (!getenv("SEDI_NO_DUMP"))
+        for (size_t k = 0; k < cfg().dumps.size(); k++) {
+          const long long ev = cfg().dumps[k].every;
+          const long long to_next = ev - (cfg().ntimestep % ev);
+          if (to_next < seg) seg = to_next;
+        }
+      run_segment(seg);
+      remaining -= seg;
+      if (!cfg().dumps.empty()) write_dumps();
+    }
+  }
+
+  // ---- n DEM sub-steps ending in an end-of-step state, chunked so that the host only synchronises every `chunk` launches
+  void run_segment(long long nsteps) {
     if (!setup_done) setup();
     need_device();
     if (params_dirty) build_base_params();

@@ -8,6 +8,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# `dump` commands of the shipped input scripts write relative to the working directory, as LAMMPS does: keep the
+# repository clean while testing
+os.environ.setdefault("SEDI_DUMP_DIR", __import__("tempfile").mkdtemp(prefix="sedi_dump_"))
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

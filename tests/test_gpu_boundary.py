@@ -240,8 +240,11 @@ def test_four_spheres_golden_dump_gpu(oracle_mod):
     """shipped case multiParticlesCollideDia through the device-resident coupling API, against the reference's own
     dump rows (tolerances and their reason: tests/test_oracle_golden.py::check_four_spheres)"""
     from test_oracle_golden import check_four_spheres
+    import os
     case = cases.four_spheres_collide()
     e = make_engine(case)
+    # the case's own dump command (in.lammps:31): the golden files are per-particle extracts of this file
+    e.command("dump id all custom 1000 four_spheres.bubblemd id type diameter mass x y z vx vy vz")
     e.mesh_box(case["mesh_lo"], case["mesh_hi"], case["mesh_n"])
     e.coupling_config(DRAG_SYAMLAL_OBRIEN, FORCE_DRAG | FORCE_PGRAD, case["nub"], case["rhob"], case["g"], 1e-3)
     Uf, _, gradp = cases.uniform_fields(case)
@@ -255,6 +258,22 @@ def test_four_spheres_golden_dump_gpu(oracle_mod):
         if (k + 1) % 20 == 0:
             rows.append(e.atoms())
     check_four_spheres(rows)
+    e.close()
+    # ---- the dump file itself: EXTERNAL LAMMPS `dump custom` text layout, one snapshot per 1000 DEM steps incl. step 0
+    path = os.path.join(os.environ["SEDI_DUMP_DIR"], "four_spheres.bubblemd")
+    lines = open(path).read().split("\n")
+    snaps = [i for i, l in enumerate(lines) if l == "ITEM: TIMESTEP"]
+    assert len(snaps) == 21 and [int(lines[i + 1]) for i in snaps] == list(range(0, 20001, 1000))
+    s0 = snaps[0]
+    assert lines[s0 + 2] == "ITEM: NUMBER OF ATOMS" and lines[s0 + 3] == "4"
+    assert lines[s0 + 4] == "ITEM: BOX BOUNDS ff ff ff" and lines[s0 + 5:s0 + 8] == ["0 0.2", "0 0.1", "0 0.1"]
+    assert lines[s0 + 8] == "ITEM: ATOMS id type diameter mass x y z vx vy vz "
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "multiParticlesCollideDia")
+    for p in range(4):   # step-0 rows are identical TEXT to the reference's dump rows (same "%d %d %g ... " formatting)
+        assert lines[s0 + 9 + p] == open(os.path.join(gold, "p%d.dat" % (p + 1))).readline().rstrip("\n")
+    for n in range(20):  # later snapshots carry the same state the API returns, at %g precision
+        got = np.array([[float(t) for t in lines[snaps[n + 1] + 9 + p].split()] for p in range(4)])
+        assert np.allclose(got[:, 4:7], rows[n]["x"], rtol=6e-6, atol=0) and np.allclose(got[:, 7:10], rows[n]["v"], rtol=6e-6, atol=1e-12)
 
 
 def test_coupling_history_lubrication_inlet_terms(oracle_mod):
