@@ -94,7 +94,7 @@ struct StepParams {
   double c_kts;    // 8/8.84 * kt              : tangential spring = -polyhertz * c_kts * shear
   double c_ctd;    // sqrt(st/sn) 2 sqrt(5/6) beta : tangential dashpot = sqrt(sn meff) * c_ctd
   double c_ekt;    // 8/(8.84 kt)              : Coulomb rescale offset = ctd * vtr * c_ekt
-  int has_fdrag, fdrag_added_mass;
+  int has_fdrag, fdrag_added_mass, has_cyl_wall;
   double imgshift[27][3];  // periodic image code -> shift vector
   FixDev fix[MAX_FIXES];
 };

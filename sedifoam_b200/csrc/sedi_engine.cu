@@ -546,6 +546,7 @@ class Engine {
         case FIX_COHESIVE: F.d[0] = s.ah; F.d[1] = s.lam; F.d[2] = s.smin; F.d[3] = s.smax; F.i0 = s.opt; P.has_cohesive = 1; break;
         case FIX_WALL_GRAN:
           F.i0 = s.wallstyle; F.i1 = s.wiggle; F.i2 = s.wshear; F.i3 = s.axis;
+          if (s.wallstyle > ZPLANE) P.has_cyl_wall = 1;
           F.d[0] = s.wall.kn; F.d[1] = s.wall.kt; F.d[2] = s.wall.gamman; F.d[3] = s.wall.gammat; F.d[4] = s.wall.xmu;
           F.d[5] = s.lo; F.d[6] = s.hi; F.d[7] = s.cylradius;
           F.d[8] = (c.pair == PAIR_HERTZFIX_HISTORY) ? fix_beta(s.wall.gamman) : 0.0;
