@@ -607,24 +607,19 @@ class Engine {
       launches++;
       return;
     }
+    const bool pbc = P.periodic_any != 0;
+#define SEDI_LAUNCH_KSTEP(PK)                                                                      \
+  do {                                                                                             \
+    if (tl) { if (pbc) k_step<PK, true, true><<<blocks, KT, 0, stream>>>(P, seq); else k_step<PK, true, false><<<blocks, KT, 0, stream>>>(P, seq); } \
+    else { if (pbc) k_step<PK, false, true><<<blocks, KT, 0, stream>>>(P, seq); else k_step<PK, false, false><<<blocks, KT, 0, stream>>>(P, seq); } \
+  } while (0)
     switch (cfg().pair) {
-      case PAIR_HERTZFIX_HISTORY:
-        if (tl) k_step<PAIR_HERTZFIX_HISTORY, true><<<blocks, KT, 0, stream>>>(P, seq);
-        else k_step<PAIR_HERTZFIX_HISTORY, false><<<blocks, KT, 0, stream>>>(P, seq);
-        break;
-      case PAIR_HOOKE_HISTORY:
-        if (tl) k_step<PAIR_HOOKE_HISTORY, true><<<blocks, KT, 0, stream>>>(P, seq);
-        else k_step<PAIR_HOOKE_HISTORY, false><<<blocks, KT, 0, stream>>>(P, seq);
-        break;
-      case PAIR_HOOKE:
-        if (tl) k_step<PAIR_HOOKE, true><<<blocks, KT, 0, stream>>>(P, seq);
-        else k_step<PAIR_HOOKE, false><<<blocks, KT, 0, stream>>>(P, seq);
-        break;
-      default:
-        if (tl) k_step<PAIR_NONE, true><<<blocks, KT, 0, stream>>>(P, seq);
-        else k_step<PAIR_NONE, false><<<blocks, KT, 0, stream>>>(P, seq);
-        break;
+      case PAIR_HERTZFIX_HISTORY: SEDI_LAUNCH_KSTEP(PAIR_HERTZFIX_HISTORY); break;
+      case PAIR_HOOKE_HISTORY: SEDI_LAUNCH_KSTEP(PAIR_HOOKE_HISTORY); break;
+      case PAIR_HOOKE: SEDI_LAUNCH_KSTEP(PAIR_HOOKE); break;
+      default: SEDI_LAUNCH_KSTEP(PAIR_NONE); break;
     }
+#undef SEDI_LAUNCH_KSTEP
     launches++;
   }
 
