@@ -89,6 +89,13 @@ long long sedi_get_profile(void *ptr, double *kernel_ms);
 
 /* --- coupling (mirror of enhancedCloud, device resident).  Mesh = single-block uniform blockMesh. */
 void sedi_mesh_box(void *ptr, const double *lo, const double *hi, const int *ncell);
+/* Rectilinear mesh: graded blocks (`simpleGrading`) and axis-aligned blocks stacked into one tensor-product grid.
+ * xfaces/yfaces/zfaces hold ncell[d] + 1 ascending face coordinates (as in the host's mesh.points()); cell_label[i + nx
+ * (j + ny k)] is the host solver's label of that cell (blockMesh numbers cells block by block), NULL = the tensor index.
+ * Cell owner = the face interval containing the particle centre (replaces softParticle::move tracking,
+ * lammpsFoam/softParticle.C:102-151).  Diffusion smoothing is not available on this mesh type. */
+void sedi_mesh_rectilinear(void *ptr, const int *ncell, const double *xfaces, const double *yfaces, const double *zfaces,
+                           const int *cell_label);
 int sedi_mesh_ncells(void *ptr);
 /* drag model / force switches: names of constant/cloudProperties (enhancedCloud.C:586-598) */
 #define SEDI_DRAG_ERGUN_WENYU_ID 0

@@ -60,6 +60,7 @@ def _load(kind):
                                             _dp, _dp, _dp, _dp, _dp, _dp]
     lib.ora_foam_particle_force_extra.argtypes = [C.c_int, _ip, _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_double, C.c_double,
                                                   C.c_double, C.c_int, _dp, _dp, _dp, _dp, C.c_int, _dp, _dp]
+    lib.ora_foam_cell_owner_rect.argtypes = [C.c_int, _dp, _ip, _dp, _dp, _dp, C.c_void_p, _ip]
     lib.ora_foam_cell_owner.argtypes = [C.c_int, _dp, _dp, _dp, _ip, _ip]
     lib.ora_foam_particle_to_eulerian.argtypes = [C.c_int, _ip, _dp, _dp, C.c_int, _dp, _dp, _dp]
     lib.ora_foam_calc_tc.argtypes = [C.c_int, _ip, _dp, _dp, _dp, _dp, C.c_int, _dp, C.c_int, C.c_double, C.c_double, _dp, _dp]
@@ -213,6 +214,17 @@ def cell_owner(x, lo, hi, ncell, kind="port"):
     out = np.zeros(len(x), np.int32)
     lib.ora_foam_cell_owner(len(x), x, np.ascontiguousarray(lo, np.float64), np.ascontiguousarray(hi, np.float64),
                             np.ascontiguousarray(ncell, np.int32), out)
+    return out
+
+
+def cell_owner_rect(x, xf, yf, zf, label=None, kind="port"):
+    lib = _load(kind)
+    x = np.ascontiguousarray(x, np.float64)
+    c = lambda a: np.ascontiguousarray(a, np.float64)
+    nc = np.array([len(xf) - 1, len(yf) - 1, len(zf) - 1], np.int32)
+    lab = None if label is None else np.ascontiguousarray(label, np.int32)
+    out = np.zeros(len(x), np.int32)
+    lib.ora_foam_cell_owner_rect(len(x), x, nc, c(xf), c(yf), c(zf), _ptr(lab), out)
     return out
 
 

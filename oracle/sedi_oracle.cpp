@@ -300,6 +300,27 @@ void ora_foam_particle_force_extra(int n, const int *cell, const double *x, cons
   }
 }
 
+// Cell owner on a rectilinear mesh (graded blocks / axis-aligned blocks stacked into a tensor-product grid, SURVEY
+// 8a15): the face interval that contains the particle centre on each axis, mapped to the host's cell label.  Replaces
+// the face-to-face tracking of softParticle::move (lammpsFoam/softParticle.C:102-151), whose result on such a mesh is
+// the cell containing the end point.  Linear scan on purpose (the CUDA kernel bisects).
+void ora_foam_cell_owner_rect(int n, const double *x, const int *nc, const double *xf, const double *yf, const double *zf,
+                              const int *label, int *cell) {
+  const double *f[3] = {xf, yf, zf};
+  for (int p = 0; p < n; p++) {
+    int idx[3]; bool in = true;
+    for (int k = 0; k < 3; k++) {
+      const double v = x[3 * p + k];
+      idx[k] = -1;
+      for (int i = 0; i < nc[k]; i++) if (v >= f[k][i] && v < f[k][i + 1]) { idx[k] = i; break; }
+      if (idx[k] < 0) in = false;
+    }
+    if (!in) { cell[p] = -1; continue; }
+    const int t = idx[0] + nc[0] * (idx[1] + nc[1] * idx[2]);
+    cell[p] = label ? label[t] : t;
+  }
+}
+
 // Cell owner on a single-block axis-aligned uniform blockMesh: cell = i + nx (j + ny k)  (SURVEY 8a15, Appendix B2).
 // Points outside the block get -1 (the reference deletes such particles on the Foam side, softParticle.C:177-184).
 void ora_foam_cell_owner(int n, const double *x, const double *lo, const double *hi, const int *ncell, int *cell) {

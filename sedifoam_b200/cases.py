@@ -248,3 +248,43 @@ fix zwall all wall/gran 4910.0 NULL 0 NULL 0 0 zplane 0.00 0.10
               extra=dict(name="four_spheres_collide", Uf=(0.0, 0.0, 0.0), g=(0.0, -9.8, 0.0), dt=1e-5, substeps=50))
     c["mesh_n"] = np.array([40, 20, 1], np.int32)
     return c
+
+
+def blockmesh_divide(lo, hi, n, expansion=1.0):
+    """face coordinates of one blockMesh edge: n cells from lo to hi, `simpleGrading` expansion ratio = last cell size /
+    first cell size (EXTERNAL OpenFOAM blockMesh lineDivide: lambda_i = (1 - g^i) / (1 - g^n), g = ratio^(1/(n-1)),
+    uniform when |g - 1| <= 1e-5; restated from the published algorithm -- a host with OpenFOAM passes mesh.points())."""
+    lam = np.arange(n + 1, dtype=np.float64) / n
+    if n > 1:
+        g = float(expansion) ** (1.0 / (n - 1))
+        if abs(g - 1.0) > 1e-5:
+            lam = (1.0 - g ** np.arange(n + 1)) / (1.0 - g ** n)
+    f = lo + lam * (hi - lo)
+    f[0], f[-1] = lo, hi
+    return f
+
+
+def blockmesh_stacked(xspec, yblocks, zspec):
+    """axis-aligned hex blocks stacked along y (cases/example-cases/BL24-TH1, transport-vortex-dune; one block = the
+    graded single-block cases): xspec / zspec = (lo, hi, n, expansion), yblocks = [(lo, hi, n, expansion), ...].
+    Returns xf, yf, zf and the blockMesh cell label of every tensor cell (cells are numbered block by block, x fastest)."""
+    xf = blockmesh_divide(*xspec); zf = blockmesh_divide(*zspec)
+    ys, offs, nys = [], [], []
+    off = 0
+    nx, nz = len(xf) - 1, len(zf) - 1
+    for b, (lo, hi, n, e) in enumerate(yblocks):
+        f = blockmesh_divide(lo, hi, n, e)
+        ys.append(f if b == 0 else f[1:])
+        offs.append(off); nys.append(n)
+        off += nx * n * nz
+    yf = np.concatenate(ys)
+    ny = len(yf) - 1
+    label = np.zeros(nx * ny * nz, np.int32)
+    j0 = 0
+    for b, n in enumerate(nys):
+        for k in range(nz):
+            for j in range(n):
+                t = np.arange(nx) + nx * ((j0 + j) + ny * k)
+                label[t] = offs[b] + np.arange(nx) + nx * (j + n * k)
+        j0 += n
+    return xf, yf, zf, label

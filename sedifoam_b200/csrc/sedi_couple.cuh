@@ -20,7 +20,20 @@ static __device__ __constant__ double kROOTVSMALL = 1.0e-150;
 struct MeshBox {  // single-block uniform hex mesh: cell = i + nx (j + ny k)
   double lo[3], hi[3], dx[3];
   int nc[3];
+  // rectilinear form (graded blocks, axis-aligned blocks stacked into one tensor-product grid): face coordinates per
+  // axis, nc[d] + 1 values each, and the host solver's cell label of every tensor cell (null = i + nx (j + ny k))
+  int rect;
+  const double *face[3];
+  const int *label;
 };
+
+// owner interval of x among ascending face coordinates: largest I with f[I] <= x, -1 outside [f[0], f[n])
+__device__ __forceinline__ int face_interval(const double *f, int n, double x) {
+  if (!(x >= f[0]) || !(x < f[n])) return -1;
+  int lo = 0, hi = n;   // invariant: f[lo] <= x < f[hi]
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (x >= f[mid]) lo = mid; else hi = mid; }
+  return lo;
+}
 
 enum { SEDI_DRAG_ERGUN_WENYU = 0, SEDI_DRAG_SYAMLAL_OBRIEN = 1 };
 enum { SEDI_FORCE_DRAG = 1, SEDI_FORCE_PGRAD = 2, SEDI_FORCE_BUOY = 4, SEDI_FORCE_ADDEDMASS = 8, SEDI_FORCE_LIFT = 16,
@@ -75,6 +88,13 @@ __global__ void k_locate_cells(const D4 *posr, int n, MeshBox M, int *cell) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n) return;
   const D4 x = posr[p];
+  if (M.rect) {
+    const int i0 = face_interval(M.face[0], M.nc[0], x.x), i1 = face_interval(M.face[1], M.nc[1], x.y), i2 = face_interval(M.face[2], M.nc[2], x.z);
+    int c = -1;
+    if (i0 >= 0 && i1 >= 0 && i2 >= 0) { c = i0 + M.nc[0] * (i1 + M.nc[1] * i2); if (M.label) c = M.label[c]; }
+    cell[p] = c;
+    return;
+  }
   const double t0 = (x.x - M.lo[0]) / M.dx[0], t1 = (x.y - M.lo[1]) / M.dx[1], t2 = (x.z - M.lo[2]) / M.dx[2];
   const int i0 = (int)floor(t0), i1 = (int)floor(t1), i2 = (int)floor(t2);
   const bool in = !(t0 < 0.0) && !(t1 < 0.0) && !(t2 < 0.0) && i0 < M.nc[0] && i1 < M.nc[1] && i2 < M.nc[2];

@@ -1119,6 +1119,7 @@ class Engine {
     need_device();
     long long C = 1;
     for (int d = 0; d < 3; d++) { mesh.lo[d] = lo[d]; mesh.hi[d] = hi[d]; mesh.nc[d] = nc[d]; mesh.dx[d] = (hi[d] - lo[d]) / nc[d]; C *= nc[d]; }
+    mesh.rect = 0; mesh.label = 0; mesh.face[0] = mesh.face[1] = mesh.face[2] = 0;
     if (C <= 0 || C > 0x7fffffff) fatal("sedi_mesh_box: bad cell count");
     ncells = (int)C;
     Uf.ensure(3 * (size_t)C); gamma.ensure(C); gradp.ensure(3 * (size_t)C); DDtU.ensure(3 * (size_t)C); curlU.ensure(3 * (size_t)C);
@@ -1129,6 +1130,46 @@ class Engine {
     const double V = mesh.dx[0] * mesh.dx[1] * mesh.dx[2];
     k_fill_double<<<cdiv(C, 256), 256, 0, stream>>>(cellV.p, (size_t)C, V);
     have_mesh = true; have_DDtU = have_curlU = false; have_gradp = true; cell_valid = false;
+  }
+
+  // Rectilinear mesh (graded blocks, e.g. `simpleGrading (1 10 1)` of cases/example-cases/transport-bedload,
+  // and axis-aligned blocks stacked into one tensor-product grid, cases/example-cases/BL24-TH1): face coordinates
+  // per axis as the host mesh has them, plus the host's cell label of every tensor cell (NULL = i + nx (j + ny k)).
+  Buf<double> mesh_faces[3];
+  Buf<int> mesh_label;
+  void mesh_rectilinear(const int *nc, const double *xf, const double *yf, const double *zf, const int *label) {
+    need_device();
+    const double *f[3] = {xf, yf, zf};
+    long long C = 1;
+    for (int d = 0; d < 3; d++) {
+      if (nc[d] < 1) fatal("sedi_mesh_rectilinear: bad cell count");
+      for (int k = 0; k < nc[d]; k++) if (!(f[d][k + 1] > f[d][k])) fatal("sedi_mesh_rectilinear: face coordinates must ascend");
+      C *= nc[d];
+    }
+    if (C > 0x7fffffff) fatal("sedi_mesh_rectilinear: bad cell count");
+    const int ncu[3] = {nc[0], nc[1], nc[2]};
+    double lo[3], hi[3];
+    for (int d = 0; d < 3; d++) { lo[d] = f[d][0]; hi[d] = f[d][nc[d]]; }
+    mesh_box(lo, hi, ncu);   // allocates the cell fields; dx / cellV are overwritten below
+    std::vector<double> V((size_t)C);
+    std::vector<char> seen((size_t)C, 0);
+    for (int k = 0; k < nc[2]; k++) for (int j = 0; j < nc[1]; j++) for (int i = 0; i < nc[0]; i++) {
+      const long long t = i + (long long)nc[0] * (j + (long long)nc[1] * k);
+      const long long c = label ? label[t] : t;
+      if (c < 0 || c >= C || seen[c]) fatal("sedi_mesh_rectilinear: cell labels must be a permutation of 0..C-1");
+      seen[c] = 1;
+      V[c] = (xf[i + 1] - xf[i]) * (yf[j + 1] - yf[j]) * (zf[k + 1] - zf[k]);
+    }
+    CK(cudaMemcpyAsync(cellV.p, V.data(), (size_t)C * sizeof(double), cudaMemcpyHostToDevice, stream));
+    for (int d = 0; d < 3; d++) {
+      mesh_faces[d].ensure((size_t)nc[d] + 1);
+      CK(cudaMemcpyAsync(mesh_faces[d].p, f[d], ((size_t)nc[d] + 1) * sizeof(double), cudaMemcpyHostToDevice, stream));
+      mesh.face[d] = mesh_faces[d].p;
+    }
+    mesh.label = 0;
+    if (label) { mesh_label.ensure((size_t)C); CK(cudaMemcpyAsync(mesh_label.p, label, (size_t)C * sizeof(int), cudaMemcpyHostToDevice, stream)); mesh.label = mesh_label.p; }
+    CK(cudaStreamSynchronize(stream));
+    mesh.rect = 1;
   }
 
   void put_cell_fields(const double *hUf, const double *hgamma, const double *hgradp, const double *hDDtU, const double *hcurlU) {
@@ -1204,6 +1245,7 @@ class Engine {
     launches += 2;
   }
   void smooth_component(double *field, int stride, int off) {
+    if (mesh.rect) fatal("diffusion smoothing is built for uniform single-block meshes only (rectilinear / graded mesh given)");
     const int C = ncells, T = 256;
     cg_r.ensure(C); cg_z.ensure(C); cg_p.ensure(C); cg_Ap.ensure(C); cg_partial.ensure(1024); cg_s.ensure(8); h_cg.ensure(8);
     SmoothGrid G;
@@ -1518,6 +1560,9 @@ void sedi_profile(void *ptr, int on) { Engine *e = E(ptr); e->prof_on = (on != 0
 long long sedi_get_profile(void *ptr, double *kernel_ms) { Engine *e = E(ptr); if (kernel_ms) *kernel_ms = e->prof_ms; return e->prof_steps; }
 
 void sedi_mesh_box(void *ptr, const double *lo, const double *hi, const int *ncell) { E(ptr)->mesh_box(lo, hi, ncell); }
+void sedi_mesh_rectilinear(void *ptr, const int *ncell, const double *xfaces, const double *yfaces, const double *zfaces, const int *cell_label) {
+  E(ptr)->mesh_rectilinear(ncell, xfaces, yfaces, zfaces, cell_label);
+}
 int sedi_mesh_ncells(void *ptr) { return E(ptr)->ncells; }
 void sedi_coupling_config(void *ptr, int drag_model, int force_flags, double nub, double rhob, const double *g, double deltaT) {
   Engine *e = E(ptr);

@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "sedi_abi_version", "sedi_device_count", "sedi_set_device", "sedi_set_box", "sedi_add_atoms", "sedi_set_omega",
     "sedi_get_state", "sedi_get_pairs", "sedi_get_wall_shear", "sedi_force_rebuild", "sedi_get_stat", "sedi_reset_stats",
     "sedi_synchronize", "sedi_stream", "sedi_last_step_ms", "sedi_timer_start", "sedi_timer_stop_ms", "sedi_profile",
-    "sedi_get_profile", "sedi_mesh_box", "sedi_mesh_ncells", "sedi_coupling_config",
+    "sedi_get_profile", "sedi_mesh_box", "sedi_mesh_rectilinear", "sedi_mesh_ncells", "sedi_coupling_config",
     "sedi_put_cell_fields", "sedi_coupling_time_index", "sedi_coupling_inlet", "sedi_get_history_state", "sedi_locate", "sedi_compute_fluid_force", "sedi_scatter_alpha_u", "sedi_calc_tc",
     "sedi_enable_diag", "sedi_get_coupling_diag", "sedi_step", "sedi_comm_init", "sedi_comm_unique_id", "sedi_comm_rank", "sedi_comm_stat",
     "sedi_decomp_grid", "sedi_decomp_owner", "sedi_decomp_links", "sedi_smooth_config", "sedi_smooth_uf", "sedi_smooth_field",
@@ -105,6 +105,7 @@ def load_library():
         "sedi_profile": (None, [vp, i]),
         "sedi_get_profile": (ll, [vp, C.POINTER(C.c_double)]),
         "sedi_mesh_box": (None, [vp, vp, vp, vp]),
+        "sedi_mesh_rectilinear": (None, [vp, vp, vp, vp, vp, vp]),
         "sedi_mesh_ncells": (i, [vp]),
         "sedi_coupling_config": (None, [vp, i, i, d, d, vp, d]),
         "sedi_put_cell_fields": (None, [vp] + [vp] * 5),
@@ -334,6 +335,12 @@ class Lammps:
     def mesh_box(self, lo, hi, ncell):
         lo = _f64(lo); hi = _f64(hi); nc = _i32(ncell)
         self.lib.sedi_mesh_box(self.h, _vp(lo), _vp(hi), _vp(nc))
+
+    def mesh_rectilinear(self, xf, yf, zf, label=None):
+        xf, yf, zf = _f64(xf), _f64(yf), _f64(zf)
+        nc = np.array([len(xf) - 1, len(yf) - 1, len(zf) - 1], np.int32)
+        lab = None if label is None else np.ascontiguousarray(label, np.int32)
+        self.lib.sedi_mesh_rectilinear(self.h, _vp(nc), _vp(xf), _vp(yf), _vp(zf), _vp(lab))
 
     def mesh_ncells(self):
         return self.lib.sedi_mesh_ncells(self.h)

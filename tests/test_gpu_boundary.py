@@ -329,3 +329,40 @@ def test_coupling_history_lubrication_inlet_terms(oracle_mod):
         v_prev = st["v"]; Uf_prev = Uf
         e.sedi_step(10)
     assert hit["lub"] > 0 and hit["inlet"] > 0 and hit["window"] > 0   # every branch was exercised
+
+
+def test_cell_owner_graded_stacked_blocks(oracle_mod):
+    """SURVEY 8a15 on the mesh of cases/example-cases/BL24-TH1 (three blocks stacked in y, the lowest graded 0.1, cells
+    numbered block by block): owner labels bit-exact against the restated interval search, cell volumes through the
+    scatter's built-in invariant sum(gamma V) = sum(Vp) (enhancedCloud.C:964-976)"""
+    xf, yf, zf, label = cases.blockmesh_stacked((0.0, 0.016, 16, 1.0), [(0.0, 0.008, 20, 0.1), (0.008, 0.012, 40, 1.0), (0.012, 0.016, 40, 1.0)],
+                                                (0.0, 0.008, 4, 1.0))
+    assert len(yf) == 101 and np.all(np.diff(yf) > 0) and abs((yf[20] - yf[19]) / (yf[1] - yf[0]) - 0.1) < 1e-12
+    case = cases.sediment_column(dims=(20, 18, 10), d=5.0e-4, phi=0.35)     # 10 x 9 x 5 mm column inside the 16 x 16 x 8 mm mesh
+    e = make_engine(case)
+    e.mesh_rectilinear(xf, yf, zf, label)
+    assert e.mesh_ncells() == 16 * 100 * 4
+    e.coupling_config(DRAG_ERGUN_WENYU, FORCE_DRAG | FORCE_PGRAD, case["nub"], case["rhob"], case["g"], 2e-4)
+    e.step(40)
+    e.enable_diag(True)
+    C = e.mesh_ncells()
+    e.put_cell_fields(np.zeros((C, 3)), np.zeros(C), np.zeros((C, 3)))
+    e.compute_fluid_force()
+    st = e.atoms()
+    cell = oracle_mod.cell_owner_rect(st["x"], xf, yf, zf, label)
+    assert np.array_equal(e.coupling_diag()["cell"], cell) and (cell >= 0).all()
+    assert len(np.unique(cell)) > 300                                     # spread over graded and uniform blocks
+    # volumes: tensor cell (i, j, k) -> label
+    V = np.zeros(C)
+    nx, ny = 16, 100
+    for k in range(4):
+        for j in range(ny):
+            V[label[np.arange(nx) + nx * (j + ny * k)]] = np.diff(xf) * (yf[j + 1] - yf[j]) * (zf[k + 1] - zf[k])
+    d = 2.0 * st["radius"]
+    g_ref, Ue_ref = oracle_mod.particle_to_eulerian(cell, d, st["v"], V)
+    g, Ue = e.scatter_alpha_u()
+    assert rel_err(g, g_ref) < 1e-12 and rel_err(Ue, Ue_ref) < 1e-11
+    assert abs((g * V).sum() / (np.pi / 6 * (d ** 3).sum()) - 1.0) < 1e-12
+    # points outside the mesh are unowned; a point exactly on an interior face belongs to the upper cell
+    probe = np.array([[0.004, yf[20], 0.002], [0.004, -1e-9, 0.002], [0.016, 0.001, 0.002]])
+    assert list(oracle_mod.cell_owner_rect(probe, xf, yf, zf, label)) == [int(label[4 + 16 * (20 + 100 * 1)]), -1, -1]

@@ -60,3 +60,18 @@ def test_history_force_window_regime_moves_n0(oracle_mod):
     assert np.isclose(n0k, 50 - dn, rtol=1e-12)
     assert np.isclose(Sk[0], (dn - 1) / dn * 1.0, rtol=1e-12)      # tau_h == tau_h_old, no new increment (dupdt = 0)
     assert np.isclose(F[0], 0.9279 * Sk[0] * dT, rtol=1e-12)       # dn < 1 -> g1n = 0.9279
+
+
+def test_blockmesh_grading_and_labels(oracle_mod):
+    """host helper for graded / stacked blockMesh blocks: geometric face spacing and block-wise labels"""
+    from sedifoam_b200 import cases
+    f = cases.blockmesh_divide(0.0, 1.0, 10, 10.0)
+    w = np.diff(f)
+    assert np.isclose(w[-1] / w[0], 10.0) and np.allclose(w[1:] / w[:-1], 10.0 ** (1 / 9)) and f[0] == 0.0 and f[-1] == 1.0
+    assert np.allclose(cases.blockmesh_divide(0.0, 2.0, 4, 1.0), [0, 0.5, 1.0, 1.5, 2.0])
+    xf, yf, zf, label = cases.blockmesh_stacked((0, 2, 2, 1.0), [(0, 1, 2, 1.0), (1, 3, 1, 1.0)], (0, 1, 2, 1.0))
+    assert sorted(label) == list(range(12))
+    # block 0 holds labels 0..7 (2 x 2 x 2), block 1 labels 8..11 (2 x 1 x 2): tensor cell (i=1, j=2, k=1) is block 1's (1, 0, 1)
+    assert label[1 + 2 * (2 + 3 * 1)] == 8 + 1 + 2 * (0 + 1 * 1)
+    pts = np.array([[0.5, 0.25, 0.25], [1.5, 2.0, 0.75], [0.5, 3.0, 0.5]])
+    assert list(oracle_mod.cell_owner_rect(pts, xf, yf, zf, label)) == [0, 8 + 1 + 2 * 1, -1]
