@@ -93,7 +93,7 @@ void sedi_mesh_box(void *ptr, const double *lo, const double *hi, const int *nce
  * xfaces/yfaces/zfaces hold ncell[d] + 1 ascending face coordinates (as in the host's mesh.points()); cell_label[i + nx
  * (j + ny k)] is the host solver's label of that cell (blockMesh numbers cells block by block), NULL = the tensor index.
  * Cell owner = the face interval containing the particle centre (replaces softParticle::move tracking,
- * lammpsFoam/softParticle.C:102-151).  Diffusion smoothing is not available on this mesh type. */
+ * lammpsFoam/softParticle.C:102-151).  Diffusion smoothing uses the finite-volume Laplacian of the cell widths. */
 void sedi_mesh_rectilinear(void *ptr, const int *ncell, const double *xfaces, const double *yfaces, const double *zfaces,
                            const int *cell_label);
 int sedi_mesh_ncells(void *ptr);

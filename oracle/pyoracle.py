@@ -277,3 +277,40 @@ def smooth_field(phi, ncell, dx, bandwidth, steps, Ddiag=(1.0, 1.0, 1.0)):
         for k in range(flat.shape[1]):
             flat[:, k] = lu.solve(flat[:, k])
     return out
+
+
+def smooth_field_rect(phi, xf, yf, zf, label, bandwidth, steps, Ddiag=(1.0, 1.0, 1.0)):
+    """smoothField on a rectilinear (graded / stacked-block) mesh: the volume-integrated finite-volume system of
+    fvm::ddt - fvm::laplacian on an orthogonal mesh,  V_c (phi_c - phi_c^n)/d_tau = sum_f D_nn A_f (phi_nb - phi_c)/delta_f,
+    zeroGradient walls, solved directly.  phi is indexed by the host cell label.  PARITY UNPINNED (no OpenFOAM here)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+    h = [np.diff(np.asarray(f, np.float64)) for f in (xf, yf, zf)]
+    nx, ny, nz = len(h[0]), len(h[1]), len(h[2])
+    C = nx * ny * nz
+    lab = np.arange(C) if label is None else np.asarray(label)
+    dtau = (bandwidth * bandwidth / 4.0) / (steps + 1.0e-150)
+    idx = np.arange(C).reshape(nz, ny, nx)              # tensor index t = i + nx (j + ny k)
+    HX, HY, HZ = np.meshgrid(h[2], h[1], h[0], indexing="ij")[::-1]   # each [nz][ny][nx]: hx, hy, hz of the cell
+    V = (HX * HY * HZ).ravel()
+    rows, cols, vals = [], [], []
+    diag = V.copy()
+    for axis, (H, D) in enumerate(((HX, Ddiag[0]), (HY, Ddiag[1]), (HZ, Ddiag[2]))):
+        ax = 2 - axis                                     # array axis of this direction
+        sl_lo = [slice(None)] * 3; sl_hi = [slice(None)] * 3
+        sl_lo[ax] = slice(0, -1); sl_hi[ax] = slice(1, None)
+        a = idx[tuple(sl_lo)].ravel(); b = idx[tuple(sl_hi)].ravel()
+        area = (V / H.ravel())                            # face area = V / h along the normal
+        coef = dtau * D * area[a] / (0.5 * (H.ravel()[a] + H.ravel()[b]))
+        rows += [a, b]; cols += [b, a]; vals += [-coef, -coef]
+        np.add.at(diag, a, coef); np.add.at(diag, b, coef)
+    rows.append(np.arange(C)); cols.append(np.arange(C)); vals.append(diag)
+    A = sp.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(C, C))
+    lu = spl.splu(A)
+    out = np.array(phi, np.float64, copy=True)
+    flat = out.reshape(C, -1)
+    for _ in range(int(steps)):
+        for k in range(flat.shape[1]):
+            t = flat[lab, k]                              # tensor order
+            flat[lab, k] = lu.solve(V * t)
+    return out

@@ -1135,7 +1135,7 @@ class Engine {
   // Rectilinear mesh (graded blocks, e.g. `simpleGrading (1 10 1)` of cases/example-cases/transport-bedload,
   // and axis-aligned blocks stacked into one tensor-product grid, cases/example-cases/BL24-TH1): face coordinates
   // per axis as the host mesh has them, plus the host's cell label of every tensor cell (NULL = i + nx (j + ny k)).
-  Buf<double> mesh_faces[3];
+  Buf<double> mesh_faces[3], mesh_width[3], cg_diag;
   Buf<int> mesh_label;
   void mesh_rectilinear(const int *nc, const double *xf, const double *yf, const double *zf, const int *label) {
     need_device();
@@ -1165,6 +1165,10 @@ class Engine {
       mesh_faces[d].ensure((size_t)nc[d] + 1);
       CK(cudaMemcpyAsync(mesh_faces[d].p, f[d], ((size_t)nc[d] + 1) * sizeof(double), cudaMemcpyHostToDevice, stream));
       mesh.face[d] = mesh_faces[d].p;
+      std::vector<double> h((size_t)nc[d]);
+      for (int k = 0; k < nc[d]; k++) h[k] = f[d][k + 1] - f[d][k];
+      mesh_width[d].ensure((size_t)nc[d]);
+      CK(cudaMemcpy(mesh_width[d].p, h.data(), (size_t)nc[d] * sizeof(double), cudaMemcpyHostToDevice));
     }
     mesh.label = 0;
     if (label) { mesh_label.ensure((size_t)C); CK(cudaMemcpyAsync(mesh_label.p, label, (size_t)C * sizeof(int), cudaMemcpyHostToDevice, stream)); mesh.label = mesh_label.p; }
@@ -1240,12 +1244,11 @@ class Engine {
   bool smoothing_on(int flag) const { return (smooth_flags & flag) && smooth_b > 0.0 && smooth_steps > 0; }
   void dot_to(const double *a, int sa, int oa, const double *b, int sb, int ob, int nC, double *out) {
     const int nb = std::min(1024, cdiv(nC, 256));
-    k_dot_partial<<<nb, 256, 0, stream>>>(a, sa, oa, b, sb, ob, nC, cg_partial.p);
+    k_dot_partial<<<nb, 256, 0, stream>>>(a, sa, oa, b, sb, ob, nC, cg_partial.p, mesh.rect ? cellV.p : (const double *)0);
     k_dot_final<<<1, 256, 0, stream>>>(cg_partial.p, nb, out);
     launches += 2;
   }
   void smooth_component(double *field, int stride, int off) {
-    if (mesh.rect) fatal("diffusion smoothing is built for uniform single-block meshes only (rectilinear / graded mesh given)");
     const int C = ncells, T = 256;
     cg_r.ensure(C); cg_z.ensure(C); cg_p.ensure(C); cg_Ap.ensure(C); cg_partial.ensure(1024); cg_s.ensure(8); h_cg.ensure(8);
     SmoothGrid G;
@@ -1253,10 +1256,23 @@ class Engine {
     const double dtau = (smooth_b * smooth_b / 4) / (smooth_steps + 1.0e-150);   // enhancedCloud.C:564-565
     G.wx = dtau * smooth_D[0] / (mesh.dx[0] * mesh.dx[0]); G.wy = dtau * smooth_D[1] / (mesh.dx[1] * mesh.dx[1]); G.wz = dtau * smooth_D[2] / (mesh.dx[2] * mesh.dx[2]);
     const int nblk = cdiv(C, T);
+    G.rect = mesh.rect; G.hx = G.hy = G.hz = 0; G.label = 0; G.diag = 0; G.dtx = G.dty = G.dtz = 0.0;
+    if (mesh.rect) {  // finite-volume coefficients from the cell widths; the diagonal is tabulated once per call
+      G.dtx = dtau * smooth_D[0]; G.dty = dtau * smooth_D[1]; G.dtz = dtau * smooth_D[2];
+      G.hx = mesh_width[0].p; G.hy = mesh_width[1].p; G.hz = mesh_width[2].p; G.label = mesh.label;
+      cg_diag.ensure(C);
+      k_smooth_apply_rect<<<nblk, T, 0, stream>>>(G, (const double *)0, (double *)0, 1, 0, cg_diag.p);
+      G.diag = cg_diag.p;
+      launches++;
+    }
+    auto apply = [&](const double *x, double *y, int st, int of) {
+      if (mesh.rect) k_smooth_apply_rect<<<nblk, T, 0, stream>>>(G, x, y, st, of, (double *)0);
+      else k_smooth_apply<<<nblk, T, 0, stream>>>(G, x, y, st, of);
+    };
     for (int step = 0; step < smooth_steps; step++) {
       // A x = b with b = field (also the initial guess); s = {rz, pAp, rz_new, rr, bb}
       dot_to(field, stride, off, field, stride, off, C, cg_s.p + 4);
-      k_smooth_apply<<<nblk, T, 0, stream>>>(G, field, cg_Ap.p, stride, off);
+      apply(field, cg_Ap.p, stride, off);
       k_cg_init<<<nblk, T, 0, stream>>>(G, field, stride, off, cg_Ap.p, cg_r.p, cg_z.p, cg_p.p, C);
       dot_to(cg_r.p, 1, 0, cg_z.p, 1, 0, C, cg_s.p + 0);
       dot_to(cg_r.p, 1, 0, cg_r.p, 1, 0, C, cg_s.p + 3);
@@ -1268,7 +1284,7 @@ class Engine {
           CK(cudaStreamSynchronize(stream));
           if (!(h_cg.p[3] > 1.0e-24 * h_cg.p[4]) || h_cg.p[0] == 0.0) break;
         }
-        k_smooth_apply<<<nblk, T, 0, stream>>>(G, cg_p.p, cg_Ap.p, 1, 0);
+        apply(cg_p.p, cg_Ap.p, 1, 0);
         dot_to(cg_p.p, 1, 0, cg_Ap.p, 1, 0, C, cg_s.p + 1);
         k_cg_step1<<<nblk, T, 0, stream>>>(field, stride, off, cg_r.p, cg_p.p, cg_Ap.p, cg_s.p, G, cg_z.p, C);
         dot_to(cg_r.p, 1, 0, cg_z.p, 1, 0, C, cg_s.p + 2);

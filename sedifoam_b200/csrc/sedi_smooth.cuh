@@ -14,7 +14,41 @@
 
 namespace sedi {
 
-struct SmoothGrid { int nx, ny, nz; double wx, wy, wz; };  // w = d_tau * D_dd / dx_d^2
+// uniform mesh: w = d_tau * D_dd / dx_d^2.  Rectilinear mesh (rect != 0): finite-volume form per cell,
+//   (1 + sum_f w_f) phi_c - sum_f w_f phi_nb = phi^n_c ,  w_f = dt_d / (h_c * 0.5 (h_c + h_nb)) ,  dt_d = d_tau * D_dd,
+// with h the cell widths along the face normal (exactly fvm::laplacian's  A_f / (V_c delta_f)  on an orthogonal mesh).
+// The row form is self-adjoint in the volume-weighted inner product, which is the one the CG loop then uses
+// (equivalent to PCG on OpenFOAM's volume-integrated symmetric matrix).  Fields are stored under the host's cell
+// labels; `label` maps the tensor index to them (null = identity), `diag` holds the matrix diagonal by label.
+struct SmoothGrid {
+  int nx, ny, nz; double wx, wy, wz;
+  int rect; double dtx, dty, dtz; const double *hx, *hy, *hz; const int *label; const double *diag;
+};
+
+__device__ __forceinline__ int smooth_lab(const SmoothGrid &G, int t) { return G.label ? G.label[t] : t; }
+// y = A x on a rectilinear mesh, one thread per tensor cell; also used (x == null) to build the diagonal
+__global__ void k_smooth_apply_rect(SmoothGrid G, const double *x, double *y, int stride, int off, double *diag_out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int C = G.nx * G.ny * G.nz;
+  if (t >= C) return;
+  const int i = t % G.nx, j = (t / G.nx) % G.ny, k = t / (G.nx * G.ny);
+  const int c = smooth_lab(G, t);
+  const double xc = x ? x[(size_t)c * stride + off] : 0.0;
+  double acc = xc, dg = 1.0;
+  const double hx = G.hx[i], hy = G.hy[j], hz = G.hz[k];
+#define SEDI_FACE(cond, tn, h, hn, dt)                                                                 \
+  if (cond) { const double w = (dt) / ((h) * (0.5 * ((h) + (hn)))); dg += w;                          \
+              if (x) acc += w * (xc - x[(size_t)smooth_lab(G, tn) * stride + off]); }
+  SEDI_FACE(i > 0, t - 1, hx, G.hx[i - 1], G.dtx)
+  SEDI_FACE(i < G.nx - 1, t + 1, hx, G.hx[i + 1], G.dtx)
+  SEDI_FACE(j > 0, t - G.nx, hy, G.hy[j - 1], G.dty)
+  SEDI_FACE(j < G.ny - 1, t + G.nx, hy, G.hy[j + 1], G.dty)
+  SEDI_FACE(k > 0, t - G.nx * G.ny, hz, G.hz[k - 1], G.dtz)
+  SEDI_FACE(k < G.nz - 1, t + G.nx * G.ny, hz, G.hz[k + 1], G.dtz)
+#undef SEDI_FACE
+  if (x) y[c] = acc;
+  if (diag_out) diag_out[c] = dg;
+}
 
 // y = A x  for one component of an interleaved field (stride = 1 scalar, 3 vector)
 __global__ void k_smooth_apply(SmoothGrid G, const double *x, double *y, int stride, int off) {
@@ -34,6 +68,7 @@ __global__ void k_smooth_apply(SmoothGrid G, const double *x, double *y, int str
 }
 
 __device__ __forceinline__ double smooth_diag(const SmoothGrid &G, int c) {
+  if (G.rect) return G.diag[c];
   const int i = c % G.nx, j = (c / G.nx) % G.ny, k = c / (G.nx * G.ny);
   double d = 1.0;
   d += G.wx * ((i > 0) + (i < G.nx - 1)) + G.wy * ((j > 0) + (j < G.ny - 1)) + G.wz * ((k > 0) + (k < G.nz - 1));
@@ -41,9 +76,12 @@ __device__ __forceinline__ double smooth_diag(const SmoothGrid &G, int c) {
 }
 
 // deterministic dot product: per-block partial sums in a fixed tree, then one block adds the partials in order
-__global__ void __launch_bounds__(256) k_dot_partial(const double *a, int sa, int oa, const double *b, int sb, int ob, int n, double *partial) {
+__global__ void __launch_bounds__(256) k_dot_partial(const double *a, int sa, int oa, const double *b, int sb, int ob, int n, double *partial,
+                                                     const double *w) {   // w: optional cell weights (volumes)
   __shared__ double sm[256];
   double acc = 0.0;
+  if (w) { for (int c = blockIdx.x * 256 + threadIdx.x; c < n; c += gridDim.x * 256) acc += w[c] * (a[(size_t)c * sa + oa] * b[(size_t)c * sb + ob]); }
+  else
   for (int c = blockIdx.x * 256 + threadIdx.x; c < n; c += gridDim.x * 256) acc += a[(size_t)c * sa + oa] * b[(size_t)c * sb + ob];
   sm[threadIdx.x] = acc;
   __syncthreads();
