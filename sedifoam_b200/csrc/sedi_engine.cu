@@ -258,7 +258,7 @@ class Engine {
         beta_pair(0), pair_evals_unique(0), nbuilds(0), pair_evals(0), steps_done(0), launches(0), list_gran_dir(0), list_type_dir(0), list_gran_img(0),
         list_type_img(0), chunk(16), last_step_ms(0), count_in_kernel(false), have_mesh(false), ncells(0), have_DDtU(false),
         have_curlU(false), have_gradp(false), have_Uf(false), drag_model(0), force_flags(SEDI_FORCE_DRAG | SEDI_FORCE_PGRAD), nub(1e-6), rhob(1000.0),
-        deltaT(1.0), hist_alloc(false), have_UfOld(false), time_index(0), inlet_option(0), want_diag(false), smooth_b(0.0), smooth_steps(0), smooth_flags(0), smooth_iters_last(0), prof_on(false), prof_ms(0), prof_steps(0) {
+        deltaT(1.0), inject_pending(false), hist_alloc(false), have_UfOld(false), time_index(0), inlet_option(0), want_diag(false), smooth_b(0.0), smooth_steps(0), smooth_flags(0), smooth_iters_last(0), prof_on(false), prof_ms(0), prof_steps(0) {
     gvec[0] = gvec[1] = gvec[2] = 0.0;
     memset(inlet_force, 0, sizeof(inlet_force)); memset(inlet_box, 0, sizeof(inlet_box)); memset(inlet_ecc, 0, sizeof(inlet_ecc));
     smooth_D[0] = smooth_D[1] = smooth_D[2] = 1.0;
@@ -753,6 +753,10 @@ class Engine {
       B.gcellstart = comm.d_gstart; B.gorder = comm.d_gorder;
       if (narr > 0) { B.arr_nh = comm.d_arr_nh; B.arr_tag = comm.d_arr_tag; B.arr_shear = comm.d_arr_shear; if (!Lo.valid) B.n_old = n_old; }
     }
+    if (inject_pending) {  // every row is an "arrival" that brings its contact history as (partner tag, shear) pairs
+      B.have_old = 1; B.n_old = 0; B.nn_old = 0;
+      B.arr_nh = inj_nh.p; B.arr_tag = inj_tag.p; B.arr_shear = inj_shear.p;
+    }
     B.maxcount = ctrl.p + 3; B.npairs = counters.p;
     if (Ln.cap < 12) Ln.cap = std::max(Lo.cap, 12);   // k_step reads the first nine list words of every row unconditionally
     for (int attempt = 0; attempt < 3; attempt++) {
@@ -788,7 +792,7 @@ class Engine {
   long long list_pairs_undirected() const { return (list_gran_dir - list_gran_img) / 2 + list_gran_img; }
 
   // ---- Verlet::setup (first `run` of the session, even with `pre no`; softParticleCloud.C:189 lammps_step(0)) -----
-  void setup() {
+  void setup(bool evaluate_forces = true) {
     if (!loaded) load_atoms();
     need_device();
     dt_init = cfg().dt;
@@ -816,8 +820,10 @@ class Engine {
     setup_bins();
     rebuild();
     build_base_params();
-    launch_step(MODE_SETUP, cur, cfg().ntimestep, 0);
-    pair_evals += list_pairs_undirected();
+    if (evaluate_forces) {
+      launch_step(MODE_SETUP, cur, cfg().ntimestep, 0);
+      pair_evals += list_pairs_undirected();
+    }
     setup_done = true;
     if (!cfg().dumps.empty()) write_dumps();   // Output::setup writes the initial snapshot
   }
@@ -1136,6 +1142,10 @@ class Engine {
   // and axis-aligned blocks stacked into one tensor-product grid, cases/example-cases/BL24-TH1): face coordinates
   // per axis as the host mesh has them, plus the host's cell label of every tensor cell (NULL = i + nx (j + ny k)).
   Buf<double> mesh_faces[3], mesh_width[3], cg_diag;
+  // particle injection / deletion: state of the surviving particles carried across the re-upload
+  bool inject_pending;
+  Buf<int> inj_nh, inj_tag;
+  Buf<D4> inj_shear;
   Buf<int> mesh_label;
   void mesh_rectilinear(const int *nc, const double *xf, const double *yf, const double *zf, const int *label) {
     need_device();
@@ -1393,6 +1403,114 @@ class Engine {
   // ---- particle injection / deletion (library.cpp:406-621).  Host round trip: the device state is
   // folded back into the script's atom table, edited there, and uploaded again; the next run re-does setup.  Contact
   // and wall history of surviving particles restart from zero (the reference keeps them) -- documented in DESIGN.md.
+  // Everything a surviving particle owns besides its state quads, by device row (= order of script.atoms after
+  // sync_host_atoms): per-atom fix arrays (fix_fluid_drag.cpp:211-224, fix_wall_granFix.cpp:726-732), stored force and
+  // torque, wall-touch bits, Foam rank, history-force state, and the contact history as (partner tag, shear) lists --
+  // what LAMMPS' AtomVec::copy + Fix::copy_arrays keep when library.cpp:406-621 edits the atom table.
+  struct RowCarry {
+    int n, nplanes;
+    std::vector<std::vector<double> > planes;   // fdrag, dudt, vold, uold, f, tq (18), wall shear (3 per wall), history force (4)
+    std::vector<unsigned> wmask;
+    std::vector<int> foam;
+    std::vector<int> nh, htag;                  // contact history: count and partner tags, MIG_MAXH per row
+    std::vector<double> hshear;                 // 3 per entry
+    RowCarry() : n(0), nplanes(0) {}
+  };
+  std::vector<double *> carry_plane_ptrs() {
+    std::vector<double *> p;
+    Plane2 *groups[] = {fdrag, dudt, vold, uold, f, tq};
+    for (int g = 0; g < 6; g++) for (int d = 0; d < 3; d++) p.push_back(groups[g][d].get());
+    for (int w = 0; w < cfg().nwalls; w++) for (int d = 0; d < 3; d++) p.push_back(wshear[w][d].get());
+    if (hist_alloc) for (int d = 0; d < 4; d++) p.push_back(hist[d].get());
+    return p;
+  }
+  bool carry_enabled() const { return setup_done && comm.nranks == 1 && !getenv("SEDI_INJECT_RESET"); }
+  void save_rows(RowCarry &R) {
+    const int m = nlocal;
+    R.n = m;
+    std::vector<double *> ptrs = carry_plane_ptrs();
+    R.nplanes = (int)ptrs.size();
+    R.planes.assign(ptrs.size(), std::vector<double>((size_t)m));
+    for (size_t k = 0; k < ptrs.size(); k++) if (m) CK(cudaMemcpyAsync(R.planes[k].data(), ptrs[k], (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    R.wmask.assign(m, 0u); R.foam.assign(m, 0);
+    if (m) {
+      CK(cudaMemcpyAsync(R.wmask.data(), wmask[icur].p, (size_t)m * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+      CK(cudaMemcpyAsync(R.foam.data(), foam[icur].p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    }
+    CK(cudaStreamSynchronize(stream));
+    // contact history by tag (directed rows, as stored)
+    R.nh.assign(m, 0); R.htag.assign((size_t)m * MIG_MAXH, 0); R.hshear.assign((size_t)m * MIG_MAXH * 3, 0.0);
+    const long long tot = get_pairs(0, 0, 0, 0, 0, 0);
+    if (tot > 0) {
+      std::vector<int> ti(tot), tj(tot), touch(tot);
+      std::vector<unsigned> meta(tot);
+      std::vector<double> sh(3 * (size_t)tot);
+      get_pairs(ti.data(), tj.data(), meta.data(), touch.data(), sh.data(), tot);
+      std::vector<int> tg(m);
+      get_state(0, 0, 0, 0, 0, 0, 0, tg.data(), 0, 0);
+      std::vector<int> row_of(maxtag + 2, -1);
+      for (int i = 0; i < m; i++) if (tg[i] >= 0 && tg[i] <= maxtag) row_of[tg[i]] = i;
+      for (long long e = 0; e < tot; e++) {
+        if (!touch[e]) continue;
+        const int i = row_of[ti[e]];
+        if (i < 0) continue;
+        if (R.nh[i] >= MIG_MAXH) fatal("more than 16 touching partners on one particle: contact history cannot be carried across injection / deletion");
+        const size_t s = (size_t)i * MIG_MAXH + R.nh[i]++;
+        R.htag[s] = tj[e];
+        for (int d = 0; d < 3; d++) R.hshear[3 * s + d] = sh[3 * (size_t)e + d];
+      }
+    }
+  }
+  // keep[k] = old row of the k-th atom of the new table, -1 for an injected particle
+  void restore_rows(const RowCarry &R, const std::vector<int> &keep) {
+    const int m = (int)keep.size();
+    if (!m) return;
+    if (R.nplanes > 18 + 3 * cfg().nwalls && !hist_alloc) {  // history-force planes existed before the re-upload
+      for (int d = 0; d < 4; d++) for (int b = 0; b < 2; b++) { hist[d].b[b].ensure(npad); CK(cudaMemsetAsync(hist[d].b[b].p, 0, (size_t)npad * sizeof(double), stream)); hist[d].cur = 0; }
+      hist_alloc = true;
+    }
+    std::vector<double *> ptrs = carry_plane_ptrs();
+    std::vector<double> tmp((size_t)m);
+    for (size_t k = 0; k < ptrs.size() && k < R.planes.size(); k++) {
+      for (int i = 0; i < m; i++) tmp[i] = keep[i] >= 0 ? R.planes[k][keep[i]] : 0.0;
+      CK(cudaMemcpy(ptrs[k], tmp.data(), (size_t)m * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    std::vector<unsigned> wm(m); std::vector<int> fo(m), nh(m), ht((size_t)m * MIG_MAXH, 0);
+    std::vector<D4> hs((size_t)m * MIG_MAXH);
+    memset(hs.data(), 0, hs.size() * sizeof(D4));
+    for (int i = 0; i < m; i++) {
+      const int o = keep[i];
+      wm[i] = o >= 0 ? R.wmask[o] : 0u; fo[i] = o >= 0 ? R.foam[o] : 0; nh[i] = o >= 0 ? R.nh[o] : 0;
+      for (int q = 0; q < nh[i]; q++) {
+        const size_t so = (size_t)o * MIG_MAXH + q, sn = (size_t)i * MIG_MAXH + q;
+        ht[sn] = R.htag[so];
+        hs[sn].x = R.hshear[3 * so]; hs[sn].y = R.hshear[3 * so + 1]; hs[sn].z = R.hshear[3 * so + 2];
+      }
+    }
+    CK(cudaMemcpy(wmask[icur].p, wm.data(), (size_t)m * sizeof(unsigned), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(foam[icur].p, fo.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice));
+    inj_nh.ensure((size_t)m); inj_tag.ensure((size_t)m * MIG_MAXH); inj_shear.ensure((size_t)m * MIG_MAXH);
+    CK(cudaMemcpy(inj_nh.p, nh.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(inj_tag.p, ht.data(), ht.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(inj_shear.p, hs.data(), hs.size() * sizeof(D4), cudaMemcpyHostToDevice));
+  }
+  // re-upload the edited atom table and bring the survivors' state back.  The reference edits the table in place and
+  // forces a re-neighbouring at the next step (library.cpp:486-490, :606-611); here the table is rebuilt at once.
+  void reinject(const RowCarry &R, const std::vector<int> &keep) {
+    const long long step = cfg().ntimestep;
+    load_atoms();
+    restore_rows(R, keep);
+    inject_pending = true;
+    // bins + list with the carried contact history.  No force evaluation: the reference does not run Verlet::setup
+    // here (`run N pre no`), the next half-kick uses the stored f(n) -- which does not know the injected particles
+    // yet -- and an extra evaluation would apply the Coulomb rescale of the shear springs once more
+    // (pair_gran_hertzFix_history.cpp:244-252 is not guarded by shearupdate).
+    setup(false);
+    inject_pending = false;
+    cfg().ntimestep = step;
+    CK(cudaStreamSynchronize(stream));
+  }
+
   void sync_host_atoms() {
     if (!loaded || !nlocal) return;
     const int m = nlocal;
@@ -1404,7 +1522,12 @@ class Engine {
     script.mask = mk;
   }
   void create_particles(int np, const double *pos, const double *tagd, double diameter, double rho, int type, const double *vel) {
+    const bool carry = carry_enabled() && nlocal > 0;
+    RowCarry R;
+    if (carry) save_rows(R);
     sync_host_atoms();
+    std::vector<int> keep;
+    for (size_t i = 0; i < script.atoms.size(); i++) keep.push_back((int)i);
     const int active = cfg().find_group("active");  // library.cpp:447-450: mask = 1 | bit("active")
     for (int m = 0; m < np; m++) {
       script.add_atom((int)tagd[m], type, diameter, rho, pos + 3 * (size_t)m, vel);
@@ -1412,11 +1535,17 @@ class Engine {
       const double rad = 0.5 * diameter;
       script.atoms.rmass.back() = 4.0 * SEDI_PI_LIBRARY / 3.0 * rad * rad * rad * rho;
       script.mask.back() = 1 | active;
+      keep.push_back(-1);
     }
     loaded = false; setup_done = false;
+    if (carry) reinject(R, keep);
   }
   void delete_particles(const int *list, int nd) {  // list holds atom tags (library.cpp:507-621)
+    const bool carry = carry_enabled() && nlocal > 0;
+    RowCarry R;
+    if (carry) save_rows(R);
     sync_host_atoms();
+    std::vector<int> keep;
     std::vector<int> del(list, list + nd);
     std::sort(del.begin(), del.end());
     AtomData &a = script.atoms, b;
@@ -1426,9 +1555,11 @@ class Engine {
       b.tag.push_back(a.tag[i]); b.type.push_back(a.type[i]); b.radius.push_back(a.radius[i]); b.rmass.push_back(a.rmass[i]);
       for (int d = 0; d < 3; d++) { b.x.push_back(a.x[3 * i + d]); b.v.push_back(a.v[3 * i + d]); b.omega.push_back(a.omega[3 * i + d]); }
       mk.push_back(script.mask[i]);
+      keep.push_back((int)i);
     }
     script.atoms = b; script.mask = mk;
     loaded = false; setup_done = false;
+    if (carry) reinject(R, keep);
   }
 };
 

@@ -394,3 +394,56 @@ def test_smoothing_on_graded_stacked_mesh(oracle_mod):
     assert rel_err(got_s, ref_s) < 1e-9 and rel_err(got_v, ref_v) < 1e-9
     assert abs((got_s * V).sum() / (phi * V).sum() - 1.0) < 1e-11
     assert got_s.std() < phi.std() and 0 < e.smooth_last_iters() < 400
+
+
+def test_create_delete_keep_contact_and_wall_history(oracle_mod):
+    """library.cpp:406-621 edits the atom table in place: the other particles keep their contact history
+    (FixShearHistory), wall history and per-atom fix arrays.  A particle injected far above the bed and deleted again
+    must leave the bed's trajectory where an undisturbed run puts it (shear springs are loaded: a run that dropped the
+    history at the injection ends measurably elsewhere)."""
+    import os
+    case = cases.fluidized_bed(dims=(8, 8, 8), vjit=0.2)          # lively bed: tangential springs get loaded
+    top = case["box_hi"]
+    pos = np.array([[0.5 * top[0], 0.97 * top[1], 0.5 * top[2]]])
+
+    def run(disturb, reset=False):
+        if reset:
+            os.environ["SEDI_INJECT_RESET"] = "1"
+        try:
+            e = make_engine(case)
+            e.command("group active type 1")
+            m = float(case["rho"][0] * np.pi / 6.0 * case["diam"][0] ** 3)
+            e.put_local_info(np.tile([0.0, 0.2 * 9.8 * m, 0.0], (len(case["tag"]), 1)), case["tag"])
+            e.step(150)
+            if disturb:
+                e.create_particle(pos, [5001.0], 4.0e-4, 2500.0, 1, (0.0, 0.0, 0.0))
+                assert e.get_local_n() == len(case["tag"]) + 1
+            e.step(60)
+            if disturb:
+                e.delete_particle([5001])
+                assert e.get_local_n() == len(case["tag"])
+            e.step(150)
+            st = e.atoms()
+            pr = e.pairs()
+            ws = e.wall_shear(1)
+            e.close()
+            return st, pr, ws
+        finally:
+            os.environ.pop("SEDI_INJECT_RESET", None)
+
+    ref, pref, wref = run(False)
+    got, pgot, wgot = run(True)
+    L = float(np.abs(case["box_hi"] - case["box_lo"]).max())
+    vmax = np.abs(ref["v"]).max()
+    assert np.array_equal(got["tag"], ref["tag"])
+    ex, ev = np.abs(got["x"] - ref["x"]).max() / L, np.abs(got["v"] - ref["v"]).max() / vmax
+    assert ex < 1e-12 and ev < 1e-12, (ex, ev)      # measured: bitwise identical
+    assert rel_err(wgot, wref) < 1e-6 and np.abs(wref).max() > 0
+    # loaded springs exist, and they are the same springs
+    key = lambda p: np.lexsort((p["tj"], p["ti"]))
+    a, b = key(pref), key(pgot)
+    assert np.array_equal(pref["ti"][a], pgot["ti"][b]) and np.array_equal(pref["tj"][a], pgot["tj"][b])
+    assert np.abs(pref["shear"]).max() > 0 and rel_err(pgot["shear"][b], pref["shear"][a]) < 1e-6
+    # control: the old behaviour (history dropped at the edit) does not pass this bar
+    lost, _, _ = run(True, reset=True)
+    assert np.abs(lost["v"] - ref["v"]).max() / vmax > 1e-5
