@@ -25,6 +25,11 @@ struct CloudProperties {          // constant/cloudProperties + transportPropert
   int subCycles;
   double g[3];
   bool particleDrag, particlePressureGrad, particleBuoyancy, particleAddedMass, particleLift;
+  bool particleHistoryForce, lubricationForce;        // enhancedCloud.C:595-598 (single GPU for the history force)
+  double inletForce[3];           // enhancedCloud.C:600-608; active inside inletBox when |inletForce| > 0
+  double inletBox[9];             // x1 x2 y1 y2 z1 z2 r1 r2 - (softParticleCloud.C:471, pointInRegion :1354-1415)
+  int addParticleOption;          // 1 box, 2 hollow cylinder
+  double addParticleBoxEccentricity[3];
   double nub, rhob;
   double diffusionBandWidth;      // 0 = pure PCM, no smoothing (cases/.../expWachem_PCM)
   int diffusionSteps;
@@ -32,9 +37,11 @@ struct CloudProperties {          // constant/cloudProperties + transportPropert
   bool UfSmooth, UpSmooth, dragSmooth, alphaSmooth;   // defaults true (enhancedCloud.C:573-576)
   CloudProperties()
       : dragModel("ErgunWenYu"), subCycles(1), particleDrag(true), particlePressureGrad(true), particleBuoyancy(false),
-        particleAddedMass(false), particleLift(false), nub(1e-6), rhob(1000.0), diffusionBandWidth(0.0), diffusionSteps(0),
+        particleAddedMass(false), particleLift(false), particleHistoryForce(false), lubricationForce(false), addParticleOption(0), nub(1e-6), rhob(1000.0), diffusionBandWidth(0.0), diffusionSteps(0),
         UfSmooth(true), UpSmooth(true), dragSmooth(true), alphaSmooth(true) {
     g[0] = g[1] = g[2] = 0.0; smoothDirection[0] = smoothDirection[1] = smoothDirection[2] = 1.0;
+    for (int k = 0; k < 3; k++) inletForce[k] = addParticleBoxEccentricity[k] = 0.0;
+    for (int k = 0; k < 9; k++) inletBox[k] = 0.0;
   }
 };
 
@@ -44,6 +51,21 @@ class enhancedCloud {
   enhancedCloud(void *lmp, const double lo[3], const double hi[3], const int ncell[3], const CloudProperties &cp, double deltaT)
       : lmp_(lmp), cp_(cp), deltaT_(deltaT) {
     sedi_mesh_box(lmp_, lo, hi, ncell);
+    init();
+  }
+  // graded / stacked-block blockMesh: face coordinates per axis (ncell[d] + 1 values, e.g. from mesh.points()) and the
+  // solver's label of every tensor cell (NULL = i + nx (j + ny k)); cases/example-cases/BL24-TH1, transport-bedload
+  enhancedCloud(void *lmp, const int ncell[3], const double *xfaces, const double *yfaces, const double *zfaces, const int *cellLabel,
+                const CloudProperties &cp, double deltaT)
+      : lmp_(lmp), cp_(cp), deltaT_(deltaT) {
+    sedi_mesh_rectilinear(lmp_, ncell, xfaces, yfaces, zfaces, cellLabel);
+    init();
+  }
+
+ private:
+  void init() {
+    const CloudProperties &cp = cp_;
+    const double deltaT = deltaT_;
     nCells_ = sedi_mesh_ncells(lmp_);
     const int model = (cp.dragModel == "SyamlalOBrien") ? SEDI_DRAG_SYAMLAL_OBRIEN_ID : SEDI_DRAG_ERGUN_WENYU_ID;
     int flags = 0;
@@ -52,6 +74,12 @@ class enhancedCloud {
     if (cp.particleBuoyancy) flags |= SEDI_FORCE_BUOY_BIT;
     if (cp.particleAddedMass) flags |= SEDI_FORCE_ADDEDMASS_BIT;
     if (cp.particleLift) flags |= SEDI_FORCE_LIFT_BIT;
+    if (cp.particleHistoryForce) flags |= SEDI_FORCE_HISTORY_BIT;
+    if (cp.lubricationForce) flags |= SEDI_FORCE_WALL_LUB_BIT;
+    if (cp.addParticleOption > 0 && (cp.inletForce[0] != 0.0 || cp.inletForce[1] != 0.0 || cp.inletForce[2] != 0.0)) {
+      flags |= SEDI_FORCE_INLET_BIT;
+      sedi_coupling_inlet(lmp_, cp.inletForce, cp.inletBox, cp.addParticleOption, cp.addParticleBoxEccentricity);
+    }
     sedi_coupling_config(lmp_, model, flags, cp.nub, cp.rhob, cp.g, deltaT);
     int sflags = 0;
     if (cp.UfSmooth) sflags |= SEDI_SMOOTH_UF_BIT;
@@ -71,6 +99,8 @@ class enhancedCloud {
     lammps_step(lmp_, 0);                      // softParticleCloud.C:189
     sedi_scatter_alpha_u(lmp_, gamma_.data(), Ue_.data());  // enhancedCloud.C:635 particleToEulerianField()
   }
+
+ public:
 
   // fluid fields of the current time step (Ub, grad p, DDtUb, curl Ub): pointers to [C][3] doubles, NULL = absent
   void setFluidFields(const double *Ub, const double *gradp, const double *DDtUb, const double *curlUb) {
