@@ -150,9 +150,9 @@ inline std::vector<std::string> tokenize(const char *line) {
 }
 
 struct ScriptAction {
-  enum Kind { NONE, RUN, READ_DATA } kind;
+  enum Kind { NONE, RUN, READ_DATA, WRITE_RESTART, READ_RESTART, RESTART_EVERY } kind;
   long long nsteps;
-  std::string path;
+  std::string path, path2;
   ScriptAction() : kind(NONE), nsteps(0) {}
 };
 
@@ -397,9 +397,18 @@ class Script {
       }
     }
     else if (c == "atom_modify" || c == "communicate" || c == "comm_modify" || c == "thermo" ||
-             c == "thermo_style" || c == "thermo_modify" || c == "restart" || c == "dimension" || c == "echo" ||
+             c == "thermo_style" || c == "thermo_modify" || c == "dimension" || c == "echo" ||
              c == "log" || c == "dump_modify" || c == "compute" || c == "neigh_modify") {
       // accepted, no effect on the hot path (neigh_modify delay 0 every 1 check yes is the only mode implemented)
+    }
+    else if (c == "write_restart") { if (a.size() < 2) fatal("Illegal write_restart command"); act.kind = ScriptAction::WRITE_RESTART; act.path = a[1]; }
+    else if (c == "read_restart") { if (a.size() < 2) fatal("Illegal read_restart command"); act.kind = ScriptAction::READ_RESTART; act.path = a[1]; }
+    else if (c == "restart") {   // restart 0 | restart N file | restart N file1 file2
+      if (a.size() < 2) fatal("Illegal restart command");
+      act.kind = ScriptAction::RESTART_EVERY; act.nsteps = atoll(a[1].c_str());
+      if (act.nsteps > 0 && a.size() < 3) fatal("Illegal restart command");
+      if (a.size() > 2) act.path = a[2];
+      if (a.size() > 3) act.path2 = a[3];
     }
     else if (c == "units") { if (a.size() > 1 && a[1] != "lj") fatal("Only lj units are supported (reference inputs set none)"); }
     else if (c == "boundary") {

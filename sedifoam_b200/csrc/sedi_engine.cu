@@ -258,7 +258,7 @@ class Engine {
         beta_pair(0), pair_evals_unique(0), nbuilds(0), pair_evals(0), steps_done(0), launches(0), list_gran_dir(0), list_type_dir(0), list_gran_img(0),
         list_type_img(0), chunk(16), last_step_ms(0), count_in_kernel(false), have_mesh(false), ncells(0), have_DDtU(false),
         have_curlU(false), have_gradp(false), have_Uf(false), drag_model(0), force_flags(SEDI_FORCE_DRAG | SEDI_FORCE_PGRAD), nub(1e-6), rhob(1000.0),
-        deltaT(1.0), inject_pending(false), hist_alloc(false), have_UfOld(false), time_index(0), inlet_option(0), want_diag(false), smooth_b(0.0), smooth_steps(0), smooth_flags(0), smooth_iters_last(0), prof_on(false), prof_ms(0), prof_steps(0) {
+        deltaT(1.0), restart_every(0), restart_toggle(0), restart_pending(false), restart_carry(0), inject_pending(false), hist_alloc(false), have_UfOld(false), time_index(0), inlet_option(0), want_diag(false), smooth_b(0.0), smooth_steps(0), smooth_flags(0), smooth_iters_last(0), prof_on(false), prof_ms(0), prof_steps(0) {
     gvec[0] = gvec[1] = gvec[2] = 0.0;
     memset(inlet_force, 0, sizeof(inlet_force)); memset(inlet_box, 0, sizeof(inlet_box)); memset(inlet_ecc, 0, sizeof(inlet_ecc));
     smooth_D[0] = smooth_D[1] = smooth_D[2] = 1.0;
@@ -329,6 +329,9 @@ class Engine {
     params_dirty = true;
     if (a.kind == ScriptAction::READ_DATA) loaded = false;
     if (a.kind == ScriptAction::RUN) run(a.nsteps);
+    if (a.kind == ScriptAction::WRITE_RESTART) write_restart(a.path);
+    if (a.kind == ScriptAction::READ_RESTART) read_restart(a.path);
+    if (a.kind == ScriptAction::RESTART_EVERY) { restart_every = a.nsteps; restart_path[0] = a.path; restart_path[1] = a.path2; restart_toggle = 0; }
   }
 
   void file(const char *path) {
@@ -793,6 +796,7 @@ class Engine {
 
   // ---- Verlet::setup (first `run` of the session, even with `pre no`; softParticleCloud.C:189 lammps_step(0)) -----
   void setup(bool evaluate_forces = true) {
+    if (restart_pending) { setup_from_restart(); return; }
     if (!loaded) load_atoms();
     need_device();
     dt_init = cfg().dt;
@@ -897,9 +901,17 @@ class Engine {
           const long long to_next = ev - (cfg().ntimestep % ev);
           if (to_next < seg) seg = to_next;
         }
+      if (restart_every > 0) { const long long to_next = restart_every - (cfg().ntimestep % restart_every); if (to_next < seg) seg = to_next; }
       run_segment(seg);
       remaining -= seg;
       if (!cfg().dumps.empty()) write_dumps();
+      if (restart_every > 0 && cfg().ntimestep % restart_every == 0) {
+        std::string p = restart_path[restart_path[1].empty() ? 0 : restart_toggle];
+        if (!restart_path[1].empty()) restart_toggle ^= 1;
+        const size_t star = p.find('*');
+        if (star != std::string::npos) { char b[32]; snprintf(b, sizeof(b), "%lld", cfg().ntimestep); p.replace(star, 1, b); }
+        write_restart(p);
+      }
     }
   }
 
@@ -1142,6 +1154,14 @@ class Engine {
   // and axis-aligned blocks stacked into one tensor-product grid, cases/example-cases/BL24-TH1): face coordinates
   // per axis as the host mesh has them, plus the host's cell label of every tensor cell (NULL = i + nx (j + ny k)).
   Buf<double> mesh_faces[3], mesh_width[3], cg_diag;
+  // checkpoint / resume (`restart N file`, `write_restart`, `read_restart`): own binary format, see write_restart
+  long long restart_every;
+  std::string restart_path[2];
+  int restart_toggle;
+  bool restart_pending;
+  struct RowCarryBox;             // defined with RowCarry below
+  RowCarryBox *restart_carry;
+  std::vector<std::string> restart_wall_ids;
   // particle injection / deletion: state of the surviving particles carried across the re-upload
   bool inject_pending;
   Buf<int> inj_nh, inj_tag;
@@ -1509,6 +1529,119 @@ class Engine {
     inject_pending = false;
     cfg().ntimestep = step;
     CK(cudaStreamSynchronize(stream));
+  }
+
+  // ---- checkpoint / resume ---------------------------------------------------------------------------------------
+  // The reference restarts its LAMMPS side with LAMMPS' own `restart` / `read_restart` (commented out in the shipped
+  // inputs, e.g. multiParticlesCollideDia/in.lammps:37); the per-atom state that must survive is what
+  // FixWallGranFix::pack_restart (fix_wall_granFix.cpp:750-777), FixFluidDrag's per-atom arrays and FixShearHistory
+  // carry.  LAMMPS' binary layout is not reproduced: the file is this library's own (magic "SEDIRST1", little endian):
+  // header, atom table, the RowCarry planes, wall-touch bits, Foam rank, contact history as (partner tag, shear) lists.
+  // Resume is exact: no force evaluation at the restart (stored f(n), torque(n) are used by the next half-kick).
+  struct RowCarryBox { RowCarry R; };
+  static void wr(FILE *fp, const void *p, size_t n) { if (n && fwrite(p, 1, n, fp) != n) fatal("write_restart: short write"); }
+  static void rd(FILE *fp, void *p, size_t n) { if (n && fread(p, 1, n, fp) != n) fatal("read_restart: file is truncated"); }
+  std::string resolve_path(const std::string &path) const {
+    const char *dir = getenv("SEDI_DUMP_DIR");
+    if (dir && path.size() && path[0] != '/') return std::string(dir) + "/" + path;
+    return path;
+  }
+  void write_restart(const std::string &path) {
+    if (comm.nranks > 1) fatal("write_restart: single GPU only in this version");
+    if (!setup_done) setup();
+    RowCarry R;
+    save_rows(R);
+    sync_host_atoms();
+    const AtomData &a = script.atoms;
+    const SimConfig &c = cfg();
+    FILE *fp = fopen(resolve_path(path).c_str(), "wb");
+    if (!fp) fatal("Cannot open restart file", path.c_str());
+    const char magic[8] = {'S', 'E', 'D', 'I', 'R', 'S', 'T', '1'};
+    wr(fp, magic, 8);
+    const long long step = c.ntimestep; wr(fp, &step, 8);
+    wr(fp, &c.dt, 8); wr(fp, &dt_init, 8);
+    wr(fp, &c.ntypes, 4); wr(fp, c.periodic, 12); wr(fp, c.boxlo, 24); wr(fp, c.boxhi, 24);
+    const int n = (int)a.size(), nw = c.nwalls, hh = hist_alloc ? 1 : 0;
+    wr(fp, &n, 4); wr(fp, &nw, 4); wr(fp, &hh, 4); wr(fp, &time_index, 4);
+    for (size_t k = 0; k < c.fixes.size(); k++) if (c.fixes[k].kind == FIX_WALL_GRAN) {
+      const int len = (int)strlen(c.fixes[k].id), wi = c.fixes[k].wall_index;
+      wr(fp, &wi, 4); wr(fp, &len, 4); wr(fp, c.fixes[k].id, len);
+    }
+    wr(fp, a.tag.data(), 4 * (size_t)n); wr(fp, a.type.data(), 4 * (size_t)n); wr(fp, script.mask.data(), 4 * (size_t)n);
+    wr(fp, a.x.data(), 24 * (size_t)n); wr(fp, a.v.data(), 24 * (size_t)n); wr(fp, a.omega.data(), 24 * (size_t)n);
+    wr(fp, a.radius.data(), 8 * (size_t)n); wr(fp, a.rmass.data(), 8 * (size_t)n);
+    const int np = R.nplanes; wr(fp, &np, 4);
+    for (int k = 0; k < np; k++) wr(fp, R.planes[k].data(), 8 * (size_t)n);
+    wr(fp, R.wmask.data(), 4 * (size_t)n); wr(fp, R.foam.data(), 4 * (size_t)n);
+    wr(fp, R.nh.data(), 4 * (size_t)n); wr(fp, R.htag.data(), 4 * (size_t)n * MIG_MAXH); wr(fp, R.hshear.data(), 24 * (size_t)n * MIG_MAXH);
+    fclose(fp);
+  }
+  void read_restart(const std::string &path) {
+    if (comm.nranks > 1) fatal("read_restart: single GPU only in this version");
+    FILE *fp = fopen(resolve_path(path).c_str(), "rb");
+    if (!fp) fatal("Cannot open restart file", path.c_str());
+    char magic[8]; rd(fp, magic, 8);
+    if (memcmp(magic, "SEDIRST1", 8)) fatal("read_restart: not a libsedi_b200 restart file", path.c_str());
+    SimConfig &c = cfg();
+    long long step; rd(fp, &step, 8); c.ntimestep = step;
+    double dt_file, dt0; rd(fp, &dt_file, 8); rd(fp, &dt0, 8); c.dt = dt_file;
+    rd(fp, &c.ntypes, 4); rd(fp, c.periodic, 12); rd(fp, c.boxlo, 24); rd(fp, c.boxhi, 24); c.have_box = 1;
+    for (int d = 0; d < 3; d++) c.boundary_str[d] = c.periodic[d] ? "pp" : "ff";
+    int n, nw, hh, tix; rd(fp, &n, 4); rd(fp, &nw, 4); rd(fp, &hh, 4); rd(fp, &tix, 4);
+    if (n < 0 || nw < 0 || nw > MAX_WALLS) fatal("read_restart: corrupt header");
+    time_index = tix;
+    restart_wall_ids.assign(nw, std::string());
+    for (int k = 0; k < nw; k++) {
+      int wi, len; rd(fp, &wi, 4); rd(fp, &len, 4);
+      if (wi < 0 || wi >= nw || len < 0 || len > 4096) fatal("read_restart: corrupt wall table");
+      std::string id(len, ' '); rd(fp, &id[0], len); restart_wall_ids[wi] = id;
+    }
+    AtomData &a = script.atoms;
+    a = AtomData();
+    a.tag.resize(n); a.type.resize(n); script.mask.resize(n); a.x.resize(3 * (size_t)n); a.v.resize(3 * (size_t)n); a.omega.resize(3 * (size_t)n);
+    a.radius.resize(n); a.rmass.resize(n);
+    rd(fp, a.tag.data(), 4 * (size_t)n); rd(fp, a.type.data(), 4 * (size_t)n); rd(fp, script.mask.data(), 4 * (size_t)n);
+    rd(fp, a.x.data(), 24 * (size_t)n); rd(fp, a.v.data(), 24 * (size_t)n); rd(fp, a.omega.data(), 24 * (size_t)n);
+    rd(fp, a.radius.data(), 8 * (size_t)n); rd(fp, a.rmass.data(), 8 * (size_t)n);
+    if (!restart_carry) restart_carry = new RowCarryBox();
+    RowCarry &R = restart_carry->R;
+    R = RowCarry();
+    R.n = n;
+    int np; rd(fp, &np, 4);
+    if (np != 18 + 3 * nw + 4 * hh) fatal("read_restart: corrupt plane table");
+    R.nplanes = np;
+    R.planes.assign(np, std::vector<double>((size_t)n));
+    for (int k = 0; k < np; k++) rd(fp, R.planes[k].data(), 8 * (size_t)n);
+    R.wmask.resize(n); R.foam.resize(n); R.nh.resize(n); R.htag.resize((size_t)n * MIG_MAXH); R.hshear.resize((size_t)n * MIG_MAXH * 3);
+    rd(fp, R.wmask.data(), 4 * (size_t)n); rd(fp, R.foam.data(), 4 * (size_t)n);
+    rd(fp, R.nh.data(), 4 * (size_t)n); rd(fp, R.htag.data(), 4 * (size_t)n * MIG_MAXH); rd(fp, R.hshear.data(), 24 * (size_t)n * MIG_MAXH);
+    fclose(fp);
+    loaded = false; setup_done = false; restart_pending = true;
+  }
+  // first setup after read_restart: the fixes are known now, so the stored per-atom state can be matched to them
+  // (LAMMPS matches restart_peratom data by fix id; wall history is matched by the wall fix's id here)
+  void setup_from_restart() {
+    restart_pending = false;
+    RowCarry &F = restart_carry->R;
+    const SimConfig &c = cfg();
+    const int n = F.n, nw_file = (int)restart_wall_ids.size(), hh = (F.nplanes - 18 - 3 * nw_file) / 4;
+    RowCarry R;
+    R.n = n;
+    R.wmask.assign(n, 0u); R.foam = F.foam; R.nh = F.nh; R.htag = F.htag; R.hshear = F.hshear;
+    for (int k = 0; k < 18; k++) R.planes.push_back(F.planes[k]);
+    std::vector<int> file_wall(c.nwalls, -1);
+    for (size_t k = 0; k < c.fixes.size(); k++) if (c.fixes[k].kind == FIX_WALL_GRAN)
+      for (int w = 0; w < nw_file; w++) if (restart_wall_ids[w] == std::string(c.fixes[k].id)) file_wall[c.fixes[k].wall_index] = w;
+    for (int w = 0; w < c.nwalls; w++) for (int d = 0; d < 3; d++)
+      R.planes.push_back(file_wall[w] >= 0 ? F.planes[18 + 3 * file_wall[w] + d] : std::vector<double>((size_t)n, 0.0));
+    for (int i = 0; i < n; i++) for (int w = 0; w < c.nwalls; w++) if (file_wall[w] >= 0 && ((F.wmask[i] >> file_wall[w]) & 1u)) R.wmask[i] |= (1u << w);
+    if (hh) for (int d = 0; d < 4; d++) R.planes.push_back(F.planes[18 + 3 * nw_file + d]);
+    R.nplanes = (int)R.planes.size();
+    std::vector<int> keep(n);
+    for (int i = 0; i < n; i++) keep[i] = i;
+    hist_alloc = false;
+    reinject(R, keep);
+    delete restart_carry; restart_carry = 0;
   }
 
   void sync_host_atoms() {

@@ -447,3 +447,45 @@ def test_create_delete_keep_contact_and_wall_history(oracle_mod):
     # control: the old behaviour (history dropped at the edit) does not pass this bar
     lost, _, _ = run(True, reset=True)
     assert np.abs(lost["v"] - ref["v"]).max() / vmax > 1e-5
+
+
+def test_restart_resumes_exactly(oracle_mod, tmp_path):
+    """`write_restart` / `read_restart` / `restart N file` (SURVEY 8f rank 4; per-atom state of FixWallGranFix::pack_restart
+    fix_wall_granFix.cpp:750-777, fix fdrag's arrays, FixShearHistory): a run resumed from the file ends bitwise where the
+    uninterrupted run ends -- contact history, wall history and the stored forces all travel."""
+    import os
+    from sedifoam_b200 import Lammps
+    case = cases.fluidized_bed(dims=(8, 8, 8), vjit=0.2)
+    old = os.environ.get("SEDI_DUMP_DIR")
+    os.environ["SEDI_DUMP_DIR"] = str(tmp_path)
+    try:
+        a = make_engine(case)
+        m = float(case["rho"][0] * np.pi / 6.0 * case["diam"][0] ** 3)
+        a.put_local_info(np.tile([0.0, 0.2 * 9.8 * m, 0.0], (len(case["tag"]), 1)), case["tag"])
+        a.command("restart 100 bed.*.rst")
+        a.step(150)
+        a.command("restart 0")
+        a.command("write_restart bed_150.rst")
+        a.step(150)
+        sa, pa, wa = a.atoms(), a.pairs(), a.wall_shear(1)
+        a.close()
+        assert os.path.exists(tmp_path / "bed.100.rst") and not os.path.exists(tmp_path / "bed.200.rst")
+        for fname, nmore in (("bed_150.rst", 150), ("bed.100.rst", 200)):
+            b = Lammps()
+            b.command("atom_style sphere")
+            b.command("read_restart " + fname)
+            b.commands(case["script"])
+            b.step(nmore)
+            sb, pb, wb = b.atoms(), b.pairs(), b.wall_shear(1)
+            b.close()
+            assert np.array_equal(sb["tag"], sa["tag"])
+            assert np.array_equal(sb["x"], sa["x"]) and np.array_equal(sb["v"], sa["v"]) and np.array_equal(sb["omega"], sa["omega"]), fname
+            key = lambda p: np.lexsort((p["tj"], p["ti"]))
+            ka, kb = key(pa), key(pb)
+            assert np.array_equal(pa["ti"][ka], pb["ti"][kb]) and np.array_equal(pa["shear"][ka], pb["shear"][kb]) and np.abs(pa["shear"]).max() > 0
+            assert np.array_equal(wa, wb) and np.abs(wa).max() > 0
+    finally:
+        if old is None:
+            os.environ.pop("SEDI_DUMP_DIR", None)
+        else:
+            os.environ["SEDI_DUMP_DIR"] = old
