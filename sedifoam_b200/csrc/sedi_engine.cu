@@ -256,7 +256,7 @@ class Engine {
       : device(0), dev_ready(false), loaded(false), setup_done(false), params_dirty(true), cell_valid(false), stream(0), n(0),
         nlocal(0), nghost(0), npad(0), maxtag(0), cur(0), icur(0), ecur(0), cutneighmax(0), dt_init(0), lub_R0(0), lub_RT0(0), lub_RS0(0),
         beta_pair(0), pair_evals_unique(0), nbuilds(0), pair_evals(0), steps_done(0), launches(0), list_gran_dir(0), list_type_dir(0), list_gran_img(0),
-        list_type_img(0), chunk(16), last_step_ms(0), count_in_kernel(false), have_mesh(false), ncells(0), have_DDtU(false),
+        list_type_img(0), chunk(50), last_step_ms(0), count_in_kernel(false), have_mesh(false), ncells(0), have_DDtU(false),
         have_curlU(false), have_gradp(false), have_Uf(false), drag_model(0), force_flags(SEDI_FORCE_DRAG | SEDI_FORCE_PGRAD), nub(1e-6), rhob(1000.0),
         deltaT(1.0), restart_every(0), restart_toggle(0), restart_pending(false), restart_carry(0), inject_pending(false), hist_alloc(false), have_UfOld(false), time_index(0), inlet_option(0), want_diag(false), smooth_b(0.0), smooth_steps(0), smooth_flags(0), smooth_iters_last(0), prof_on(false), prof_ms(0), prof_steps(0) {
     gvec[0] = gvec[1] = gvec[2] = 0.0;
