@@ -267,6 +267,9 @@ class Engine {
     memset(&mesh, 0, sizeof(mesh));
     const char *e = getenv("SEDI_CHUNK");
     if (e && atoi(e) > 0) chunk = atoi(e);
+    graph_on = true;
+    e = getenv("SEDI_GRAPH");
+    if (e && atoi(e) == 0) graph_on = false;
     use_rows = false;
     e = getenv("SEDI_KSTEP_PATH");
     if (e && !strcmp(e, "rows")) use_rows = true;
@@ -276,6 +279,7 @@ class Engine {
   }
 
   ~Engine() {
+    if (dev_ready) { cudaSetDevice(device); destroy_graphs(); }
     for (size_t k = 0; k < script.cfg.dumps.size(); k++) if (script.cfg.dumps[k].fp) { fclose(script.cfg.dumps[k].fp); script.cfg.dumps[k].fp = 0; }
     if (!dev_ready) return;
     cudaSetDevice(device);
@@ -410,6 +414,7 @@ class Engine {
     }
     alloc_rows(rows);
     cur = 0; icur = 0; ecur = 0;
+    drop_graphs();
     hist_alloc = false;   // history-force state restarts with the atom table (softParticle.C:63-64: n0 = 0, sumDeltaFb = 0)
     ell[0].valid = ell[1].valid = false; ell[0].rows_valid = ell[1].rows_valid = false; ell[0].hist_in_rows = ell[1].hist_in_rows = false;
     if (n) {
@@ -559,6 +564,7 @@ class Engine {
       }
     }
     params_dirty = false;
+    drop_graphs();
   }
 
   // per-launch part of the parameter block
@@ -675,6 +681,7 @@ class Engine {
 
   void rebuild() {
     need_device();
+    drop_graphs();
     rows_history_to_ell();
     const SimConfig &c = cfg();
     const int T = 256;
@@ -931,6 +938,40 @@ class Engine {
       const bool mg = comm.nranks > 1;
       if (pending_initial) { launch_initial(in, ++seq); in ^= 1; nk++; if (mg) comm.forward(*this, in, true); }
       if (prof_on) CK(cudaEventRecord(evk0, stream));
+      bool wiggle = false;
+      for (size_t k = 0; k < cfg().fixes.size(); k++) if (cfg().fixes[k].kind == FIX_WALL_GRAN && cfg().fixes[k].wiggle) wiggle = true;
+      if (graph_on && !mg && !wiggle && K == chunk && K > 1) {   // odd-sized remainders after a rebuild are launched directly
+        const int lastflag = (remaining == K) ? 1 : 0;
+        StepGraph *g = 0;
+        for (size_t k = 0; k < graphs.size(); k++) if (graphs[k].in == in && graphs[k].K == K && graphs[k].last == lastflag && graphs[k].seq0 == seq) g = &graphs[k];
+        if (!g || g->stale) {
+          const long long l0 = launches;
+          cudaGraph_t gr;
+          CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+          int cin = in, cseq = seq;
+          for (int s = 0; s < K; s++) { launch_step((lastflag && s == K - 1) ? MODE_LAST : MODE_FUSED, cin, cfg().ntimestep + s + 1, ++cseq); cin ^= 1; }
+          CK(cudaStreamEndCapture(stream, &gr));
+          launches = l0;
+          if (g) {  // same topology, new kernel arguments
+            cudaGraphExecUpdateResultInfo info;
+            if (cudaGraphExecUpdate(g->exec, gr, &info) != cudaSuccess) {
+              cudaGetLastError();
+              CK(cudaGraphExecDestroy(g->exec));
+              CK(cudaGraphInstantiate(&g->exec, gr, 0));
+            }
+            g->stale = false;
+          } else {
+            StepGraph ng; ng.in = in; ng.K = K; ng.last = lastflag; ng.seq0 = seq; ng.stale = false;
+            CK(cudaGraphInstantiate(&ng.exec, gr, 0));
+            if (graphs.size() >= 16) destroy_graphs();
+            graphs.push_back(ng);
+            g = &graphs.back();
+          }
+          CK(cudaGraphDestroy(gr));
+        }
+        CK(cudaGraphLaunch(g->exec, stream));
+        launches += K; seq += K; in ^= (K & 1);
+      } else
       for (int s = 0; s < K; s++) {
         const bool last = (remaining - s == 1);
         launch_step(last ? MODE_LAST : MODE_FUSED, in, cfg().ntimestep + s + 1, ++seq);
@@ -1154,6 +1195,16 @@ class Engine {
   // and axis-aligned blocks stacked into one tensor-product grid, cases/example-cases/BL24-TH1): face coordinates
   // per axis as the host mesh has them, plus the host's cell label of every tensor cell (NULL = i + nx (j + ny k)).
   Buf<double> mesh_faces[3], mesh_width[3], cg_diag;
+  // CUDA graphs of the k_step launches of one chunk (single GPU, no wiggling wall): one graph launch per chunk, so the
+  // sub-step sequence does not depend on the host keeping up with 50 launches.  The kernel arguments baked into a graph
+  // (buffer parity, sequence numbers, list / plane pointers) stay valid until the next rebuild or parameter change.
+  struct StepGraph { int in, K, last, seq0; bool stale; cudaGraphExec_t exec; };
+  std::vector<StepGraph> graphs;
+  bool graph_on;
+  void destroy_graphs() { for (size_t k = 0; k < graphs.size(); k++) cudaGraphExecDestroy(graphs[k].exec); graphs.clear(); }
+  // pointers / parameters changed (rebuild, new script line): the executable graphs are kept and re-parameterised in
+  // place on their next use (cudaGraphExecUpdate), which is much cheaper than instantiating them again
+  void drop_graphs() { for (size_t k = 0; k < graphs.size(); k++) graphs[k].stale = true; }
   // checkpoint / resume (`restart N file`, `write_restart`, `read_restart`): own binary format, see write_restart
   long long restart_every;
   std::string restart_path[2];
