@@ -223,13 +223,20 @@ def write_lammps_files(case, directory):
     return script
 
 
-def four_spheres_collide():
-    """the shipped regression case cases/auto-testing/test-cases/multiParticlesCollideDia (in.lammps, IC_uniform.in,
-    constant/{cloudProperties,transportProperties,environmentalProperties}, blockMeshDict): four spheres of different
-    diameter in water, two of them overlapping at the start, stock gran/hooke/history + wall/gran, SyamlalOBrien,
-    dt_DEM = 1e-5, dt_fluid = 1e-3, subCycles 2; golden dump every 1000 DEM steps in data/origin/p{1..4}.dat."""
-    x = np.array([[5e-2, 7.5e-2, 5e-2], [9e-2, 8.5e-2, 5e-2], [9.2e-2, 8.5e-2, 5e-2], [1.7e-1, 6.5e-2, 5e-2]])
-    d = np.array([3.5e-3, 3.0e-3, 2.5e-3, 2.0e-3])
+def four_spheres_collide(variant="dia"):
+    """the shipped regression cases cases/auto-testing/test-cases/multiParticlesCollideDia and ...CollideRho (in.lammps,
+    IC_uniform.in, constant/{cloudProperties,transportProperties,environmentalProperties}, blockMeshDict): four spheres
+    of different diameter ("dia") or different density ("rho") in water, two of them overlapping at the start, stock
+    gran/hooke/history + wall/gran, SyamlalOBrien, dt_DEM = 1e-5, dt_fluid = 1e-3, subCycles 2; golden dump every 1000
+    DEM steps in data/origin/p{1..4}.dat."""
+    if variant == "rho":
+        x = np.array([[5e-2, 7.5e-2, 5e-2], [9e-2, 8.5e-2, 5e-2], [9.1e-2, 8.5e-2, 5e-2], [1.7e-1, 7.5e-2, 5e-2]])
+        d = np.array([1.5e-3, 1.5e-3, 1.5e-3, 1.5e-3])
+        rho = np.array([4650.0, 3650.0, 2650.0, 1650.0])
+    else:
+        x = np.array([[5e-2, 7.5e-2, 5e-2], [9e-2, 8.5e-2, 5e-2], [9.2e-2, 8.5e-2, 5e-2], [1.7e-1, 6.5e-2, 5e-2]])
+        d = np.array([3.5e-3, 3.0e-3, 2.5e-3, 2.0e-3])
+        rho = 2650.0
     script = """
 neighbor 0.02 bin
 neigh_modify delay 0
@@ -244,7 +251,7 @@ fix xwall all wall/gran 4910.0 NULL 0 NULL 0 0 xplane 0.00 0.20
 fix ywall all wall/gran 4910.0 NULL 0 NULL 0 0 yplane 0.00 0.10
 fix zwall all wall/gran 4910.0 NULL 0 NULL 0 0 zplane 0.00 0.10
 """
-    c = _base(x, d, 2650.0, (0, 0, 0), (0.2, 0.1, 0.1), ("f", "f", "f"), script, 5e-3,
+    c = _base(x, d, rho, (0, 0, 0), (0.2, 0.1, 0.1), ("f", "f", "f"), script, 5e-3,
               extra=dict(name="four_spheres_collide", Uf=(0.0, 0.0, 0.0), g=(0.0, -9.8, 0.0), dt=1e-5, substeps=50))
     c["mesh_n"] = np.array([40, 20, 1], np.int32)
     return c

@@ -236,6 +236,26 @@ def test_create_and_delete_particles(oracle_mod):
     assert np.isfinite(st["x"]).all()
 
 
+def test_four_spheres_rho_golden_dump_gpu(oracle_mod):
+    """second shipped golden case, multiParticlesCollideRho (tolerances: tests/test_oracle_golden.py::check_four_spheres_rho)"""
+    from test_oracle_golden import check_four_spheres_rho
+    case = cases.four_spheres_collide("rho")
+    e = make_engine(case)
+    e.mesh_box(case["mesh_lo"], case["mesh_hi"], case["mesh_n"])
+    e.coupling_config(DRAG_SYAMLAL_OBRIEN, FORCE_DRAG | FORCE_PGRAD, case["nub"], case["rhob"], case["g"], 1e-3)
+    Uf, _, gradp = cases.uniform_fields(case)
+    e.put_cell_fields(Uf, None, gradp)
+    e.setup()
+    rows = []
+    for k in range(400):
+        e.scatter_alpha_u(device_only=True)
+        e.compute_fluid_force()
+        e.sedi_step(50)
+        if (k + 1) % 20 == 0:
+            rows.append(e.atoms())
+    check_four_spheres_rho(rows)
+
+
 def test_four_spheres_golden_dump_gpu(oracle_mod):
     """shipped case multiParticlesCollideDia through the device-resident coupling API, against the reference's own
     dump rows (tolerances and their reason: tests/test_oracle_golden.py::check_four_spheres)"""

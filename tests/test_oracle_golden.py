@@ -69,6 +69,27 @@ def test_smoothing_restatement_known_answers(oracle_mod):
 GOLD4 = os.path.join(HERE, "golden", "multiParticlesCollideDia")
 
 
+GOLD4_RHO = os.path.join(HERE, "golden", "multiParticlesCollideRho")
+
+
+def check_four_spheres_rho(rows):
+    """same check against cases/auto-testing/test-cases/multiParticlesCollideRho/data/origin/p{1..4}.dat (equal diameters,
+    densities 4650 / 3650 / 2650 / 1650).  Isolated spheres 1 and 4: within 0.1 mm and 1 % of the settling speed over
+    20 000 DEM steps; the colliding pair 2/3 (thrown apart along x, then a wall bounce whose instant differs by a few
+    steps without the entrained fluid): within 3 mm after 50 mm of travel."""
+    for p in range(4):
+        g = np.loadtxt(os.path.join(GOLD4_RHO, "p%d.dat" % (p + 1)))
+        assert g.shape == (21, 10)
+        vt = np.abs(g[:, 8]).max()
+        ex = max(np.abs(rows[n]["x"][p] - g[n + 1][4:7]).max() for n in range(20))
+        ev = max(np.abs(rows[n]["v"][p] - g[n + 1][7:10]).max() for n in range(20))
+        if p in (0, 3):
+            assert ev < 0.01 * vt and ex < 2.0e-4, (p, ex, ev)
+        else:
+            assert ex < 3.0e-3 and ev < 0.45 * vt, (p, ex, ev)
+        assert abs(rows[0]["radius"][p] * 2 - g[0][2]) < 1e-12 and abs(rows[0]["rmass"][p] / g[0][3] - 1) < 1e-5
+
+
 def check_four_spheres(rows):
     """rows[n] = state sorted by tag after (n+1)*1000 DEM steps, against data/origin/p{1..4}.dat (LAMMPS `dump custom`
     rows `id type diameter mass x y z vx vy vz`, 6 significant digits).  The fluid is prescribed quiescent here (no
@@ -88,8 +109,12 @@ def check_four_spheres(rows):
         assert abs(rows[0]["radius"][p] * 2 - g[0][2]) < 1e-12 and abs(rows[0]["rmass"][p] / g[0][3] - 1) < 1e-5
 
 
-def test_four_spheres_golden_dump(oracle_mod):
-    case = cases.four_spheres_collide()
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("variant", ["dia", "rho"])
+def test_four_spheres_golden_dump(oracle_mod, variant):
+    case = cases.four_spheres_collide(variant)
     o = make_oracle(oracle_mod, case)
     o.setup()
     lo, hi, nc = case["mesh_lo"], case["mesh_hi"], case["mesh_n"]
@@ -108,4 +133,4 @@ def test_four_spheres_golden_dump(oracle_mod):
         if (k + 1) % 20 == 0:
             a = o.atoms(); a["radius"] = radius; a["rmass"] = rmass
             rows.append(a)
-    check_four_spheres(rows)
+    (check_four_spheres if variant == "dia" else check_four_spheres_rho)(rows)
