@@ -900,6 +900,7 @@ class Engine {
     if (!setup_done) setup();
     if (nsteps <= 0) return;
     long long remaining = nsteps;
+    double ms_total = 0.0;
     while (remaining > 0) {
       long long seg = remaining;
       if (!getenv("SEDI_NO_DUMP"))
@@ -910,6 +911,7 @@ class Engine {
         }
       if (restart_every > 0) { const long long to_next = restart_every - (cfg().ntimestep % restart_every); if (to_next < seg) seg = to_next; }
       run_segment(seg);
+      ms_total += last_step_ms;
       remaining -= seg;
       if (!cfg().dumps.empty()) write_dumps();
       if (restart_every > 0 && cfg().ntimestep % restart_every == 0) {
@@ -920,6 +922,7 @@ class Engine {
         write_restart(p);
       }
     }
+    last_step_ms = ms_total;
   }
 
   // ---- n DEM sub-steps ending in an end-of-step state, chunked so that the host only synchronises every `chunk` launches
