@@ -190,6 +190,7 @@ def main():
     config = {"workload": "configs[2]: %d-particle fluidized bed per GPU, gran/hertzFix/history + wall/granFix + fdrag(ErgunWenYu), "
                           "%d DEM sub-steps per coupling step" % (int(np.prod(dims)), S),
               "particles_per_gpu": int(np.prod(dims)), "substeps_per_step": S, "dt_dem": 2e-6, "skin_over_d": 0.25,
+              "cold_start_ramp": "50 untimed steps (about 1 s) before the W warm-up steps",
               "decomposition": "1 GPU" if world == 1 else "%d bricks, ghost halo every sub-step" % world}
 
     if args.impl == "reference":
@@ -281,6 +282,15 @@ def main():
         eng.scatter_alpha_u(device_only=True)
         eng.calc_tc(device_only=True)
 
+    # cold-start ramp, untimed and in addition to the W warm-up steps: a fresh box needs a few hundred ms of load before
+    # clocks, power state, lazily loaded modules and the CUDA graphs of the sub-step chunks are in their steady state
+    # (one measured run started at 27 ms per step and was at 17 ms half a second later)
+    nramp = 50                      # a fixed count: the steps are collective on several GPUs
+    for _ in range(nramp):
+        device_step()
+    eng.synchronize()
+    barrier()
+    log("ramp: %d untimed steps" % nramp)
     for _ in range(W):
         device_step()
         log("warm-up step done: %.2f ms, rebuilds so far %d" % (eng.last_step_ms(), eng.stat("nbuilds")))
