@@ -1,20 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- the reference's headline metric on B200: M particle-contact-updates / s at 1e6 particles.
 
-One "step" = one coupling step of the particle hot path on a 1e6-particle bed (BASELINE.json configs[2]):
+One "step" = one coupling step of the particle hot path (default: BASELINE.json configs[2], a 1e6-particle settled random
+bed per GPU):
     fluid force (gather Uf / gamma / grad p at the owner cell, ErgunWenYu drag)  ->  `substeps` DEM sub-steps
     (neighbour rebuilds as needed, Hertz-Mindlin contact sweep with shear history, wall/granFix, gravity, fdrag,
     nve/sphere)  ->  cell-owner location  ->  scatter of void fraction / solid velocity / momentum source.
 Unit of work: one neighbour-list pair evaluated by the contact sweep in one DEM sub-step, counted once
-per undirected pair.
+per undirected pair, touching or not.
 
 value : device-resident throughput (cell fields and particle state already in HBM), CUDA events on the engine stream.
 e2e   : the same metric through the reference's own boundary (interfaceToLammps/library.h): host fluid-force array ->
         lammps_put_local_info -> lammps_step(substeps) -> lammps_get_local_info -> host x, v ; copies inside the timing.
-roofline : dominant kernel k_step (one fused DEM sub-step), algorithmic bytes 188 N + 56 P per launch over its
-        CUDA-event duration, against MEASURED_PEAKS.json.
+        `e2e` uses page-locked caller arrays, `e2e_pageable` plain `new double[]`-style arrays as the unchanged
+        softParticleCloud allocates them (softParticleCloud.C:908-912, 959-963).
+roofline : dominant kernel (one fused DEM sub-step), algorithmic bytes 188 N + 56 P per launch over its CUDA-event
+        duration, against MEASURED_PEAKS.json.
 cpu_baseline / --impl reference : the reference's own plug-in sources (oracle/_ref, compiled from /root/reference by
-        oracle/Makefile) driven by the oracle's restated LAMMPS loop on the host cores.
+        oracle/Makefile) driven by the oracle's restated LAMMPS loop on the host cores: `cores` independent sub-domain
+        replicas of the same bed without halo exchange (favourable to the CPU).
+
+--config 1..4 selects the other BASELINE.json configurations (same line schema); --scaling strong splits ONE bed over
+the GPUs instead of giving every GPU its own brick; --bed lattice|random selects the round-1 crystal / the unsettled
+overlap-removal packing instead of the settled random bed.
 """
 import argparse
 import json
@@ -31,8 +39,75 @@ import numpy as np  # noqa: E402
 
 METRIC = "M particle-contact-updates/sec at 1e6 particles"
 UNIT = "M pair-updates/s"
-BED_DIMS = (100, 100, 100)   # 1e6 particles per GPU
 SUBSTEPS = 100               # DEM sub-steps per coupling step (shipped cases: dt_fluid / dt_DEM = 100)
+WEAK_GRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 1, 2), 8: (4, 1, 2)}
+CUBE_GRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+WORKLOADS = {
+    1: "configs[1]: 1e5 monodisperse spheres (random, phi 0.30) sedimenting in a periodic column, gran/hertzFix/history + wall/granFix floor + fdrag(ErgunWenYu)",
+    2: "configs[2]: 1e6-particle settled random bed, gran/hertzFix/history + wall/granFix + fdrag(ErgunWenYu)",
+    3: "configs[3]: 1e6-particle cohesive bed (d 50 um) under a sheared wall/granFix lid, gran/hertzFix/history + fix cohesive + fdrag(ErgunWenYu)",
+    4: "configs[4]: polydisperse (0.3-0.7 mm) dense periodic packing, hybrid/overlay gran/hertzFix/history + lubricate/poly, 1.25e6 particles per GPU",
+}
+
+
+def build_case(cfg, bed, world, rank, scaling, frac=None, size=1.0):
+    """the synthetic input of one rank (brick) or, frac = (fx, fz), of one CPU sub-domain replica; size scales the bed edge"""
+    from sedifoam_b200 import cases
+    s = size
+    if cfg == 2:
+        if frac is not None:
+            if bed == "lattice":
+                return cases.fluidized_bed(dims=(int(100 * s * frac[0]), int(100 * s), int(100 * s * frac[1])))
+            if bed == "random":
+                return cases.random_bed(tiles=(5 * s * frac[0], 8 * s, 5 * s * frac[1]))
+            return cases.settled_bed(columns=(5 * s * frac[0], 5 * s * frac[1]))
+        pg = WEAK_GRID[world]
+        mult = (1, 1, 1) if scaling == "strong" else pg
+        brick = (pg, rank) if world > 1 else None
+        if bed == "lattice":
+            dims = tuple(int(100 * s) * m for m in mult)
+            block = None
+            if world > 1:
+                c = (rank % pg[0], 0, rank // (pg[0] * pg[1]))
+                per = [dims[k] // pg[k] for k in range(3)]
+                block = (c[0] * per[0], (c[0] + 1) * per[0], 0, dims[1], c[2] * per[2], (c[2] + 1) * per[2])
+            return cases.fluidized_bed(dims=dims, seed=cases.SEED + rank, block=block)
+        if bed == "random":
+            return cases.random_bed(tiles=(5 * s * mult[0], 8 * s, 5 * s * mult[2]), brick=brick)
+        return cases.settled_bed(columns=(5 * s * mult[0], 5 * s * mult[2]), brick=brick)
+    if cfg == 1:
+        if frac is not None:
+            return cases.random_column(tiles=(2 * s * frac[0], 5 * s, 2 * s * frac[1]))
+        pg = WEAK_GRID[world]
+        return cases.random_column(tiles=(2 * s, 5 * s, 2 * s), brick=(pg, rank) if world > 1 else None)
+    if cfg == 3:
+        if frac is not None:
+            return cases.random_cohesive_bed(tiles=(5 * s * frac[0], 8 * s, 5 * s * frac[1]))
+        pg = WEAK_GRID[world]
+        return cases.random_cohesive_bed(tiles=(5 * s, 8 * s, 5 * s), brick=(pg, rank) if world > 1 else None)
+    if cfg == 4:
+        if frac is not None:
+            return cases.random_poly_lubricated(tiles=(max(1, round(5 * s * frac[0])), max(1, round(10 * s)), max(1, round(5 * s * frac[1]))))
+        pg = CUBE_GRID[world]
+        mult = (1, 1, 1) if scaling == "strong" else pg
+        t = tuple(max(1, round(v * s)) * m for v, m in zip((5, 10, 5), mult))
+        return cases.random_poly_lubricated(tiles=t, brick=(pg, rank) if world > 1 else None)
+    raise ValueError("unknown --config")
+
+
+def proc_grid(cfg, world):
+    return CUBE_GRID[world] if cfg == 4 else WEAK_GRID[world]
+
+
+def make_config(cfg, bed, world, scaling, S, size):
+    """identical in both arms (the driver compares the dicts)"""
+    c = {"workload": WORKLOADS[cfg] + ", %d DEM sub-steps per coupling step" % S, "config_index": cfg, "substeps_per_step": S,
+         "scaling_mode": scaling, "bed": bed if cfg == 2 else "random", "skin_over_d": 0.25 if cfg != 4 else 0.06,
+         "l2": "per-step working set (2 x 96 B state + list + history > 300 MB per 1e6 particles) exceeds the 126 MB L2; no flush needed"}
+    if size != 1.0:
+        c["size_factor"] = size
+    return c
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -41,22 +116,19 @@ SUBSTEPS = 100               # DEM sub-steps per coupling step (shipped cases: d
 _CPU = {}
 
 
-def _cpu_init(dims, kind, seed_base, counter):
+def _cpu_init(cfg, bed, frac, size, kind, counter):
     """worker start-up (once): build this worker's sub-domain replica of the bed and run LAMMPS' setup on it"""
     from oracle import pyoracle
     from sedifoam_b200 import cases
     with counter.get_lock():
-        r = counter.value
         counter.value += 1
-    case = cases.fluidized_bed(dims=dims, seed=seed_base + r)
+    case = build_case(cfg, bed, 1, 0, "weak", frac=frac, size=size)
     o = pyoracle.Oracle(kind)
     cases.apply(case, o)
     o.setup()
-    n = len(case["tag"])
-    m = case["rho"] * np.pi / 6.0 * case["diam"] ** 3
-    o.put_fdrag(np.tile([0.0, 9.8 * 0.3, 0.0], (n, 1)) * m[:, None], case["tag"])
+    o.put_fdrag(cases.bench_fluid_force(case), case["tag"])
     _CPU["o"] = o
-    _CPU["n"] = n
+    _CPU["n"] = len(case["tag"])
 
 
 def _cpu_step(nsteps):
@@ -73,23 +145,23 @@ class CpuArm:
     host core: an upper bound for a `cores`-rank MPI run of the reference, which has no threading of its own.  The
     force kernels are the reference's own sources (oracle/_ref) when that library is present, else the port."""
 
-    def __init__(self, cores, dims_total=BED_DIMS):
+    def __init__(self, cores, cfg=2, bed="settled", size=1.0):
         import multiprocessing as mp
         from oracle import pyoracle
         self.kind = "reference" if pyoracle.have_reference() else "port"
         self.cores = cores
-        f = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[cores]
-        self.dims = tuple(max(2, dims_total[k] // f[k]) for k in range(3))
+        f = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (4, 2)}[cores]
+        self.frac = (1.0 / f[0], 1.0 / f[1])
         ctx = mp.get_context("spawn")
         counter = ctx.Value("i", 0)
-        self.pool = ctx.Pool(cores, initializer=_cpu_init, initargs=(self.dims, self.kind, 20261017, counter))
+        self.pool = ctx.Pool(cores, initializer=_cpu_init, initargs=(cfg, bed, self.frac, size, self.kind, counter))
 
     def step(self, nsteps):
         res = self.pool.map(_cpu_step, [nsteps] * self.cores, chunksize=1)
         evals = sum(r[0] for r in res); tmax = max(r[1] for r in res); npart = sum(r[2] for r in res)
         return dict(value=evals / tmax / 1e6, unit=UNIT, cores=self.cores, kind=self.kind,
-                    sample="%d particles (%d sub-domain replicas of %s, no halo), %d DEM sub-steps, %.1f s" %
-                           (npart, self.cores, "x".join(map(str, self.dims)), nsteps, tmax),
+                    sample="%d particles (%d sub-domain replicas, 1/%d x 1/%d of the bed each, no halo), %d DEM sub-steps, %.1f s" %
+                           (npart, self.cores, round(1 / self.frac[0]), round(1 / self.frac[1]), nsteps, tmax),
                     seconds=tmax, pair_evals=evals)
 
     def close(self):
@@ -97,8 +169,8 @@ class CpuArm:
         self.pool.join()
 
 
-def cpu_throughput(nsteps, cores, dims_total=BED_DIMS):
-    arm = CpuArm(cores, dims_total)
+def cpu_throughput(nsteps, cores, cfg, bed, size):
+    arm = CpuArm(cores, cfg, bed, size)
     try:
         arm.step(max(1, nsteps // 10))   # warm the caches / first-touch the arrays
         return arm.step(nsteps)
@@ -175,36 +247,35 @@ def main():
         faulthandler.dump_traceback_later(float(os.environ["SEDI_BENCH_TRACE"]), repeat=True, file=sys.stderr)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--dims", default=None, help="override the bed lattice, e.g. 50x50x50 (testing only)")
+    ap.add_argument("--config", type=int, default=2, help="BASELINE.json configs[i], i = 1..4 (default 2: the metric's workload)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--bed", default="settled", choices=["settled", "random", "lattice"])
+    ap.add_argument("--size", type=float, default=1.0, help="scale the bed edge (testing only; the headline needs 1.0)")
     ap.add_argument("--substeps", type=int, default=SUBSTEPS)
+    ap.add_argument("--ramp", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dims = tuple(int(v) for v in args.dims.split("x")) if args.dims else BED_DIMS
     K, W, S = args.steps, max(args.warmup, 0), args.substeps
-    config = {"workload": "configs[2]: %d-particle fluidized bed per GPU, gran/hertzFix/history + wall/granFix + fdrag(ErgunWenYu), "
-                          "%d DEM sub-steps per coupling step" % (int(np.prod(dims)), S),
-              "particles_per_gpu": int(np.prod(dims)), "substeps_per_step": S, "dt_dem": 2e-6, "skin_over_d": 0.25,
-              "cold_start_ramp": "50 untimed steps (about 1 s) before the W warm-up steps",
-              "decomposition": "1 GPU" if world == 1 else "%d bricks, ghost halo every sub-step" % world}
+    cfg = args.config
+    config = make_config(cfg, args.bed, world, args.scaling, S, args.size)
 
     if args.impl == "reference":
         if rank != 0:
             return 0
         cores = os.cpu_count() or 1
         cores = 8 if cores >= 8 else (4 if cores >= 4 else (2 if cores >= 2 else 1))
-        nsteps = S
-        # each "step" of the reference arm is a bounded sample: `nsteps` DEM sub-steps of the same bed on all host cores
+        # each "step" of the reference arm is a bounded sample: S DEM sub-steps of the same bed on all host cores
         vals = []
         t_all = time.perf_counter()
-        arm = CpuArm(cores, dims)
+        arm = CpuArm(cores, cfg, args.bed, args.size)
         for it in range(W + K):
-            r = arm.step(nsteps)
+            r = arm.step(S)
             if it >= W:
                 vals.append(r)
             if time.perf_counter() - t_all > 240 and len(vals) >= 1:
@@ -213,7 +284,7 @@ def main():
         v = float(np.mean([r["value"] for r in vals]))
         ms = float(np.mean([r["seconds"] for r in vals])) * 1e3
         line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": W, "ms_per_step": ms,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "impl": "reference", "config": config,
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": vals[-1]["cores"], "kind": vals[-1]["kind"], "sample": vals[-1]["sample"]},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -225,6 +296,9 @@ def main():
     from sedifoam_b200 import cases
     if not torch.cuda.is_available():
         print("bench.py: no CUDA device; the particle hot path has no CPU fallback", file=sys.stderr)
+        return 2
+    if world not in WEAK_GRID:
+        print("bench.py: --gpus must be 1, 2, 4 or 8", file=sys.stderr)
         return 2
     dist = None
     if world > 1:
@@ -251,16 +325,8 @@ def main():
         return float(t.item())
 
     log("generating case")
-    # weak scaling: every GPU owns one `dims` brick of a bed that grows in x and z (the bed's free surface stays in y)
-    pg = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 1, 2), 8: (4, 1, 2)}.get(world)
-    if pg is None:
-        print("bench.py: --gpus must be 1, 2, 4 or 8", file=sys.stderr)
-        return 2
-    cx, cz = rank % pg[0], rank // (pg[0] * pg[1])
-    gdims = (dims[0] * pg[0], dims[1], dims[2] * pg[2])
-    block = (cx * dims[0], (cx + 1) * dims[0], 0, dims[1], cz * dims[2], (cz + 1) * dims[2])
-    case = cases.fluidized_bed(dims=gdims, seed=cases.SEED + rank, block=block if world > 1 else None)
-    n = len(case["tag"])
+    pg = proc_grid(cfg, world)
+    case = build_case(cfg, args.bed, world, rank, args.scaling, size=args.size)
     eng = sb.Lammps(device=local_rank)
     cases.apply(case, eng)
     if world > 1:
@@ -274,6 +340,8 @@ def main():
     log("setup")
     eng.setup()
     eng.scatter_alpha_u(device_only=True)
+    n = eng.get_local_n()
+    n_tot = int(allsum(float(n)))
     log("setup done, %d particles, %d pairs" % (n, eng.stat("gran_pairs")))
 
     def device_step():
@@ -284,13 +352,11 @@ def main():
 
     # cold-start ramp, untimed and in addition to the W warm-up steps: a fresh box needs a few hundred ms of load before
     # clocks, power state, lazily loaded modules and the CUDA graphs of the sub-step chunks are in their steady state
-    # (one measured run started at 27 ms per step and was at 17 ms half a second later)
-    nramp = 50                      # a fixed count: the steps are collective on several GPUs
-    for _ in range(nramp):
+    for _ in range(args.ramp):      # a fixed count: the steps are collective on several GPUs
         device_step()
     eng.synchronize()
     barrier()
-    log("ramp: %d untimed steps" % nramp)
+    log("ramp: %d untimed steps" % args.ramp)
     for _ in range(W):
         device_step()
         log("warm-up step done: %.2f ms, rebuilds so far %d" % (eng.last_step_ms(), eng.stat("nbuilds")))
@@ -312,57 +378,65 @@ def main():
     evals = eng.stat("pair_evals_unique"); launches = eng.stat("launches"); nbuilds = eng.stat("nbuilds")
     ksteps, kms = eng.get_profile()
     eng.profile(False)
-    pairs_now = eng.stat("gran_pairs")
+    bed_stats = eng.list_stats()
+    n = eng.get_local_n()
     tot_evals = allsum(float(evals))
     value = tot_evals / (ms * 1e-3) / 1e6
 
     # ---- e2e through the reference boundary with host buffers
-    m1 = float(case["rho"][0] * np.pi / 6.0 * case["diam"][0] ** 3)
-    # the host side of the boundary: page-locked arrays, allocated once (an OpenFOAM host would keep its particle lists
-    # in such buffers); sized with slack because brick ownership changes by migration
-    ncap = int(n * 1.3) + 4096
+    ncap = int(n * 1.3) + 4096   # slack: brick ownership changes by migration
 
     def pinned(shape, dtype):
         return torch.empty(shape, dtype=dtype).pin_memory().numpy()
 
-    hb = {"fd": pinned((ncap, 3), torch.float64), "x": pinned((ncap, 3), torch.float64), "v": pinned((ncap, 3), torch.float64),
-          "tag": pinned((ncap,), torch.int32), "foam": pinned((ncap,), torch.int32), "lmp": np.zeros(ncap, np.int32)}
-    first = eng.get_local_info()
-    state = {"n": len(first["tag"])}
-    hb["tag"][:state["n"]] = first["tag"]; hb["foam"][:state["n"]] = first["foamCpuId"]
+    def pageable(shape, dtype):
+        return np.zeros(shape, dtype)
 
-    # the host-side fluid force (what the OpenFOAM side would have computed): synthetic and the same for every particle, so
-    # it is written once -- generating inputs is not part of the boundary being timed, moving them is
-    hb["fd"][:, 0] = 0.0; hb["fd"][:, 1] = 0.3 * 9.8 * m1; hb["fd"][:, 2] = 0.0
+    def e2e_loop(alloc):
+        hb = {"fd": alloc((ncap, 3), torch.float64 if alloc is pinned else np.float64), "x": alloc((ncap, 3), torch.float64 if alloc is pinned else np.float64),
+              "v": alloc((ncap, 3), torch.float64 if alloc is pinned else np.float64), "tag": alloc((ncap,), torch.int32 if alloc is pinned else np.int32),
+              "foam": alloc((ncap,), torch.int32 if alloc is pinned else np.int32), "lmp": np.zeros(ncap, np.int32)}
+        first = eng.get_local_info()
+        state = {"n": len(first["tag"])}
+        hb["tag"][:state["n"]] = first["tag"]; hb["foam"][:state["n"]] = first["foamCpuId"]
+        # the host-side fluid force (what the OpenFOAM side would have computed): synthetic, a fixed fraction of the weight,
+        # written once -- generating inputs is not part of the boundary being timed, moving them is
+        hb["fd"][:] = 0.0
+        if cfg != 4:   # configs[4] has no gravity; its particles differ in mass
+            hb["fd"][:, 1] = 0.3 * 9.8 * float(case["rho"][0] * np.pi / 6.0 * case["diam"][0] ** 3)
 
-    def e2e_step():
-        nl = state["n"]                            # particles this rank owned after the previous step
-        eng.put_local_info(hb["fd"][:nl], hb["tag"][:nl], foam_cpu=hb["foam"][:nl])
-        eng.step(S)
-        nl = eng.get_local_n()
-        eng.get_local_info(hb["x"][:nl], hb["v"][:nl], hb["foam"][:nl], hb["lmp"][:nl], hb["tag"][:nl])   # x, v, ids back on the host
-        state["n"] = nl
+        def e2e_step():
+            nl = state["n"]                            # particles this rank owned after the previous step
+            eng.put_local_info(hb["fd"][:nl], hb["tag"][:nl], foam_cpu=hb["foam"][:nl])
+            eng.step(S)
+            nl = eng.get_local_n()
+            eng.get_local_info(hb["x"][:nl], hb["v"][:nl], hb["foam"][:nl], hb["lmp"][:nl], hb["tag"][:nl])   # x, v, ids back on the host
+            state["n"] = nl
 
-    e2e_step()
-    eng.reset_stats()
-    barrier(); eng.synchronize()
-    t1 = time.perf_counter()
-    for _ in range(K):
         e2e_step()
-    eng.synchronize()
-    e2e_s = allmax(time.perf_counter() - t1)
-    barrier()
+        eng.reset_stats()
+        barrier(); eng.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(K):
+            e2e_step()
+        eng.synchronize()
+        secs = allmax(time.perf_counter() - t1)
+        barrier()
+        ev = allsum(float(eng.stat("pair_evals_unique")))
+        return ev / secs / 1e6, secs
+
+    e2e_value, e2e_s = e2e_loop(pinned)
     log("e2e region done: %.3f s" % e2e_s)
-    e2e_evals = allsum(float(eng.stat("pair_evals_unique")))
-    e2e_value = e2e_evals / e2e_s / 1e6
-    h2d = int(allsum(float(n))) * (24 + 4 + 4)
-    d2h = int(allsum(float(n))) * (24 + 24 + 4 + 4)
+    e2e_pg_value, e2e_pg_s = e2e_loop(pageable)
+    log("e2e (pageable) region done: %.3f s" % e2e_pg_s)
+    h2d = n_tot * (24 + 4 + 4)
+    d2h = n_tot * (24 + 24 + 4 + 4)
     if rank == 0:
         sampler.stop()
 
     # ---- roofline of the dominant kernel (fused DEM sub-step): 188 B / particle + 56 B / undirected pair per launch
     peak, peak_src = load_peak()
-    P_avg = evals / max(1, eng_steps(K, S))
+    P_avg = evals / max(1, K * S)
     alg_bytes = 188.0 * n + 56.0 * P_avg
     k_avg_ms = kms / max(1, ksteps)
     achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9 if k_avg_ms > 0 else 0.0
@@ -370,11 +444,15 @@ def main():
     tp = os.path.join(ROOT, "profiles", "k_step_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("dram_bytes_per_launch") if (cfg == 2 and tj.get("bed", "lattice") == args.bed and args.size == 1.0) else None
         except Exception:
             traffic = None
+    kname = {1: "gran/hertzFix/history", 2: "gran/hertzFix/history", 3: "gran/hertzFix/history + fix cohesive",
+             4: "gran/hertzFix/history + lubricate/poly"}[cfg]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "k_step<gran/hertzFix/history>", "avg_launch_us": k_avg_ms * 1e3, "launches_timed": ksteps,
+                "kernel": ("k_step_wq<%s>" if cfg in (1, 2) and not os.environ.get("SEDI_KSTEP_PATH") else "k_step<%s>") % kname,
+                "avg_launch_us": k_avg_ms * 1e3, "launches_timed": ksteps,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_share_of_step": kms / ms_dev if ms_dev > 0 else None}
 
@@ -382,35 +460,40 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         try:
             cores = 8 if (os.cpu_count() or 1) >= 8 else 1
-            cpu = cpu_throughput(2 * S, cores, dims)
+            cpu = cpu_throughput(2 * S, cores, cfg, args.bed, args.size)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as ex:  # the checker is test infrastructure; its absence must not break the GPU number
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
 
     if rank == 0:
-        config.update({"pairs_per_particle": pairs_now / n, "ghost_rows_rank0": eng.stat("nghost"),
-                       "halo": ("NVLink peer-memory push (CUDA IPC) + signal barrier" if eng.comm_stat("p2p") else "NCCL send/recv") if world > 1 else "none", "neighbor_rebuilds_in_timed_region": nbuilds,
-                       "l2": "per-step working set (2x96 B state + list + history > 300 MB at 1e6 particles) exceeds the 126 MB L2; no flush needed",
-                       "solid_fraction": float(np.pi / 6 / (1 - 2e-3) ** 3)})
+        bed_info = {"particles_rank0": n, "particles_total": n_tot, "decomposition": "1 GPU" if world == 1 else "%dx%dx%d bricks, ghost halo every sub-step" % pg,
+                    "ghost_rows_rank0": eng.stat("nghost"),
+                    "halo": ("NVLink peer-memory push (CUDA IPC) + signal barrier" if eng.comm_stat("p2p") else "NCCL send/recv") if world > 1 else "none",
+                    "neighbor_rebuilds_in_timed_region": nbuilds, "cold_start_ramp_steps": args.ramp}
+        bed_info.update(bed_stats)
+        if case.get("column_meta"):
+            bed_info["settled_column"] = json.loads(case["column_meta"])
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_buffers": "page-locked"},
+                "e2e_pageable": {"value": e2e_pg_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                 "host_buffers": "pageable (staged through the library's pinned buffers)"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary(),
-                "particle_steps_per_s": world * n * K * S / (ms * 1e-3), "wall_s_timed_region": wall}
+                "bed": bed_info, "particle_steps_per_s": n_tot * K * S / (ms * 1e-3), "wall_s_timed_region": wall}
         print(json.dumps(line), flush=True)
     eng.close()
+    del eng
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    torch.cuda.synchronize()
     return 0
-
-
-def eng_steps(K, S):
-    return K * S
 
 
 if __name__ == "__main__":
     rc = main()
     sys.stdout.flush(); sys.stderr.flush()
-    os._exit(rc)   # skip interpreter finalisation: two CUDA runtimes (torch's and the engine's) tear down in undefined order
+    if os.environ.get("SEDI_BENCH_HARD_EXIT"):
+        os._exit(rc)
+    sys.exit(rc)   # normal interpreter exit: the driver's exit hooks (loaded-library record) must run

@@ -68,6 +68,9 @@ void sedi_get_state(void *ptr, double *x, double *v, double *omega, double *f, d
  * meta: bit30 granular list, bit31 type-cutoff list, bits 25..29 periodic image code (13 = none). */
 long long sedi_get_pairs(void *ptr, int *tag_i, int *tag_j, unsigned *meta, int *touch, double *shear, long long cap);
 void sedi_get_wall_shear(void *ptr, int wall, double *shear /* [n][3], device order */);
+/* list statistics per owned row (device order): directed list entries, and how many of them overlapped in the last
+ * sub-step (contact-history mask); either pointer may be NULL */
+void sedi_get_row_stats(void *ptr, int *entries, int *touching);
 void sedi_force_rebuild(void *ptr);
 /* which: 0 neighbour rebuilds, 1 undirected granular pair evaluations, 2 DEM steps, 3 directed granular entries,
  *        4 directed type-list entries, 5 ELL row capacity, 6 kernel launches issued, 7 local particle count,

@@ -8,7 +8,10 @@ set_box / add_atoms / commands.  SI numbers pass through LAMMPS `lj` units as in
 """
 import numpy as np
 
+from . import packing
+
 SEED = 20261017
+TILE_N = 5000      # particles per periodic random tile: 5 x 8 x 5 tiles = 1e6, 2 x 5 x 2 = 1e5, 5 x 10 x 5 = 1.25e6
 
 
 def lattice(dims, spacing, origin, jitter, rng, block=None):
@@ -52,6 +55,11 @@ def apply(case, sim):
     sim.set_box(case["box_lo"], case["box_hi"], case["ntypes"])
     sim.add_atoms(case["tag"], case["type"], case["diam"], case["rho"], case["x"], case["v"])
     sim.commands(case["script"])
+    if case.get("omega") is not None:   # initial spins (settled beds), before the first setup on both sides
+        if type(sim).__name__ == "Oracle":
+            sim.set_omega(case["omega"])
+        else:
+            sim.set_omega(case["tag"], case["omega"])
 
 
 def fluidized_bed(dims=(100, 100, 100), d=5.0e-4, rho=2650.0, overlap=2.0e-3, skin_frac=0.25, dt=2.0e-6, kn=1.0e7, e=0.9,
@@ -295,3 +303,256 @@ def blockmesh_stacked(xspec, yblocks, zspec):
                 label[t] = offs[b] + np.arange(nx) + nx * (j + n * k)
         j0 += n
     return xf, yf, zf, label
+
+
+# ---- random packings (BASELINE.json: "synthetic random packings of the named N"; generator: sedifoam_b200/packing.py) ----
+GRAN_WALL = "fix {id} all wall/granFix {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 {plane} {lo} {hi}"
+
+
+def _fill_box(T, scale, tiles, lo, hi, brick):
+    """particles of the tiled packing inside the whole box, or -- brick = (procgrid, rank) -- inside this rank's brick of
+    the engine's decomposition (LAMMPS `processors`: uniform split of [lo, hi], x fastest) plus a thin margin; the
+    engine keeps the atoms it owns (read_data semantics), tags are the same whoever generates a particle."""
+    tiles = np.asarray(tiles, np.float64)
+    blo, bhi = np.zeros(3), tiles.copy()
+    if brick is not None:
+        grid, rank = brick
+        L = T[2] * scale
+        c = (rank % grid[0], (rank // grid[0]) % grid[1], rank // (grid[0] * grid[1]))
+        for k in range(3):
+            w = (hi[k] - lo[k]) / grid[k]
+            blo[k] = max(0.0, (lo[k] + c[k] * w) / L - 0.02) if c[k] > 0 else 0.0
+            bhi[k] = min(tiles[k], (lo[k] + (c[k] + 1) * w) / L + 0.02) if c[k] < grid[k] - 1 else tiles[k]
+    xt, dt_, ids = packing.fill(T, blo, bhi, grid=tiles)
+    if len(ids) and ids.max() >= 2 ** 31 - 2:
+        raise ValueError("too many particles for 32-bit tags")
+    return xt * scale, dt_ * scale, (ids + 1).astype(np.int32)
+
+
+def random_bed(tiles=(5, 8, 5), d=5.0e-4, rho=2650.0, phi=0.58, skin_frac=0.25, dt=2.0e-6, kn=1.0e7, e=0.9, mu=0.4, head=0.5,
+               seed=SEED, vjit=1.0e-3, brick=None, tile_n=TILE_N):
+    """configs[2]: 1e6-particle bed as a disordered packing -- `tiles` periodic random tiles of `tile_n` spheres at solid
+    fraction `phi` (about 2.4 touching pairs per particle with overlaps of order 1e-3 d: a settled bed under its own
+    weight), granular walls one radius outside the cut faces, free head-room on top; Hertz-Mindlin pair + wall/granFix +
+    gravity + fdrag.  brick = (procgrid, rank) generates only that rank's brick (multi-GPU)."""
+    T = packing.tile(tile_n, phi, seed)
+    L = T[2] * d
+    r = 0.5 * d
+    lo = np.zeros(3) - r
+    hi = np.asarray(tiles, np.float64) * L + r
+    hi[1] = tiles[1] * L * (1.0 + head)
+    x, _, tags = _fill_box(T, d, tiles, lo, hi, brick)
+    rng = np.random.default_rng(seed + 1 + (0 if brick is None else brick[1]))
+    v = rng.uniform(-vjit, vjit, size=x.shape)
+    w = dict(kn=kn, e=e, mu=mu)
+    script = f"""
+neighbor {skin_frac * d:.9g} bin
+neigh_modify delay 0
+pair_style gran/hertzFix/history {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1
+pair_coeff * *
+timestep {dt:.9g}
+fix 1 all nve/sphere
+fix 2 all gravity 9.8 vector 0 -1 0
+fix 3 all fdrag
+{GRAN_WALL.format(id="xw", plane="xplane", lo="%.17g" % lo[0], hi="%.17g" % hi[0], **w)}
+{GRAN_WALL.format(id="yw", plane="yplane", lo="%.17g" % lo[1], hi="%.17g" % hi[1], **w)}
+{GRAN_WALL.format(id="zw", plane="zplane", lo="%.17g" % lo[2], hi="%.17g" % hi[2], **w)}
+"""
+    return _base(x, d, rho, lo, hi, ("f", "f", "f"), script, 4.0 * d, v=v, tags=tags,
+                 extra=dict(name="random_bed", Uf=(0.0, 0.02, 0.0), g=(0.0, -9.8, 0.0), dt=dt, substeps=100, packing="random",
+                            solid_fraction=phi, tiles=tuple(tiles)))
+
+
+def random_column(tiles=(2, 5, 2), d=5.0e-4, rho=2650.0, phi=0.30, skin_frac=0.25, dt=2.0e-6, kn=1.0e7, e=0.9, mu=0.4,
+                  seed=SEED, tile_n=TILE_N, head=0.12, brick=None):
+    """configs[1]: 1e5 monodisperse spheres at phi = 0.30 (random, overlap-free) sedimenting in a column periodic in x and
+    z with a granular floor."""
+    T = packing.tile(tile_n, phi, seed, margin=0.02)
+    L = T[2] * d
+    lo = np.array([0.0, -0.5 * d, 0.0])
+    hi = np.asarray(tiles, np.float64) * L
+    hi[1] *= (1.0 + head)
+    x, _, tags = _fill_box(T, d, tiles, lo, hi, brick)
+    script = f"""
+neighbor {skin_frac * d:.9g} bin
+neigh_modify delay 0
+pair_style gran/hertzFix/history {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1
+pair_coeff * *
+timestep {dt:.9g}
+fix 1 all nve/sphere
+fix 2 all gravity 9.8 vector 0 -1 0
+fix 3 all fdrag
+fix yw all wall/granFix {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 yplane {lo[1]:.17g} NULL
+"""
+    return _base(x, d, rho, lo, hi, ("p", "f", "p"), script, 4.0 * d, tags=tags,
+                 extra=dict(name="random_column", Uf=(0.0, 0.0, 0.0), g=(0.0, -9.8, 0.0), dt=dt, substeps=100, packing="random",
+                            solid_fraction=phi, tiles=tuple(tiles)))
+
+
+def random_cohesive_bed(tiles=(5, 8, 5), d=5.0e-5, rho=2650.0, phi=0.58, dt=2.0e-8, kn=1.0e7, e=0.9, mu=0.4, opt=1, vshear=0.01,
+                        seed=SEED, tile_n=TILE_N, brick=None):
+    """configs[3]: 1e6-particle cohesive silt bed (d = 50 um) under shear: periodic in x / z, wall/granFix floor, sheared
+    wall/granFix lid resting on the bed, fix cohesive (opt 1), Hertz-Mindlin pair."""
+    T = packing.tile(tile_n, phi, seed)
+    L = T[2] * d
+    r = 0.5 * d
+    lo = np.array([0.0, -r, 0.0])
+    hi = np.asarray(tiles, np.float64) * L
+    hi[1] = tiles[1] * L + r - 2.0e-3 * d      # the lid presses on the topmost particles
+    x, _, tags = _fill_box(T, d, tiles, lo, hi, brick)
+    smax = 1.0e-6
+    skin = max(0.25 * d, 2.0 * smax)
+    script = f"""
+neighbor {skin:.9g} bin
+neigh_modify delay 0
+pair_style gran/hertzFix/history {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1
+pair_coeff * *
+timestep {dt:.9g}
+fix 1 all nve/sphere
+fix 2 all gravity 9.8 vector 0 -1 0
+fix 3 all fdrag
+fix 4 all cohesive 1e-20 1e-7 4e-10 {smax:.9g} {opt}
+fix yb all wall/granFix {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 yplane {lo[1]:.17g} NULL
+fix yt all wall/granFix {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 yplane NULL {hi[1]:.17g} shear x {vshear:.9g}
+"""
+    return _base(x, d, rho, lo, hi, ("p", "f", "p"), script, 4.0 * d, tags=tags,
+                 extra=dict(name="random_cohesive_bed", Uf=(0.05, 0.0, 0.0), g=(0.0, -9.8, 0.0), dt=dt, substeps=100,
+                            packing="random", solid_fraction=phi, tiles=tuple(tiles)))
+
+
+def random_poly_lubricated(tiles=(5, 10, 5), dmin=3.0e-4, dmax=7.0e-4, rho=2650.0, phi=0.55, dt=2.0e-6, kn=1.0e7, e=0.9, mu=0.4,
+                           visc=1.0e-3, seed=SEED, vjit=0.01, brick=None, tile_n=TILE_N):
+    """configs[4]: polydisperse (d ~ U[dmin, dmax]) dense periodic packing at phi = 0.55 with hybrid/overlay
+    gran/hertzFix/history + lubricate/poly (full list, cutoff 1.5 dmax).  5 x 10 x 5 tiles = 1.25e6 particles; the 1e7
+    weak-scaling point is tiles = (10, 20, 10) on a 2 x 2 x 2 processor grid (brick = (grid, rank)).
+    cut_inner = 1.001 dmax: the reference switches lubrication off inside cut_inner (pair_lubricate_poly.cpp:294-297) and
+    takes log(1/h) of the gap outside it (:308), so every overlapping pair must lie inside cut_inner or the reference
+    itself produces NaN."""
+    dm = 0.5 * (dmin + dmax)
+    T = packing.tile(tile_n, phi, seed, dlo=dmin / dm, dhi=dmax / dm)
+    L = T[2] * dm
+    lo = np.zeros(3)
+    hi = np.asarray(tiles, np.float64) * L
+    x, diam, tags = _fill_box(T, dm, tiles, lo, hi, brick)
+    rng = np.random.default_rng(seed + 1 + (0 if brick is None else brick[1]))
+    v = rng.uniform(-vjit, vjit, size=x.shape)
+    skin = 0.1 * dmin
+    script = f"""
+neighbor {skin:.9g} bin
+neigh_modify delay 0
+pair_style hybrid/overlay gran/hertzFix/history {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 lubricate/poly {visc:.9g} 1 1 {1.001 * dmax:.9g} {1.5 * dmax:.9g}
+pair_coeff * *
+timestep {dt:.9g}
+fix 1 all nve/sphere
+fix 3 all fdrag
+"""
+    return _base(x, diam, rho, lo, hi, ("p", "p", "p"), script, 4.0 * dmax, v=v, tags=tags,
+                 extra=dict(name="random_poly_lubricated", Uf=(0.0, 0.0, 0.0), g=(0.0, 0.0, 0.0), dt=dt, substeps=100,
+                            packing="random", solid_fraction=phi, tiles=tuple(tiles)))
+
+
+# ---- settled beds: a random column relaxed under gravity by the DEM itself, then repeated in x and z -------------------------
+def settling_column(tile_n=TILE_N, height=8, d=5.0e-4, rho=2650.0, phi=0.58, skin_frac=0.25, dt=2.0e-6, kn=1.0e7, e=0.9, mu=0.4,
+                    seed=SEED, head=0.5):
+    """the input of tools/make_settled_column.py: `height` random tiles stacked on a granular floor, periodic in x and z."""
+    T = packing.tile(tile_n, phi, seed)
+    L = T[2] * d
+    tiles = (1, height, 1)
+    lo = np.array([0.0, -0.5 * d, 0.0])
+    hi = np.array([L, height * L * (1.0 + head), L])
+    x, _, tags = _fill_box(T, d, tiles, lo, hi, None)
+    script = f"""
+neighbor {skin_frac * d:.9g} bin
+neigh_modify delay 0
+pair_style gran/hertzFix/history {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1
+pair_coeff * *
+timestep {dt:.9g}
+fix 1 all nve/sphere
+fix 2 all gravity 9.8 vector 0 -1 0
+fix 3 all fdrag
+fix yw all wall/granFix {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 yplane {lo[1]:.17g} NULL
+"""
+    return _base(x, d, rho, lo, hi, ("p", "f", "p"), script, 4.0 * d, tags=tags,
+                 extra=dict(name="settling_column", Uf=(0.0, 0.02, 0.0), g=(0.0, -9.8, 0.0), dt=dt, substeps=100, packing="random",
+                            solid_fraction=phi, tiles=tiles, tile_n=tile_n))
+
+
+_COLUMNS = {}
+
+
+def load_column(name):
+    """a settled periodic column written by tools/make_settled_column.py: dict(x, v, omega, L = (Lx, Lz), d, meta)"""
+    import os
+    if name not in _COLUMNS:
+        path = name if os.path.exists(name) else os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", name)
+        z = np.load(path)
+        _COLUMNS[name] = dict(x=z["x"].astype(np.float64), v=z["v"].astype(np.float64), omega=z["omega"].astype(np.float64),
+                              L=(float(z["Lx"]), float(z["Lz"])), d=float(z["d"]), top=float(z["x"][:, 1].max()),
+                              meta=str(z["meta"]))
+    return _COLUMNS[name]
+
+
+def settled_bed(columns=(5, 5), column=None, rho=2650.0, skin_frac=0.25, dt=2.0e-6, kn=1.0e7, e=0.9, mu=0.4,
+                head=0.5, brick=None):
+    """configs[2]: the 1e6-particle bed of the benchmark -- a random packing SETTLED under gravity and the bench's fluid
+    force (column `column`: 5000-sphere random tiles stacked 8 high on a granular floor, periodic in x / z, run to rest
+    with the DEM of this library; tools/make_settled_column.py), repeated `columns` times in x and z (fractions allowed)
+    inside granular side walls.  Every particle sits in a force-carrying contact network (about 2.5 touching pairs per
+    particle), rows are ragged.  Velocities / spins are the column's residual ones.  brick = (procgrid, rank): only that
+    rank's brick (multi-GPU); tags do not depend on who generates a particle."""
+    import os
+    column = column or os.environ.get("SEDI_COLUMN", "column_5000x8.npz")
+    C = load_column(column)
+    d = C["d"]
+    r = 0.5 * d
+    Lx, Lz = C["L"]
+    cols = np.asarray(columns, np.float64)
+    lo = np.array([-r, -r, -r])
+    hi = np.array([cols[0] * Lx + r, (C["top"] + r) * (1.0 + head), cols[1] * Lz + r])
+    xr = [0.0, cols[0] * Lx]
+    zr = [0.0, cols[1] * Lz]
+    if brick is not None:
+        grid, rank = brick
+        c = (rank % grid[0], (rank // grid[0]) % grid[1], rank // (grid[0] * grid[1]))
+        if grid[1] != 1:
+            raise ValueError("settled_bed bricks split x and z only")
+        for k, rng_ in ((0, xr), (2, zr)):
+            w = (hi[k] - lo[k]) / grid[k]
+            m = 0.02 * (Lx if k == 0 else Lz)
+            if c[k] > 0:
+                rng_[0] = max(rng_[0], lo[k] + c[k] * w - m)
+            if c[k] < grid[k] - 1:
+                rng_[1] = min(rng_[1], lo[k] + (c[k] + 1) * w + m)
+    n0 = len(C["x"])
+    gx, gz = int(np.ceil(cols[0] - 1e-12)), int(np.ceil(cols[1] - 1e-12))
+    xs, vs, ws, ts = [], [], [], []
+    for ix in range(int(np.floor(xr[0] / Lx + 1e-12)), int(np.ceil(xr[1] / Lx - 1e-12))):
+        for iz in range(int(np.floor(zr[0] / Lz + 1e-12)), int(np.ceil(zr[1] / Lz - 1e-12))):
+            x = C["x"] + np.array([ix * Lx, 0.0, iz * Lz])
+            m = (x[:, 0] >= xr[0]) & (x[:, 0] < xr[1]) & (x[:, 2] >= zr[0]) & (x[:, 2] < zr[1])
+            xs.append(x[m]); vs.append(C["v"][m]); ws.append(C["omega"][m])
+            ts.append((ix * gz + iz) * n0 + np.nonzero(m)[0] + 1)
+    x = np.concatenate(xs); v = np.concatenate(vs); om = np.concatenate(ws); tags = np.concatenate(ts).astype(np.int32)
+    w = dict(kn=kn, e=e, mu=mu)
+    script = f"""
+neighbor {skin_frac * d:.9g} bin
+neigh_modify delay 0
+pair_style gran/hertzFix/history {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1
+pair_coeff * *
+timestep {dt:.9g}
+fix 1 all nve/sphere
+fix 2 all gravity 9.8 vector 0 -1 0
+fix 3 all fdrag
+{GRAN_WALL.format(id="xw", plane="xplane", lo="%.17g" % lo[0], hi="%.17g" % hi[0], **w)}
+{GRAN_WALL.format(id="yw", plane="yplane", lo="%.17g" % lo[1], hi="%.17g" % hi[1], **w)}
+{GRAN_WALL.format(id="zw", plane="zplane", lo="%.17g" % lo[2], hi="%.17g" % hi[2], **w)}
+"""
+    return _base(x, d, rho, lo, hi, ("f", "f", "f"), script, 4.0 * d, v=v, tags=tags,
+                 extra=dict(name="settled_bed", Uf=(0.0, 0.02, 0.0), g=(0.0, -9.8, 0.0), dt=dt, substeps=100, packing="settled random",
+                            omega=om, columns=tuple(float(c) for c in cols), column=column, column_meta=C["meta"]))
+
+
+def bench_fluid_force(case):
+    """the constant per-particle fluid force the benchmark's host side hands over (0.3 of the weight, upwards)"""
+    m = case["rho"] * np.pi / 6.0 * case["diam"] ** 3
+    return np.tile([0.0, 0.3 * 9.8, 0.0], (len(m), 1)) * m[:, None]

@@ -31,6 +31,7 @@
 #include "sedi_neigh.cuh"
 #include "sedi_step.cuh"
 #include "sedi_rows.cuh"
+#include "sedi_wq.cuh"
 #include "sedi_couple.cuh"
 #include "sedi_smooth.cuh"
 #include "sedi_halo.cuh"
@@ -226,7 +227,8 @@ class Engine {
   long long pair_evals_unique;
   long long nbuilds, pair_evals, steps_done, launches, list_gran_dir, list_type_dir, list_gran_img, list_type_img;
   int chunk;
-  bool use_rows;   // pair sweep on the ELL slot walk (default) or on the row-block kernel (SEDI_KSTEP_PATH=rows)
+  bool use_rows;   // pair sweep on the row-block kernel (SEDI_KSTEP_PATH=rows)
+  bool use_wq;     // pair sweep on the warp-queue kernel (default); SEDI_KSTEP_PATH=ell selects the per-row slot walk
   double last_step_ms;
   bool count_in_kernel;
   // boundary staging
@@ -273,6 +275,7 @@ class Engine {
     use_rows = false;
     e = getenv("SEDI_KSTEP_PATH");
     if (e && !strcmp(e, "rows")) use_rows = true;
+    use_wq = !(e && (!strcmp(e, "rows") || !strcmp(e, "ell")));
     e = getenv("SEDI_DEVICE");
     if (e) device = atoi(e);
     else if ((e = getenv("LOCAL_RANK"))) device = atoi(e);
@@ -617,6 +620,19 @@ class Engine {
       return;
     }
     const bool pbc = P.periodic_any != 0;
+    if (use_wq && !tl && cfg().pair != PAIR_NONE) {   // warp-queue kernel: one overlapping contact per lane (sedi_wq.cuh)
+      const int WT = SEDI_WQ_THREADS;
+      const int wb = std::max(1, cdiv(nlocal, WT));
+#define SEDI_LAUNCH_WQ(PK) do { if (pbc) k_step_wq<PK, true><<<wb, WT, 0, stream>>>(P, seq); else k_step_wq<PK, false><<<wb, WT, 0, stream>>>(P, seq); } while (0)
+      switch (cfg().pair) {
+        case PAIR_HERTZFIX_HISTORY: SEDI_LAUNCH_WQ(PAIR_HERTZFIX_HISTORY); break;
+        case PAIR_HOOKE_HISTORY: SEDI_LAUNCH_WQ(PAIR_HOOKE_HISTORY); break;
+        default: SEDI_LAUNCH_WQ(PAIR_HOOKE); break;
+      }
+#undef SEDI_LAUNCH_WQ
+      launches++;
+      return;
+    }
 #define SEDI_LAUNCH_KSTEP(PK)                                                                      \
   do {                                                                                             \
     if (tl) { if (pbc) k_step<PK, true, true><<<blocks, KT, 0, stream>>>(P, seq); else k_step<PK, true, false><<<blocks, KT, 0, stream>>>(P, seq); } \
@@ -991,6 +1007,7 @@ class Engine {
         CK(cudaEventElapsedTime(&kms, evk0, evk1));
         prof_ms += kms; prof_steps += done;
       }
+      if (h_ctrl.p[2] & WQ_ERR_QUEUE) fatal("Contact queue overflow: more than 24 overlapping partners per particle on average in one warp of rows");
       if (h_ctrl.p[2]) fatal("Device-side error flag raised during the DEM step");
       if ((nk + done) & 1) cur ^= 1;
       pair_evals += (long long)done * list_pairs_undirected();
@@ -1133,6 +1150,20 @@ class Engine {
     return total;
   }
 
+  // per-row list statistics: entries of every owned row and how many of them overlapped in the last sub-step
+  void get_row_stats(int *nn_out, int *ntouch_out) {
+    if (!setup_done) setup();
+    need_device();
+    const int m = nlocal;
+    if (!m) return;
+    Ell &L = ell[ecur];
+    std::vector<unsigned long long> tm(m);
+    if (nn_out) CK(cudaMemcpyAsync(nn_out, L.nn.p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(tm.data(), L.tmask.p, (size_t)m * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (ntouch_out) for (int i = 0; i < m; i++) ntouch_out[i] = __builtin_popcountll(tm[i]);
+  }
+
   void get_wall_shear(int w, double *out) {
     need_device();
     if (w < 0 || w >= cfg().nwalls) fatal("sedi_get_wall_shear: no such wall");
@@ -1165,7 +1196,18 @@ class Engine {
   }
 
   void set_omega(int m, const int *tag, const double *w) {
-    if (!loaded) load_atoms();
+    if (!loaded) {   // before the first run the atoms still live in the script: initial spins of the data set
+      AtomData &a = script.atoms;
+      std::vector<std::pair<int, int> > idx(a.size());
+      for (size_t i = 0; i < a.size(); i++) idx[i] = std::make_pair(a.tag[i], (int)i);
+      std::sort(idx.begin(), idx.end());
+      for (int k = 0; k < m; k++) {
+        std::vector<std::pair<int, int> >::iterator it = std::lower_bound(idx.begin(), idx.end(), std::make_pair(tag[k], -1));
+        if (it == idx.end() || it->first != tag[k]) continue;
+        for (int d = 0; d < 3; d++) a.omega[3 * (size_t)it->second + d] = w[3 * (size_t)k + d];
+      }
+      return;
+    }
     if (!setup_done) setup();
     Buf<int> dt; Buf<double> dw;
     dt.ensure(m); dw.ensure(3 * (size_t)m);
@@ -1858,6 +1900,7 @@ long long sedi_get_pairs(void *ptr, int *tag_i, int *tag_j, unsigned *meta, int 
   return E(ptr)->get_pairs(tag_i, tag_j, meta, touch, shear, cap);
 }
 void sedi_get_wall_shear(void *ptr, int wall, double *shear) { E(ptr)->get_wall_shear(wall, shear); }
+void sedi_get_row_stats(void *ptr, int *entries, int *touching) { E(ptr)->get_row_stats(entries, touching); }
 void sedi_force_rebuild(void *ptr) { Engine *e = E(ptr); if (!e->setup_done) e->setup(); else e->rebuild(); }
 long long sedi_get_stat(void *ptr, int which) {
   Engine *e = E(ptr);

@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "lammps_get_local_info", "lammps_put_local_info", "lammps_step", "lammps_set_timestep", "lammps_get_timestep",
     "lammps_create_particle", "lammps_delete_particle",
     "sedi_abi_version", "sedi_device_count", "sedi_set_device", "sedi_set_box", "sedi_add_atoms", "sedi_set_omega",
-    "sedi_get_state", "sedi_get_pairs", "sedi_get_wall_shear", "sedi_force_rebuild", "sedi_get_stat", "sedi_reset_stats",
+    "sedi_get_state", "sedi_get_pairs", "sedi_get_wall_shear", "sedi_get_row_stats", "sedi_force_rebuild", "sedi_get_stat", "sedi_reset_stats",
     "sedi_synchronize", "sedi_stream", "sedi_last_step_ms", "sedi_timer_start", "sedi_timer_stop_ms", "sedi_profile",
     "sedi_get_profile", "sedi_mesh_box", "sedi_mesh_rectilinear", "sedi_mesh_ncells", "sedi_coupling_config",
     "sedi_put_cell_fields", "sedi_coupling_time_index", "sedi_coupling_inlet", "sedi_get_history_state", "sedi_locate", "sedi_compute_fluid_force", "sedi_scatter_alpha_u", "sedi_calc_tc",
@@ -94,6 +94,7 @@ def load_library():
         "sedi_get_state": (None, [vp] + [vp] * 10),
         "sedi_get_pairs": (ll, [vp, vp, vp, vp, vp, vp, ll]),
         "sedi_get_wall_shear": (None, [vp, i, vp]),
+        "sedi_get_row_stats": (None, [vp, vp, vp]),
         "sedi_force_rebuild": (None, [vp]),
         "sedi_get_stat": (ll, [vp, i]),
         "sedi_reset_stats": (None, [vp]),
@@ -320,6 +321,20 @@ class Lammps:
         if m:
             self.lib.sedi_get_pairs(self.h, _vp(ti), _vp(tj), _vp(meta), _vp(touch), _vp(shear), m)
         return dict(ti=ti, tj=tj, gran=(meta >> 30) & 1, type=(meta >> 31) & 1, img=(meta >> 25) & 31, touch=touch, shear=shear)
+
+    def list_stats(self):
+        """shape of the neighbour list of this rank: pairs and overlapping pairs per particle, row-length histogram,
+        ELL width and fill (what a benchmark line says about its bed)"""
+        n = self.get_local_n()
+        nn = np.zeros(n, np.int32); nt = np.zeros(n, np.int32)
+        if n:
+            self.lib.sedi_get_row_stats(self.h, _vp(nn), _vp(nt))
+        cap = self.stat("ell_cap")
+        tot = float(nn.sum())
+        return {"pairs_per_particle": self.stat("gran_pairs") / max(1, n), "directed_entries_per_row": tot / max(1, n),
+                "touching_pairs_per_particle": 0.5 * float(nt.sum()) / max(1, n),
+                "touching_fraction": float(nt.sum()) / max(1.0, float(self.stat("gran_entries"))),
+                "row_length_hist": np.bincount(nn).tolist() if n else [], "ell_width": cap, "ell_fill": tot / max(1.0, float(cap) * n)}
 
     def wall_shear(self, wall):
         """wall history [n][3] in device row order together with the row tags"""

@@ -21,6 +21,7 @@ SCEN = {
     "column_periodic": (lambda: cases.sediment_column(dims=(14, 20, 12), phi=0.45, jitter_frac=0.08), 400, None),
     "column_periodic_x2": (lambda: cases.sediment_column(dims=(14, 20, 12), phi=0.45, jitter_frac=0.08), 300, "x"),
     "cohesive": (lambda: cases.cohesive_shear_bed(dims=(14, 8, 12), opt=1), 200, None),
+    "settled_random": (lambda: cases.settled_bed(columns=(3, 2), column="column_256x4.npz"), 300, None),
 }
 
 
@@ -59,7 +60,7 @@ def main():
                                               nglobal=eng.get_global_n()))
         if rank == 0:
             from oracle import pyoracle
-            o = pyoracle.Oracle("port")
+            o = pyoracle.Oracle("reference" if pyoracle.have_reference() else "port")
             cases.apply(case, o)
             o.setup()
             o.put_fdrag(fd, case["tag"])

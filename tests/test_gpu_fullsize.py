@@ -1,5 +1,7 @@
-"""-m gpu: BASELINE.json's full sizes (1e5 / 1e6 particles), where the CPU oracle is too slow to be the checker:
-size-independent properties of the hot path instead.
+"""-m gpu: BASELINE.json's full sizes (1e5 / 1e6 particles).
+
+Parity against the reference's own compiled objects at size (configs[1]: 1e5 particles x 1000 sub-steps, configs[2]:
+1e6 particles x 100 sub-steps; about 20-40 s of single-core CPU each), then size-independent properties of the hot path:
 
   * the directed neighbour list is symmetric (every pair sits in both partners' rows) and agrees with the
     brute-force count of overlapping lattice neighbours;
@@ -16,6 +18,51 @@ from sedifoam_b200 import cases
 from util import make_engine
 
 pytestmark = pytest.mark.gpu
+
+
+def _fullsize_parity(oracle_mod, case, nsteps, with_fdrag=True):
+    from util import directed_from_oracle, engine_rows, make_oracle, rel_err, sort_rows
+    o = make_oracle(oracle_mod, case)
+    e = make_engine(case)
+    o.setup(); e.setup()
+    if with_fdrag:
+        fd = cases.bench_fluid_force(case)
+        o.put_fdrag(fd, case["tag"]); e.put_local_info(fd, case["tag"])
+    # list at the first build: bit-exact pair set
+    ro, _, _ = directed_from_oracle(o, "gran"); rg, _, _ = engine_rows(e, "gran")
+    (ro,) = sort_rows(ro); (rg,) = sort_rows(rg)
+    assert ro.shape == rg.shape and np.array_equal(ro, rg)
+    half = nsteps // 2
+    o.run(half); e.step(half); o.run(nsteps - half); e.step(nsteps - half)
+    a, b = o.atoms(), e.atoms()
+    L = np.abs(case["box_hi"] - case["box_lo"]).max()
+    assert np.array_equal(a["tag"], b["tag"])
+    assert rel_err(b["x"], a["x"], scale=L) < 1.0e-6      # north_star: 1e-6 relative after a fixed step count
+    assert rel_err(b["v"], a["v"]) < 1.0e-6
+    assert rel_err(b["omega"], a["omega"]) < 1.0e-6
+    assert e.stat("nbuilds") == o.stat("nbuilds") and e.stat("pair_evals") == o.stat("pair_evals")
+    ro, to, so = directed_from_oracle(o, "gran", history=True); rg, tg, sg = engine_rows(e, "gran")
+    ro, to, so = sort_rows(ro, to, so); rg, tg, sg = sort_rows(rg, tg, sg)
+    assert np.array_equal(ro, rg) and np.array_equal(to, tg)    # the pair set and the touching set after the run
+    if np.abs(so).max() > 0:
+        assert rel_err(sg, so) < 1.0e-5
+    return o.kind, int(to.sum())
+
+
+def test_config1_1e5_column_parity_with_reference_objects(oracle_mod):
+    """configs[1]: 1e5 spheres sedimenting in the periodic column, 1000 DEM sub-steps, against the reference objects"""
+    case = cases.random_column()
+    assert len(case["tag"]) == 100000
+    kind, _ = _fullsize_parity(oracle_mod, case, 1000)
+    assert kind == ("reference" if oracle_mod.have_reference() else "port")
+
+
+def test_config2_1e6_settled_bed_parity_with_reference_objects(oracle_mod):
+    """configs[2]: the benchmark's own 1e6-particle settled random bed, 100 DEM sub-steps, against the reference objects"""
+    case = cases.settled_bed()
+    assert len(case["tag"]) == 1000000
+    kind, touching = _fullsize_parity(oracle_mod, case, 100)
+    assert touching > 2 * 2.0e6      # directed touching entries: more than two touching pairs per particle
 
 
 def _pairs_symmetric(e):

@@ -1,0 +1,36 @@
+"""-m gpu: the multi-GPU path (brick decomposition, NVLink peer-memory halo, migration with history) against the
+whole-box CPU oracle -- tests/mgpu_check.py under torch.distributed.run, one process per GPU.  Needs >= 2 visible GPUs
+(`gpurun --gpus 2`); skipped on a single-GPU box."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("halo", ["p2p", "nccl"])
+def test_two_gpu_parity_against_whole_box_oracle(halo):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ)
+    if halo == "nccl":
+        env["SEDI_HALO"] = "nccl"
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mgpu_check.py")], env=env, capture_output=True, text=True,
+                       timeout=900)
+    sys.stdout.write(r.stdout[-4000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("-> OK") >= 4 and "FAIL" not in r.stdout

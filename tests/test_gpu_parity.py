@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from sedifoam_b200 import cases
+import util
 from util import directed_from_oracle, engine_rows, make_engine, make_oracle, rel_err, sort_rows
 
 pytestmark = pytest.mark.gpu
@@ -16,7 +17,16 @@ TOL = 1.0e-6  # north_star tolerance for floating-point state after a fixed step
 SCENARIOS = {
     "hertz_bed_walls": (lambda: cases.fluidized_bed(dims=(12, 14, 12)), 400),
     "hertz_column_periodic": (lambda: cases.sediment_column(dims=(10, 24, 10), phi=0.45, jitter_frac=0.08), 400),
-    "hooke_history_bed": (lambda: _hooke(cases.fluidized_bed(dims=(10, 12, 10))), 300),
+    "hooke_history_bed": (lambda: util.hooke_history_bed(dims=(10, 12, 10)), 300),
+    "hooke_bed": (lambda: util.hooke_bed(dims=(8, 10, 8)), 300),
+    # moving walls and the cylinder wall of fix wall/granFix (fix_wall_granFix.cpp:254-264, :309-322)
+    "wiggle_wall_hertz": (lambda: util.wiggle_wall_bed(dims=(8, 10, 8)), 300),
+    "wiggle_wall_hooke": (lambda: util.wiggle_wall_bed(dims=(8, 10, 8), style="hooke"), 300),
+    "shear_wall": (lambda: util.shear_wall_bed(dims=(8, 10, 8)), 300),
+    "zcylinder": (lambda: util.zcylinder_bed(dims=(9, 9, 8)), 300),
+    "zcylinder_rotating": (lambda: util.zcylinder_bed(dims=(9, 9, 8), shear="x"), 300),
+    # ragged rows with a force-carrying contact network (the bench's kind of bed): settled random packing
+    "settled_random": (lambda: util.settled_random_bed(columns=(2, 2)), 400),
     "cohesive_opt1": (lambda: cases.cohesive_shear_bed(dims=(10, 8, 10), opt=1), 300),
     "cohesive_opt0": (lambda: cases.cohesive_shear_bed(dims=(10, 8, 10), opt=0), 300),
     "lubricate_poly": (lambda: cases.poly_lubricated(dims=(10, 10, 10)), 200),
@@ -27,14 +37,6 @@ SCENARIOS = {
     # ragged rows: polydisperse radii, random positions from a dilute lattice with large jitter, periodic box
     "hertz_polydisperse": (lambda: _poly(cases.sediment_column(dims=(9, 14, 9), phi=0.25, jitter_frac=0.3)), 400),
 }
-
-
-def _hooke(case):
-    case["script"] = case["script"].replace("gran/hertzFix/history 10000000 NULL 0.9 NULL 0.4 1",
-                                            "gran/hooke/history 2000.0 NULL 50.0 NULL 0.4 1")
-    case["script"] = case["script"].replace("wall/granFix 10000000 NULL 0.9 NULL 0.4 1", "wall/gran 2000.0 NULL 50.0 NULL 0.4 1")
-    assert "hooke" in case["script"] and "hertz" not in case["script"]
-    return case
 
 
 def _frozen(case):
@@ -140,10 +142,21 @@ def test_trajectory_parity(oracle_mod, name):
             assert rel_err(sg, so) < 1e-5
 
 
-def test_wall_history_parity(oracle_mod):
-    case, o, e, nsteps = _pair(oracle_mod, "hertz_bed_walls")
+def test_checker_is_the_reference_objects(oracle_mod):
+    """on a box that has oracle/_ref/libsedi_ref.so (it travels with the snapshot) every parity test of this suite
+    compares the CUDA path with the reference's own compiled sources, not with the port"""
+    if not oracle_mod.have_reference():
+        pytest.skip("oracle/_ref/libsedi_ref.so absent: the checker is the port (pinned to the reference objects by tests/test_oracle_pinning.py)")
+    case, o, e, _ = _pair(oracle_mod, "hertz_bed_walls")
+    assert o.kind == "reference" and o.lib.ora_has_ref() == 1
+
+
+@pytest.mark.parametrize("name", ["hertz_bed_walls", "wiggle_wall_hertz", "wiggle_wall_hooke", "shear_wall", "zcylinder_rotating", "settled_random"])
+def test_wall_history_parity(oracle_mod, name):
+    case, o, e, nsteps = _pair(oracle_mod, name)
     o.run(nsteps); e.step(nsteps)
-    for w in range(3):
+    nw = sum(1 for ln in case["script"].splitlines() if "wall/gran" in ln)
+    for w in range(nw):
         a, b = o.wall_shear(w), e.wall_shear(w)
         if np.abs(a).max() > 0:
             assert rel_err(b, a) < 1e-5

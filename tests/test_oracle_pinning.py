@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from sedifoam_b200 import cases
+import util
 from util import make_oracle
 
 SCENARIOS = {
@@ -17,6 +18,16 @@ SCENARIOS = {
     "cohesive_opt1": lambda: cases.cohesive_shear_bed(dims=(6, 6, 6), opt=1),
     "cohesive_opt0": lambda: cases.cohesive_shear_bed(dims=(6, 6, 6), opt=0),
     "lubricate_poly": lambda: cases.poly_lubricated(dims=(6, 6, 6)),
+    # in-tree Hooke walls (fix_wall_granFix.cpp:356-554) under the stock Hooke pairs, moving walls, the cylinder wall
+    "hooke_history_walls": lambda: util.hooke_history_bed(dims=(6, 8, 6)),
+    "hooke_walls": lambda: util.hooke_bed(dims=(6, 8, 6)),
+    "wiggle_wall_hertz": lambda: util.wiggle_wall_bed(dims=(6, 8, 6)),
+    "wiggle_wall_hooke": lambda: util.wiggle_wall_bed(dims=(6, 8, 6), style="hooke"),
+    "shear_wall": lambda: util.shear_wall_bed(dims=(6, 8, 6)),
+    "zcylinder": lambda: util.zcylinder_bed(dims=(7, 7, 6)),
+    "zcylinder_rotating": lambda: util.zcylinder_bed(dims=(7, 7, 6), shear="x"),
+    "zcylinder_shear_z": lambda: util.zcylinder_bed(dims=(7, 7, 6), shear="z"),
+    "settled_random": lambda: util.settled_random_bed(columns=(1, 1)),
 }
 
 

@@ -17,11 +17,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def one(dims, steps, warm, substeps, couple=True):
+def one(dims, steps, warm, substeps, couple=True, bed="settled", cfg=2, size=1.0):
     import numpy as np
     import sedifoam_b200 as sb
     from sedifoam_b200 import cases
-    case = cases.fluidized_bed(dims=dims)
+    import bench
+    case = cases.fluidized_bed(dims=dims) if (bed == "lattice" and cfg == 2) else bench.build_case(cfg, bed, 1, 0, "weak", size=size)
     eng = sb.Lammps(device=0)
     cases.apply(case, eng)
     eng.mesh_box(case["mesh_lo"], case["mesh_hi"], case["mesh_n"])
@@ -59,7 +60,8 @@ def one(dims, steps, warm, substeps, couple=True):
         h.update(np.ascontiguousarray(a[k][order]).tobytes())
     n = len(a["tag"])
     pairs = eng.stat("gran_pairs")
-    out = {"kstep_us": 1e3 * kms / max(1, ksteps), "ms_per_step": ms / steps, "rebuilds": eng.stat("nbuilds"), "launches_timed": ksteps,
+    ls = eng.list_stats()
+    out = {"bed": bed, "cfg": cfg, "n": n, "touching_pairs_per_particle": ls["touching_pairs_per_particle"], "ell_width": ls["ell_width"], "kstep_us": 1e3 * kms / max(1, ksteps), "ms_per_step": ms / steps, "rebuilds": eng.stat("nbuilds"), "launches_timed": ksteps,
            "pairs_per_particle": pairs / n, "GBps_alg": (188.0 * n + 56.0 * pairs) / (kms / max(1, ksteps) * 1e-3) / 1e9 if kms > 0 else 0.0,
            "state_sha": h.hexdigest()[:16]}
     print("SWEEP " + json.dumps(out), flush=True)
@@ -77,10 +79,13 @@ def main():
     ap.add_argument("--envs", default="default=", help="semicolon list name=ENV1=v1,ENV2=v2")
     ap.add_argument("--out", default=None)
     ap.add_argument("--nocouple", action="store_true", help="DEM sub-steps only (bitwise reproducible state hash)")
+    ap.add_argument("--bed", default="settled", choices=["settled", "random", "lattice"])
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--size", type=float, default=1.0)
     args = ap.parse_args()
     dims = tuple(int(v) for v in args.dims.split("x"))
     if args.one:
-        one(dims, args.steps, args.warm, args.substeps, couple=not args.nocouple)
+        one(dims, args.steps, args.warm, args.substeps, couple=not args.nocouple, bed=args.bed, cfg=args.config, size=args.size)
         return 0
     libs = args.libs.split(",") if args.libs else None
     if libs is None:
@@ -100,7 +105,7 @@ def main():
             env["SEDI_B200_LIB"] = lib
             env.update(kv)
             cmd = [sys.executable, os.path.abspath(__file__), "--one", "--dims", args.dims, "--steps", str(args.steps), "--warm", str(args.warm),
-                   "--substeps", str(args.substeps)] + (["--nocouple"] if args.nocouple else [])
+                   "--substeps", str(args.substeps), "--bed", args.bed, "--config", str(args.config), "--size", str(args.size)] + (["--nocouple"] if args.nocouple else [])
             try:
                 r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
                 line = [l for l in r.stdout.splitlines() if l.startswith("SWEEP ")]
