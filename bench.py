@@ -403,7 +403,7 @@ def main():
         # written once -- generating inputs is not part of the boundary being timed, moving them is
         hb["fd"][:] = 0.0
         if cfg != 4:   # configs[4] has no gravity; its particles differ in mass
-            hb["fd"][:, 1] = 0.3 * 9.8 * float(case["rho"][0] * np.pi / 6.0 * case["diam"][0] ** 3)
+            hb["fd"][:, 1] = cases.bench_fluid_force(case)[0, 1]
 
         def e2e_step():
             nl = state["n"]                            # particles this rank owned after the previous step

@@ -116,7 +116,9 @@ void sedi_coupling_config(void *ptr, int drag_model, int force_flags, double nub
 /* host cell fields -> device (Uf, gradp, DDtU, curlU are [C][3]; gamma is [C]); NULL = leave unchanged / absent */
 void sedi_put_cell_fields(void *ptr, const double *Uf, const double *gamma, const double *gradp, const double *DDtU,
                           const double *curlU);
-/* runTime().timeIndex() seen by the next sedi_compute_fluid_force (it then advances by one per call); history force only */
+/* runTime().timeIndex() seen by sedi_compute_fluid_force (particleHistoryForce only, enhancedCloud.C:197-234).  The host
+ * sets it once per fluid time step, BEFORE the force evaluations of that step: with subCycles > 1 evolve() evaluates the
+ * force several times per fluid step and every evaluation sees the same index.  The library never advances it itself. */
 void sedi_coupling_time_index(void *ptr, int time_index);
 /* inletForce vector, inletBox (x1 x2 y1 y2 z1 z2 r1 r2 -), addParticleOption (1 box, 2 hollow cylinder) and
  * addParticleBoxEccentricity of constant/cloudProperties (softParticleCloud.C:471, :1354-1415) */

@@ -64,6 +64,9 @@ def _load(kind):
     lib.ora_foam_cell_owner.argtypes = [C.c_int, _dp, _dp, _dp, _ip, _ip]
     lib.ora_foam_particle_to_eulerian.argtypes = [C.c_int, _ip, _dp, _dp, C.c_int, _dp, _dp, _dp]
     lib.ora_foam_calc_tc.argtypes = [C.c_int, _ip, _dp, _dp, _dp, _dp, C.c_int, _dp, C.c_int, C.c_double, C.c_double, _dp, _dp]
+    if kind == "reference" and hasattr(lib, "ora_ref_jd_ergun_wenyu"):
+        lib.ora_ref_jd_ergun_wenyu.argtypes = [C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp]
+        lib.ora_ref_jd_syamlal_obrien.argtypes = [C.c_int, _dp, _dp, _dp, C.c_double, C.c_double, _dp]
     _LIBS[kind] = lib
     return lib
 
@@ -175,10 +178,15 @@ DRAG_ERGUN_WENYU, DRAG_SYAMLAL_OBRIEN = 0, 1
 
 
 def jd(model, Ur, alpha, pd, nuf, rhof, kind="port"):
+    """Jd closure.  kind="port": the restatement (ora_foam_jd_*); kind="reference": the reference's own
+    lammpsFoam/dragModels/{ErgunWenYu,SyamlalOBrien}.C compiled by path against oracle/stubs_foam/ (oracle/_ref)."""
     lib = _load(kind)
     Ur = np.ascontiguousarray(Ur, np.float64)
     out = np.zeros_like(Ur)
-    fn = lib.ora_foam_jd_ergun_wenyu if model == DRAG_ERGUN_WENYU else lib.ora_foam_jd_syamlal_obrien
+    if kind == "reference":
+        fn = lib.ora_ref_jd_ergun_wenyu if model == DRAG_ERGUN_WENYU else lib.ora_ref_jd_syamlal_obrien
+    else:
+        fn = lib.ora_foam_jd_ergun_wenyu if model == DRAG_ERGUN_WENYU else lib.ora_foam_jd_syamlal_obrien
     fn(len(Ur), Ur, np.ascontiguousarray(alpha, np.float64), np.ascontiguousarray(pd, np.float64), nuf, rhof, out)
     return out
 

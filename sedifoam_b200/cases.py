@@ -451,6 +451,11 @@ fix 3 all fdrag
                             packing="random", solid_fraction=phi, tiles=tuple(tiles)))
 
 
+# upflow below minimum fluidisation: ErgunWenYu drag 0.07 of the weight + pressure-gradient (buoyancy) force 0.38 of it --
+# the bed stays packed (0.02 m/s, the round-1 value, lifts it: drag + buoyancy = 1.05 of the weight)
+BED_UF = (0.0, 0.002, 0.0)
+
+
 # ---- settled beds: a random column relaxed under gravity by the DEM itself, then repeated in x and z -------------------------
 def settling_column(tile_n=TILE_N, height=8, d=5.0e-4, rho=2650.0, phi=0.58, skin_frac=0.25, dt=2.0e-6, kn=1.0e7, e=0.9, mu=0.4,
                     seed=SEED, head=0.5):
@@ -473,7 +478,7 @@ fix 3 all fdrag
 fix yw all wall/granFix {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 yplane {lo[1]:.17g} NULL
 """
     return _base(x, d, rho, lo, hi, ("p", "f", "p"), script, 4.0 * d, tags=tags,
-                 extra=dict(name="settling_column", Uf=(0.0, 0.02, 0.0), g=(0.0, -9.8, 0.0), dt=dt, substeps=100, packing="random",
+                 extra=dict(name="settling_column", Uf=BED_UF, g=(0.0, -9.8, 0.0), dt=dt, substeps=100, packing="random",
                             solid_fraction=phi, tiles=tiles, tile_n=tile_n))
 
 
@@ -482,13 +487,14 @@ _COLUMNS = {}
 
 def load_column(name):
     """a settled periodic column written by tools/make_settled_column.py: dict(x, v, omega, L = (Lx, Lz), d, meta)"""
+    import json
     import os
     if name not in _COLUMNS:
         path = name if os.path.exists(name) else os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", name)
         z = np.load(path)
         _COLUMNS[name] = dict(x=z["x"].astype(np.float64), v=z["v"].astype(np.float64), omega=z["omega"].astype(np.float64),
                               L=(float(z["Lx"]), float(z["Lz"])), d=float(z["d"]), top=float(z["x"][:, 1].max()),
-                              meta=str(z["meta"]))
+                              meta=str(z["meta"]), fow=float(json.loads(str(z["meta"])).get("fluid_force_over_weight", 0.3)))
     return _COLUMNS[name]
 
 
@@ -548,11 +554,15 @@ fix 3 all fdrag
 {GRAN_WALL.format(id="zw", plane="zplane", lo="%.17g" % lo[2], hi="%.17g" % hi[2], **w)}
 """
     return _base(x, d, rho, lo, hi, ("f", "f", "f"), script, 4.0 * d, v=v, tags=tags,
-                 extra=dict(name="settled_bed", Uf=(0.0, 0.02, 0.0), g=(0.0, -9.8, 0.0), dt=dt, substeps=100, packing="settled random",
-                            omega=om, columns=tuple(float(c) for c in cols), column=column, column_meta=C["meta"]))
+                 extra=dict(name="settled_bed", Uf=BED_UF, g=(0.0, -9.8, 0.0), dt=dt, substeps=100, packing="settled random",
+                            omega=om, columns=tuple(float(c) for c in cols), column=column, column_meta=C["meta"],
+                            fluid_force_over_weight=C["fow"]))
 
 
 def bench_fluid_force(case):
-    """the constant per-particle fluid force the benchmark's host side hands over (0.3 of the weight, upwards)"""
+    """the constant per-particle fluid force the benchmark's host side hands over: a fixed fraction of the weight, upwards
+    -- for a settled bed the fraction the bed was settled with (mean ErgunWenYu drag + pressure-gradient force of the
+    bench's prescribed fluid fields), so that the bed stays at rest whichever side computes the force"""
     m = case["rho"] * np.pi / 6.0 * case["diam"] ** 3
-    return np.tile([0.0, 0.3 * 9.8, 0.0], (len(m), 1)) * m[:, None]
+    f = float(case.get("fluid_force_over_weight", 0.3))
+    return np.tile([0.0, f * 9.8, 0.0], (len(m), 1)) * m[:, None]

@@ -36,7 +36,7 @@ static const int NB_IMG_SHIFT = 25;
 static const unsigned NB_FLAG_GRAN = 1u << 30;
 static const unsigned NB_FLAG_TYPE = 1u << 31;
 static const int NB_IMG_NONE = 13;
-static const int MAX_SLOTS = 64;  // touch mask is one 64-bit word per particle
+static const int MAX_SLOTS = 64;  // granular entries per row: the touch mask is one 64-bit word per particle (type-only entries are not limited)
 static const int MAX_FIXES = 12;
 static const int MAX_WALLS = 6;
 static const int MAX_TYPES = 8;
@@ -67,7 +67,9 @@ struct StepParams {
   long long ntimestep;
   const D4 *posr_in, *velm_in, *omgt_in;
   D4 *posr_out, *velm_out, *omgt_out;
-  const int *nn;
+  const int *nn;              // granular entries per row, slots [0, nn)
+  const int *nt;              // type-only entries per row, slots [hcap, hcap + nt)
+  int hcap;
   const unsigned *nbr;
   D4 *shear;                  // [slot * npad + i], .w unused
   unsigned long long *tmask;  // touching-slot mask per particle

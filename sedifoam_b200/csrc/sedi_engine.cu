@@ -100,10 +100,10 @@ struct Plane2 {  // a per-particle plane with a permutation partner
 
 struct Ell {  // directed neighbour list + contact history, slot-major
   Buf<unsigned> nbr;
-  Buf<int> nn;
+  Buf<int> nn, nt;        // granular entries [0, nn) and type-only entries [cap, cap + nt) of every row
   Buf<unsigned long long> tmask;
   Buf<D4> shear;
-  int npad, cap;
+  int npad, cap, tcap;    // cap: granular slots (<= 64, each with a history quad); tcap: type-only slots
   bool valid;
   // row-contiguous form of the same list (k_step_rows): offsets, list words, owner-row byte, history planes
   Buf<int> off;
@@ -113,7 +113,7 @@ struct Ell {  // directed neighbour list + contact history, slot-major
   long long nentries;
   bool rows_valid;     // the row form exists
   bool hist_in_rows;   // the live contact history is in hx/hy/hz (the ELL quads are stale)
-  Ell() : npad(0), cap(0), valid(false), nentries(0), rows_valid(false), hist_in_rows(false) {}
+  Ell() : npad(0), cap(0), tcap(0), valid(false), nentries(0), rows_valid(false), hist_in_rows(false) {}
 };
 
 // small pack / unpack kernels of the C-ABI boundary -------------------------------------------------------
@@ -202,7 +202,7 @@ class Engine {
   bool hist_alloc;
   Buf<double> UfOld;         // fluid velocity field of the previous coupling step (UfSmoothed_.oldTime())
   bool have_UfOld;
-  int time_index;            // runTime().timeIndex() of the next fluid_force call
+  int time_index;            // runTime().timeIndex() seen by fluid_force (set by the host once per fluid step)
   double inlet_force[3], inlet_box[9], inlet_ecc[3];
   int inlet_option;
   Buf<unsigned> wmask[2];
@@ -290,7 +290,7 @@ class Engine {
     cudaStreamSynchronize(stream);
     // device memory is released with the process; explicit frees keep long-lived hosts clean
     for (int k = 0; k < 2; k++) { posr[k].release(); velm[k].release(); omgt[k].release(); wmask[k].release(); foam[k].release();
-      ell[k].nbr.release(); ell[k].nn.release(); ell[k].tmask.release(); ell[k].shear.release();
+      ell[k].nbr.release(); ell[k].nn.release(); ell[k].nt.release(); ell[k].tmask.release(); ell[k].shear.release();
       ell[k].off.release(); ell[k].cnbr.release(); ell[k].crow.release(); ell[k].hx.release(); ell[k].hy.release(); ell[k].hz.release(); }
     Plane2 *groups[] = {f, tq, fdrag, dudt, vold, uold, xhold};
     for (size_t g = 0; g < sizeof(groups) / sizeof(groups[0]); g++) for (int d = 0; d < 3; d++) { groups[g][d].b[0].release(); groups[g][d].b[1].release(); }
@@ -576,7 +576,7 @@ class Engine {
     P.mode = mode; P.ntimestep = ntimestep;
     P.n = nlocal;
     Ell &L = ell[ecur];
-    P.npad = L.npad; P.nn = L.nn.p; P.nbr = L.nbr.p; P.shear = L.shear.p; P.tmask = L.tmask.p;
+    P.npad = L.npad; P.nn = L.nn.p; P.nt = L.nt.p; P.hcap = L.cap; P.nbr = L.nbr.p; P.shear = L.shear.p; P.tmask = L.tmask.p;
     P.off = L.off.p; P.cnbr = L.cnbr.p; P.crow = L.crow.p; P.hx = L.hx.p; P.hy = L.hy.p; P.hz = L.hz.p;
     P.posr_in = posr[in].p; P.velm_in = velm[in].p; P.omgt_in = omgt[in].p;
     P.posr_out = posr[in ^ 1].p; P.velm_out = velm[in ^ 1].p; P.omgt_out = omgt[in ^ 1].p;
@@ -783,26 +783,32 @@ class Engine {
       B.have_old = 1; B.n_old = 0; B.nn_old = 0;
       B.arr_nh = inj_nh.p; B.arr_tag = inj_tag.p; B.arr_shear = inj_shear.p;
     }
-    B.maxcount = ctrl.p + 3; B.npairs = counters.p;
-    if (Ln.cap < 12) Ln.cap = std::max(Lo.cap, 12);   // k_step reads the first nine list words of every row unconditionally
+    B.maxcount = ctrl.p + 3; B.maxcount_t = ctrl.p + 6; B.npairs = counters.p;
+    if (Ln.cap < 16) Ln.cap = std::max(Lo.cap, 16);   // k_step_wq reads the first sixteen list words of every row unconditionally
+    if (Ln.tcap < Lo.tcap) Ln.tcap = Lo.tcap;
     for (int attempt = 0; attempt < 3; attempt++) {
       Ln.npad = npad_ell;
-      Ln.nn.ensure((size_t)npad_ell + 1); Ln.tmask.ensure(npad_ell);
-      if (Ln.cap > 0) { Ln.nbr.ensure((size_t)Ln.cap * npad_ell); Ln.shear.ensure((size_t)Ln.cap * npad_ell); }
-      B.npad = Ln.npad; B.cap = Ln.cap; B.nbr = Ln.nbr.p; B.nn = Ln.nn.p; B.tmask = Ln.tmask.p; B.shear = Ln.shear.p;
+      Ln.nn.ensure((size_t)npad_ell + 1); Ln.nt.ensure((size_t)npad_ell + 1); Ln.tmask.ensure(npad_ell);
+      Ln.nbr.ensure((size_t)(Ln.cap + Ln.tcap) * npad_ell); Ln.shear.ensure((size_t)Ln.cap * npad_ell);
+      B.npad = Ln.npad; B.cap = Ln.cap; B.tcap = Ln.tcap; B.nbr = Ln.nbr.p; B.nn = Ln.nn.p; B.nt = Ln.nt.p; B.tmask = Ln.tmask.p; B.shear = Ln.shear.p;
       CK(cudaMemsetAsync(ctrl.p + 3, 0, sizeof(int), stream));
+      CK(cudaMemsetAsync(ctrl.p + 6, 0, sizeof(int), stream));
       CK(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned long long), stream));
       if (nlocal) k_build_list<<<cdiv(nlocal, 128), 128, 0, stream>>>(B);
       launches++;
       CK(cudaMemcpyAsync(h_ctrl.p, ctrl.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+      CK(cudaMemcpyAsync(h_ctrl.p + 6, ctrl.p + 6, sizeof(int), cudaMemcpyDeviceToHost, stream));
       CK(cudaMemcpyAsync(h_counters.p, counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
       CK(cudaStreamSynchronize(stream));
       CK(cudaGetLastError());
-      int maxrow = h_ctrl.p[3];
-      if (comm.nranks > 1) { double m = maxrow; comm.allreduce_max_host(&m, 1); maxrow = (int)m; }  // same capacity decision on every rank
-      if (maxrow <= Ln.cap) break;
-      if (maxrow > MAX_SLOTS) fatal("Neighbour row longer than 64 entries: reduce the skin / cut-off (contact-history mask is 64 bits)");
-      Ln.cap = std::max(12, std::min(MAX_SLOTS, ((maxrow + 2 + 3) / 4) * 4));
+      int maxrow = h_ctrl.p[3], maxtype = h_ctrl.p[6];
+      if (comm.nranks > 1) { double m[2] = {(double)maxrow, (double)maxtype}; comm.allreduce_max_host(m, 2); maxrow = (int)m[0]; maxtype = (int)m[1]; }  // same capacity decision on every rank
+      if (maxrow <= Ln.cap && maxtype <= Ln.tcap) break;
+      // the 64-bit contact-history mask limits the GRANULAR entries of a row (partners within ri + rj + skin); entries that are
+      // only in the type-cut-off list (fix cohesive, lubricate/poly) have their own segment without such a limit
+      if (maxrow > MAX_SLOTS) fatal("More than 64 granular neighbours (within ri + rj + skin) in one row: reduce the skin (the contact-history mask is 64 bits)");
+      if (maxrow > Ln.cap) Ln.cap = std::max(16, std::min(MAX_SLOTS, ((maxrow + 2 + 3) / 4) * 4));
+      if (maxtype > Ln.tcap) Ln.tcap = ((maxtype + 4 + 3) / 4) * 4;
       if (attempt == 2) fatal("Neighbour list capacity did not converge");
     }
     list_gran_dir = (long long)h_counters.p[0]; list_type_dir = (long long)h_counters.p[1];
@@ -1127,10 +1133,11 @@ class Engine {
     rows_history_to_ell();
     Ell &L = ell[ecur];
     const int n = nlocal;
-    std::vector<int> hn(n), rs(n + 1, 0);
+    std::vector<int> hn(n), ht(n), rs(n + 1, 0);
     if (n) CK(cudaMemcpyAsync(hn.data(), L.nn.p, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (n) CK(cudaMemcpyAsync(ht.data(), L.nt.p, n * sizeof(int), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    for (int i = 0; i < n; i++) rs[i + 1] = rs[i] + hn[i];
+    for (int i = 0; i < n; i++) rs[i + 1] = rs[i] + hn[i] + ht[i];
     const long long total = rs[n];
     if (capacity < total || !total) return total;
     Buf<int> dti, dtj, dto;
@@ -1138,7 +1145,7 @@ class Engine {
     Buf<double> dsh;
     dti.ensure(total); dtj.ensure(total); dto.ensure(total); dme.ensure(total); dsh.ensure(3 * (size_t)total);
     CK(cudaMemcpyAsync(rowstart.p, rs.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
-    k_export_pairs<<<cdiv(n, 128), 128, 0, stream>>>(n, L.npad, L.nn.p, L.nbr.p, omgt[cur].p, rowstart.p, dti.p, dtj.p, dme.p, L.tmask.p,
+    k_export_pairs<<<cdiv(n, 128), 128, 0, stream>>>(n, L.npad, L.nn.p, L.nt.p, L.cap, L.nbr.p, omgt[cur].p, rowstart.p, dti.p, dtj.p, dme.p, L.tmask.p,
                                                      L.shear.p, dto.p, dsh.p);
     if (ti) CK(cudaMemcpyAsync(ti, dti.p, total * sizeof(int), cudaMemcpyDeviceToHost, stream));
     if (tj) CK(cudaMemcpyAsync(tj, dtj.p, total * sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -1158,9 +1165,12 @@ class Engine {
     if (!m) return;
     Ell &L = ell[ecur];
     std::vector<unsigned long long> tm(m);
+    std::vector<int> ht(m);
     if (nn_out) CK(cudaMemcpyAsync(nn_out, L.nn.p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CK(cudaMemcpyAsync(ht.data(), L.nt.p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, stream));
     CK(cudaMemcpyAsync(tm.data(), L.tmask.p, (size_t)m * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
+    if (nn_out) for (int i = 0; i < m; i++) nn_out[i] += ht[i];
     if (ntouch_out) for (int i = 0; i < m; i++) ntouch_out[i] = __builtin_popcountll(tm[i]);
   }
 
@@ -1361,7 +1371,8 @@ class Engine {
     for (int d = 0; d < 3; d++) { P.inletForce[d] = inlet_force[d]; P.inletEcc[d] = inlet_ecc[d]; }
     for (int d = 0; d < 9; d++) P.inletBox[d] = inlet_box[d];
     P.inletOption = inlet_option;
-    time_index++;
+    // no auto-increment: evolve() evaluates the force once per sub-cycle and every evaluation of one fluid step sees the
+    // same runTime().timeIndex() (enhancedCloud.C:197-234); the host sets it with sedi_coupling_time_index
     if (nlocal) k_particle_force<<<cdiv(nlocal, 256), 256, 0, stream>>>(P);
     launches++;
   }
@@ -1910,7 +1921,7 @@ long long sedi_get_stat(void *ptr, int which) {
     case 2: return e->steps_done;
     case 3: return e->list_gran_dir;
     case 4: return e->list_type_dir;
-    case 5: return e->ell[e->ecur].cap;
+    case 5: return e->ell[e->ecur].cap + e->ell[e->ecur].tcap;
     case 6: return e->launches;
     case 7: return e->nlocal;
     case 8: return e->list_pairs_undirected();

@@ -8,6 +8,9 @@
 //   * granular list: pair kept when rsq <= (ri + rj + skin)^2          (flag NB_FLAG_GRAN)
 //   * type list    : pair kept when rsq <= (cut[ti][tj] + skin)^2      (flag NB_FLAG_TYPE; fix cohesive's half
 //                    list, fix_cohesive.cpp:72-83, and lubricate/poly's full list, pair_lubricate_poly.cpp:463-465)
+//   * row layout   : granular entries (possibly also in the type list) fill slots [0, cap) in stencil order -- they own a
+//                    history slot and a bit of the 64-bit touch mask, so cap <= 64 --; entries that are ONLY in the type
+//                    list (beyond ri + rj + skin) follow in slots [cap, cap + tcap) without any such limit
 //   * history      : a new pair that overlaps (rsq < (ri+rj)^2) inherits the shear stored for the same partner
 //                    TAG before the rebuild, otherwise starts from zero.
 // The predicates are evaluated with exactly the reference's operation order and no FMA contraction, so the pair
@@ -18,7 +21,9 @@
 namespace sedi {
 
 struct BuildParams {
-  int n, npad, cap;
+  int n, npad, cap;              // cap: slots of the granular segment [0, cap) of a row (entries with NB_FLAG_GRAN, history, touch bit)
+  int tcap;                      // slots of the type-only segment [cap, cap + tcap): entries that are only in the type-cut-off list
+  int *nt;                       // type-only entries per row
   int want_gran, want_type, ntypes;
   const D4 *posr, *omgt;
   const int *cellstart;
@@ -42,7 +47,8 @@ struct BuildParams {
   int n_old;                     // rows of the old arrays; oldidx >= n_old marks a particle that migrated in
   const int *arr_nh, *arr_tag;   // history carried by migrated particles
   const D4 *arr_shear;
-  int *maxcount;                 // [0] max row length found
+  int *maxcount;                 // [0] longest granular segment found
+  int *maxcount_t;               // [0] longest type-only segment found
   unsigned long long *npairs;    // directed entries: [0] granular, [1] type list, [2] granular periodic-image, [3] type periodic-image
 };
 
@@ -188,7 +194,7 @@ __global__ void k_permute_planes(const int *order, int n, PlaneList L) {
 __global__ void __launch_bounds__(128) k_build_list(const __grid_constant__ BuildParams B) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned ng = 0, nt = 0, ngi = 0, nti = 0;
-  int cnt = 0;
+  int cnt = 0, cntT = 0;
   if (i < B.n) {
     const D4 pi = B.posr[i];
     const unsigned long long bi = (unsigned long long)__double_as_longlong(B.omgt[i].w);
@@ -223,6 +229,11 @@ __global__ void __launch_bounds__(128) k_build_list(const __grid_constant__ Buil
         const bool isimg = (img != NB_IMG_NONE) || (j >= B.nlocal_rows);
         if (flags & NB_FLAG_GRAN) { ng++; if (isimg) ngi++; }
         if (flags & NB_FLAG_TYPE) { nt++; if (isimg) nti++; }
+        if (!(flags & NB_FLAG_GRAN)) {   // type-only entry (fix cohesive / lubricate/poly beyond the granular cut-off): no history
+          if (cntT < B.tcap) B.nbr[(size_t)(B.cap + cntT) * B.npad + i] = (unsigned)j | ((unsigned)img << NB_IMG_SHIFT) | flags;
+          cntT++;
+          return;
+        }
         if (cnt < B.cap) {
           const size_t slot = (size_t)cnt * B.npad + i;
           B.nbr[slot] = (unsigned)j | ((unsigned)img << NB_IMG_SHIFT) | flags;
@@ -271,17 +282,20 @@ __global__ void __launch_bounds__(128) k_build_list(const __grid_constant__ Buil
         }
       }
       B.nn[i] = cnt < B.cap ? cnt : B.cap;
+      B.nt[i] = cntT < B.tcap ? cntT : B.tcap;
       B.tmask[i] = tm;
     } else {
-      B.nn[i] = 0; B.tmask[i] = 0ull;
+      B.nn[i] = 0; B.nt[i] = 0; B.tmask[i] = 0ull;
     }
   }
   const unsigned full = 0xffffffffu;
   const int wmax = __reduce_max_sync(full, cnt);
+  const int wmaxt = __reduce_max_sync(full, cntT);
   const unsigned sg = __reduce_add_sync(full, ng), st = __reduce_add_sync(full, nt);
   const unsigned sgi = __reduce_add_sync(full, ngi), sti = __reduce_add_sync(full, nti);
   if ((threadIdx.x & 31) == 0) {
     if (wmax > 0) atomicMax(B.maxcount, wmax);
+    if (wmaxt > 0) atomicMax(B.maxcount_t, wmaxt);
     if (sg) atomicAdd(&B.npairs[0], (unsigned long long)sg);
     if (st) atomicAdd(&B.npairs[1], (unsigned long long)st);
     if (sgi) atomicAdd(&B.npairs[2], (unsigned long long)sgi);
@@ -290,7 +304,7 @@ __global__ void __launch_bounds__(128) k_build_list(const __grid_constant__ Buil
 }
 
 // export the directed list as (tag_i, tag_j, flags|img) rows for the parity tests
-__global__ void k_export_pairs(int n, int npad, const int *nn, const unsigned *nbr, const D4 *omgt, const int *rowstart,
+__global__ void k_export_pairs(int n, int npad, const int *nn, const int *nt, int hcap, const unsigned *nbr, const D4 *omgt, const int *rowstart,
                                int *ti, int *tj, unsigned *meta, const unsigned long long *tmask, const D4 *shear, int *touch,
                                double *shear_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -298,18 +312,20 @@ __global__ void k_export_pairs(int n, int npad, const int *nn, const unsigned *n
   const int tagi = bits_tag((unsigned long long)__double_as_longlong(omgt[i].w));
   const int base = rowstart[i];
   const unsigned long long tm = tmask[i];
-  for (int s = 0; s < nn[i]; s++) {
+  const int ng = nn[i], ntot = ng + nt[i];
+  for (int k = 0; k < ntot; k++) {
+    const int s = k < ng ? k : hcap + (k - ng);   // granular segment, then the type-only segment
     const size_t slot = (size_t)s * npad + i;
     const unsigned e = nbr[slot];
     const int j = (int)(e & NB_IDX_MASK);
-    ti[base + s] = tagi;
-    tj[base + s] = bits_tag((unsigned long long)__double_as_longlong(omgt[j].w));
-    meta[base + s] = e & ~NB_IDX_MASK;
-    const int t = (int)((tm >> s) & 1ull);
-    touch[base + s] = t;
+    ti[base + k] = tagi;
+    tj[base + k] = bits_tag((unsigned long long)__double_as_longlong(omgt[j].w));
+    meta[base + k] = e & ~NB_IDX_MASK;
+    const int t = (k < ng) ? (int)((tm >> s) & 1ull) : 0;
+    touch[base + k] = t;
     D4 h = {0, 0, 0, 0};
     if (t) h = shear[slot];
-    shear_out[3 * (size_t)(base + s)] = h.x; shear_out[3 * (size_t)(base + s) + 1] = h.y; shear_out[3 * (size_t)(base + s) + 2] = h.z;
+    shear_out[3 * (size_t)(base + k)] = h.x; shear_out[3 * (size_t)(base + k) + 1] = h.y; shear_out[3 * (size_t)(base + k) + 2] = h.z;
   }
 }
 

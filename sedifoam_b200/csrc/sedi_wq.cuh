@@ -5,22 +5,26 @@
 // reference arithmetic (interfaceToLammps/pair_gran_hertzFix_history.cpp:120-285 and the fixes listed in
 // sedi_step.cuh), same per-particle summation order, hence the same results bit for bit (contact law and epilogue are
 // shared code).  What differs is the mapping of the pair sweep onto the machine, chosen for RAGGED rows (a random
-// packing has 2..14 list entries per particle of which about half overlap; the slot walk of k_step runs every warp
-// for its longest row and executes the 290-instruction contact law whenever ANY lane overlaps at that slot):
+// packing has 2..14 list entries per particle of which a third to a half overlap; the slot walk of k_step runs every
+// warp for its longest row and executes the 290-instruction contact law whenever ANY lane overlaps at that slot):
 //
-//   phase 1  one lane per particle walks its ELL row four slots at a time (list words coalesced, partner positions
-//            gathered) and only TESTS the distance: the result is the 64-bit touch mask of the row;
-//   queue    a warp prefix sum of the touch counts turns the 32 masks into one compact queue of (lane, slot)
-//            entries in shared memory, ordered by owner lane, then slot;
+//   phase 1  one lane per particle.  The first 16 list words of the row are requested together with the particle's own
+//            state; partner positions are gathered eight at a time and only the distance is TESTED: the result is the
+//            64-bit touch mask of the row;
+//   queue    per list slot, a warp ballot of the touch bits gives every overlapping entry a position in one compact
+//            queue of the warp's 32 rows, ordered BY SLOT, THEN LANE: consecutive queue entries belong to consecutive
+//            rows and (rows being in bin order) mostly to neighbouring partners, so the gathers of a round coalesce
+//            the way the ELL walk's do -- the L1 data pipe (wavefronts per gather), not HBM, is what an owner-ordered
+//            queue saturates (profiles/r02_*);
 //   phase 2  the warp evaluates the queue 32 entries per round, ONE OVERLAPPING CONTACT PER LANE whatever row it
 //            belongs to (full lane utilisation of the expensive part).  The owner's position / velocity / spin come
-//            from the warp's staged copy in shared memory, the partner's from HBM/L2, the history slot is read and
-//            written in place in the ELL array;
-//   reduce   force / torque of a round go through a double-buffered shared-memory panel; each owner adds the
-//            entries of its own queue range in slot order -- the floating-point sum is the sequential walk's, the run
-//            stays bitwise deterministic, there are no atomics;
+//            from the warp's staged copy in shared memory, the partner's from L1/L2 (prefetched one round ahead), the
+//            history quad is read and written in place in the ELL array;
+//   reduce   force / torque of a round go through a double-buffered shared-memory panel; each owner adds its own
+//            entries in ascending slot order -- the floating-point sum is the sequential walk's, the run stays bitwise
+//            deterministic, there are no atomics;
 //   epilogue step_epilogue<> (fixes in script order, final + initial integrate, skin/2 trigger), one lane per row.
-// Only warp-level synchronisation is used (__syncwarp / shuffles); warps of a CTA are independent.
+// Only warp-level synchronisation is used (__syncwarp / ballots / shuffles); warps of a CTA are independent.
 #pragma once
 #include "sedi_step.cuh"
 
@@ -33,13 +37,15 @@ namespace sedi {
 #define SEDI_WQ_MINB 4
 #endif
 #ifndef SEDI_WQ_QCAP
-#define SEDI_WQ_QCAP 24   // queue capacity: overlapping partners per row, averaged over the 32 rows of a warp
+#define SEDI_WQ_QCAP 16   // queue capacity: overlapping partners per row, averaged over the 32 rows of a warp
 #endif
 #ifndef SEDI_WQ_PF
-#define SEDI_WQ_PF 1      // prefetch the next round's partner lines / history slot to L1 while this round is evaluated
+#define SEDI_WQ_PF 1      // prefetch the next round's partner lines / history quad to L1 at the top of a round
 #endif
 
 static const int WQ_ERR_QUEUE = 2;   // ctrl[2] bit: a warp's contact queue overflowed
+
+__device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
 template <int PAIR, bool PBC>
 __global__ void __launch_bounds__(SEDI_WQ_THREADS, SEDI_WQ_MINB) k_step_wq(const __grid_constant__ StepParams P, const int seq) {
@@ -55,7 +61,10 @@ __global__ void __launch_bounds__(SEDI_WQ_THREADS, SEDI_WQ_MINB) k_step_wq(const
   __shared__ __align__(32) D4 s_omg[NW][32];
   __shared__ double s_part[NW][2][6][32];
   __shared__ unsigned long long s_tm[NW][32];
-  __shared__ unsigned short s_q[NW][QMAX];
+  __shared__ unsigned s_qe[NW][QMAX];          // queue: list word of the entry
+  __shared__ unsigned short s_q[NW][QMAX];     // queue: (owner lane << 8) | slot
+  __shared__ unsigned s_bal[NW][MAX_SLOTS];    // per slot: which lanes overlap at that slot
+  __shared__ unsigned short s_off[NW][MAX_SLOTS];  // per slot: queue position of its first entry
 
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -64,19 +73,46 @@ __global__ void __launch_bounds__(SEDI_WQ_THREADS, SEDI_WQ_MINB) k_step_wq(const
   if (i == 0 && P.mode != MODE_SETUP) atomicAdd(&P.ctrl[1], 1);
   if (row0 >= P.n) return;                                   // warp-uniform
 
-  // ---- own row (arrays are padded to a multiple of 128 rows: loads past n are harmless, their lanes stay idle)
+  // ---- own row and the first 16 list words (arrays are padded to a multiple of 128 rows: loads past n are harmless)
   D4 pi = ldg_d4_stream(&P.posr_in[i]);
   D4 vi = ldg_d4_stream(&P.velm_in[i]);
   D4 wi = ldg_d4_stream(&P.omgt_in[i]);
+  const int nn_raw = (i < P.n) ? ld_nc_s32(&P.nn[i]) : 0;
+  unsigned e16[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) e16[k] = ld_nc_u32(&P.nbr[(size_t)k * P.npad + i]);   // hcap >= 12 rows exist; slots >= nn hold stale words, masked below
   const bool own = (i < P.n) && !(bits_flags((unsigned long long)__double_as_longlong(wi.w)) & PFLAG_GHOST);
-  const int nni = own ? ld_nc_s32(&P.nn[i]) : 0;
+  const int nni = own ? nn_raw : 0;
   const unsigned long long tm_old = (HIST && own) ? P.tmask[i] : 0ull;
   s_pos[w][lane] = pi; s_vel[w][lane] = vi; s_omg[w][lane] = wi; s_tm[w][lane] = tm_old;
   const double radi = pi.w;
+  const int maxnn = __reduce_max_sync(full, nni);
 
   // ---- phase 1: which list entries overlap (pair :131 `rsq >= radsum*radsum` -> no contact)
   unsigned long long touch = 0ull;
-  for (int sb = 0; sb < nni; sb += 4) {
+  auto test_entry = [&](const unsigned e, const D4 &pj_in, const int s) {
+    if (!(e & NB_FLAG_GRAN)) return;
+    D4 pj = pj_in;
+    const int img = (int)((e >> NB_IMG_SHIFT) & 31u);
+    if (PBC && img != NB_IMG_NONE) {  // periodic image = LAMMPS ghost: position is fl(x_j + shift)
+      pj.x = pj.x + P.imgshift[img][0]; pj.y = pj.y + P.imgshift[img][1]; pj.z = pj.z + P.imgshift[img][2];
+    }
+    const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
+    const double rsq = delx * delx + dely * dely + delz * delz;
+    const double radsum = radi + pj.w;
+    if (rsq < radsum * radsum) touch |= (1ull << s);
+  };
+#pragma unroll
+  for (int b = 0; b < 16; b += 8) {
+    if (b < maxnn) {   // warp-uniform
+      D4 p8[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) { if (b + k >= nni) e16[b + k] = 0u; p8[k] = ldg_d4(&P.posr_in[e16[b + k] & NB_IDX_MASK]); }
+#pragma unroll
+      for (int k = 0; k < 8; k++) test_entry(e16[b + k], p8[k], b + k);
+    }
+  }
+  for (int sb = 16; sb < nni; sb += 4) {   // long rows (large skin)
     unsigned e4[4];
     D4 p4[4];
 #pragma unroll
@@ -84,38 +120,34 @@ __global__ void __launch_bounds__(SEDI_WQ_THREADS, SEDI_WQ_MINB) k_step_wq(const
 #pragma unroll
     for (int k = 0; k < 4; k++) p4[k] = ldg_d4(&P.posr_in[e4[k] & NB_IDX_MASK]);
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const unsigned e = e4[k];
-      if (!(e & NB_FLAG_GRAN)) continue;
-      D4 pj = p4[k];
-      const int img = (int)((e >> NB_IMG_SHIFT) & 31u);
-      if (PBC && img != NB_IMG_NONE) {  // periodic image = LAMMPS ghost: position is fl(x_j + shift)
-        pj.x = pj.x + P.imgshift[img][0]; pj.y = pj.y + P.imgshift[img][1]; pj.z = pj.z + P.imgshift[img][2];
-      }
-      const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
-      const double rsq = delx * delx + dely * dely + delz * delz;
-      const double radsum = radi + pj.w;
-      if (rsq < radsum * radsum) touch |= (1ull << (sb + k));
-    }
+    for (int k = 0; k < 4; k++) test_entry(e4[k], p4[k], sb + k);
   }
 
-  // ---- queue: (owner lane, slot) of every overlapping entry of the warp's 32 rows, ordered by lane then slot
-  const int cnt = __popcll(touch);
-  int incl = cnt;
+  // ---- queue: slot-major.  Entry (lane, s) sits at off[s] + (number of lower lanes that overlap at slot s).
+  const unsigned lt = lanemask_lt();
+  int total = 0;   // warp-uniform
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(full, incl, o); if (lane >= o) incl += u; }
-  const int my_a = incl - cnt, my_b = incl;
-  int total = __shfl_sync(full, incl, 31);
-  if (total > QMAX) {   // cannot happen for spheres of bounded size ratio; reported, never silently truncated
-    if (lane == 0) atomicOr(&P.ctrl[2], WQ_ERR_QUEUE);
-    total = 0;
-  }
-  if (total) {
-    int q = my_a;
-    for (unsigned long long m = touch; m; m &= m - 1) {
-      const int s = __ffsll((long long)m) - 1;
-      s_q[w][q++] = (unsigned short)((lane << 8) | s);
+  for (int k = 0; k < 16; k++) {
+    if (k < maxnn) {
+      const bool t = (touch >> k) & 1ull;
+      const unsigned bal = __ballot_sync(full, t);
+      if (lane == 0) { s_bal[w][k] = bal; s_off[w][k] = (unsigned short)total; }
+      const int q = total + __popc(bal & lt);
+      if (t && q < QMAX) { s_q[w][q] = (unsigned short)((lane << 8) | k); s_qe[w][q] = e16[k]; }
+      total += __popc(bal);
     }
+  }
+  for (int k = 16; k < maxnn; k++) {
+    const bool t = (touch >> k) & 1ull;
+    const unsigned bal = __ballot_sync(full, t);
+    if (lane == 0) { s_bal[w][k] = bal; s_off[w][k] = (unsigned short)total; }
+    const int q = total + __popc(bal & lt);
+    if (t && q < QMAX) { s_q[w][q] = (unsigned short)((lane << 8) | k); s_qe[w][q] = ld_nc_u32(&P.nbr[(size_t)k * P.npad + i]); }
+    total += __popc(bal);
+  }
+  if (total > QMAX) {   // cannot happen for spheres of moderate size ratio; reported, never silently truncated
+    if (lane == 0) atomicOr(&P.ctrl[2], WQ_ERR_QUEUE);
+    total = 0; touch = 0ull;
   }
   __syncwarp();
 
@@ -124,18 +156,23 @@ __global__ void __launch_bounds__(SEDI_WQ_THREADS, SEDI_WQ_MINB) k_step_wq(const
   HzCoef hc; hc.c_sn = P.c_sn; hc.c_ccel = P.c_ccel; hc.c_damp = P.c_damp; hc.c_kts = P.c_kts; hc.c_ctd = P.c_ctd; hc.c_ekt = P.c_ekt; hc.xmu = P.xmu;
   GranCoef gc; gc.kn = P.kn; gc.kt = P.kt; gc.gamman = P.gamman; gc.gammat = P.gammat; gc.xmu = P.xmu; gc.beta = P.beta;
   double fx = 0.0, fy = 0.0, fz = 0.0, tx = 0.0, ty = 0.0, tz = 0.0;   // pair accumulators (force_clear)
+  unsigned long long rem = touch;   // own entries not yet added, lowest slot first
+  int qnext = -1;                   // queue position of the lowest one
+  if (rem) { const int k = __ffsll((long long)rem) - 1; qnext = (int)s_off[w][k] + __popc(s_bal[w][k] & lt); }
   int buf = 0;
-  unsigned ent_nxt = (lane < total) ? s_q[w][lane] : 0u;
-  unsigned e_nxt = 0u;
-  if (lane < total) e_nxt = ld_nc_u32(&P.nbr[(size_t)(ent_nxt & 255u) * P.npad + (row0 + (int)(ent_nxt >> 8))]);
   for (int base = 0; base < total; base += 32, buf ^= 1) {
     const int q = base + lane;
-    const unsigned ent = ent_nxt, e = e_nxt;
-    if (q + 32 < total) {   // next round's queue entry and list word are requested before this round's arithmetic
-      ent_nxt = s_q[w][q + 32];
-      e_nxt = ld_nc_u32(&P.nbr[(size_t)(ent_nxt & 255u) * P.npad + (row0 + (int)(ent_nxt >> 8))]);
+#if SEDI_WQ_PF
+    if (q + 32 < total) {   // next round's partner lines and history quad start towards L1 now
+      const unsigned en = s_qe[w][q + 32], qn = s_q[w][q + 32];
+      const int jn = (int)(en & NB_IDX_MASK);
+      prefetch_l1(&P.posr_in[jn]); prefetch_l1(&P.velm_in[jn]); prefetch_l1(&P.omgt_in[jn]);
+      const int Ln = (int)(qn >> 8), sn = (int)(qn & 255u);
+      if (HIST && ((s_tm[w][Ln] >> sn) & 1ull)) prefetch_l1(&P.shear[(size_t)sn * P.npad + (row0 + Ln)]);
     }
+#endif
     if (q < total) {
+      const unsigned ent = s_q[w][q], e = s_qe[w][q];
       const int L = (int)(ent >> 8), s = (int)(ent & 255u);
       const size_t slot = (size_t)s * P.npad + (row0 + L);
       const int j = (int)(e & NB_IDX_MASK);
@@ -174,22 +211,14 @@ __global__ void __launch_bounds__(SEDI_WQ_THREADS, SEDI_WQ_MINB) k_step_wq(const
       s_part[w][buf][0][lane] = fox; s_part[w][buf][1][lane] = foy; s_part[w][buf][2][lane] = foz;
       s_part[w][buf][3][lane] = tox; s_part[w][buf][4][lane] = toy; s_part[w][buf][5][lane] = toz;
     }
-#if SEDI_WQ_PF
-    if (q + 32 < total) {   // the next round's list word has arrived by now
-      const int jn = (int)(e_nxt & NB_IDX_MASK);
-      prefetch_l1(&P.posr_in[jn]); prefetch_l1(&P.velm_in[jn]); prefetch_l1(&P.omgt_in[jn]);
-      const int Ln = (int)(ent_nxt >> 8), sn = (int)(ent_nxt & 255u);
-      if (HIST && ((s_tm[w][Ln] >> sn) & 1ull)) prefetch_l1(&P.shear[(size_t)sn * P.npad + (row0 + Ln)]);
-    }
-#endif
     __syncwarp();
     // this particle's entries inside the round, in slot order (reference: f[i] += F ; torque[i] -= radi * tor, pair :259-271)
-    const int lo = my_a > base ? my_a : base;
-    const int hi = my_b < base + 32 ? my_b : base + 32;
-    for (int k = lo; k < hi; k++) {
-      const int c = k - base;
+    while (rem && qnext < base + 32) {
+      const int c = qnext - base;
       fx += s_part[w][buf][0][c]; fy += s_part[w][buf][1][c]; fz += s_part[w][buf][2][c];
       tx -= radi * s_part[w][buf][3][c]; ty -= radi * s_part[w][buf][4][c]; tz -= radi * s_part[w][buf][5][c];
+      rem &= rem - 1;
+      if (rem) { const int k = __ffsll((long long)rem) - 1; qnext = (int)s_off[w][k] + __popc(s_bal[w][k] & lt); }
     }
     // no second barrier: the next round fills the other panel, and that round's barrier orders the reuse of this one
   }

@@ -110,6 +110,9 @@ def test_coupling_gather_force_scatter(oracle_mod, model, flags):
     assert rel_err(dg["Uri"], ref["Uri"]) < 1e-14
     assert rel_err(dg["alpha"], ref["alpha"]) == 0
     assert rel_err(dg["Jd"], ref["Jd"]) < 1e-12      # pow() differs from glibc in the last ulps
+    if oracle_mod.have_reference():   # the reference's own ErgunWenYu.C / SyamlalOBrien.C (stub-compiled into oracle/_ref)
+        jd_ref = oracle_mod.jd(model, dg["magUri"], dg["alpha"], d, case["nub"], case["rhob"], kind="reference")
+        assert rel_err(dg["Jd"], jd_ref) < 1e-12
     assert rel_err(dg["F"], ref["F"]) < 1e-12
     # scatter 1 (particleToEulerianField) and scatter 2 (calcTcFields)
     C = len(gamma)
@@ -296,7 +299,8 @@ def test_four_spheres_golden_dump_gpu(oracle_mod):
         assert np.allclose(got[:, 4:7], rows[n]["x"], rtol=6e-6, atol=0) and np.allclose(got[:, 7:10], rows[n]["v"], rtol=6e-6, atol=1e-12)
 
 
-def test_coupling_history_lubrication_inlet_terms(oracle_mod):
+@pytest.mark.parametrize("subcycles", [1, 2])
+def test_coupling_history_lubrication_inlet_terms(oracle_mod, subcycles):
     """the last three branches of updateDragOnParticles (enhancedCloud.C:197-257): reduced-order Basset history force
     carried over four coupling steps (per-particle sumDeltaFb / n0 state, both regimes of the window), lubrication
     against the y = 0 wall, and inlet forcing inside a box region -- against the restatement, in the reference's order"""
@@ -316,7 +320,6 @@ def test_coupling_history_lubrication_inlet_terms(oracle_mod):
     box = [case["box_lo"][0], case["box_lo"][0] + 0.3 * ext[0], case["box_lo"][1], case["box_hi"][1], case["box_lo"][2], case["box_hi"][2], 0, 0, 0]
     inlet = (0.0, 0.01, 0.002)
     e.coupling_inlet(inlet, box, 1)
-    e.coupling_time_index(1)
     e.enable_diag(True)
     n = len(case["tag"])
     S = np.zeros((n, 3)); n0 = np.zeros(n)
@@ -324,9 +327,13 @@ def test_coupling_history_lubrication_inlet_terms(oracle_mod):
     v_prev = np.zeros((n, 3))                           # softParticle starts with UOld = 0 (softParticle.C:58)
     Uf_prev = None
     hit = {"lub": 0, "inlet": 0, "window": 0}
-    for k in range(4):
-        Uf, gamma, gradp, DDtU, curlU = _fields(case, rng)
-        e.put_cell_fields(Uf, gamma, gradp)
+    for k in range(4 * subcycles):
+        # evolve(): one force evaluation per sub-cycle, all sub-cycles of a fluid step see the same runTime().timeIndex()
+        tix = 1 + k // subcycles
+        if k % subcycles == 0:
+            Uf, gamma, gradp, DDtU, curlU = _fields(case, rng)
+            e.put_cell_fields(Uf, gamma, gradp)
+            e.coupling_time_index(tix)
         st = e.atoms()
         e.compute_fluid_force()
         dg = e.coupling_diag()
@@ -338,7 +345,7 @@ def test_coupling_history_lubrication_inlet_terms(oracle_mod):
         F = np.ascontiguousarray(ref["F"])
         n0_before = n0.copy()
         oracle_mod.particle_force_extra(cell, st["x"], dia, st["rmass"], st["v"], v_prev, Uf, Uf if Uf_prev is None else Uf_prev,
-                                        flags, nub, rhob, deltaT, 1 + k, S, n0, F, inlet, box, 1)
+                                        flags, nub, rhob, deltaT, tix, S, n0, F, inlet, box, 1)
         assert rel_err(dg["F"], F) < 1e-11, (k, rel_err(dg["F"], F))
         Sg, n0g = e.history_state()
         assert rel_err(Sg, S) < 1e-11 and np.abs(n0g - n0).max() < 1e-9
@@ -346,7 +353,9 @@ def test_coupling_history_lubrication_inlet_terms(oracle_mod):
         hit["lub"] += int(((gap < 0.1 * dia) & (gap > 1e-4 * dia)).sum())
         hit["inlet"] += int((st["x"][:, 0] < box[1]).sum())
         hit["window"] += int((n0 != n0_before).sum())
-        v_prev = st["v"]; Uf_prev = Uf
+        v_prev = st["v"]
+        if k % subcycles == subcycles - 1:
+            Uf_prev = Uf
         e.sedi_step(10)
     assert hit["lub"] > 0 and hit["inlet"] > 0 and hit["window"] > 0   # every branch was exercised
 

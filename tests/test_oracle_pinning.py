@@ -68,3 +68,28 @@ def test_history_and_lists_match_reference(oracle_mod):
         assert np.array_equal(u, v)
     assert np.array_equal(wa, wb)
     assert pa[2].sum() > 0  # some contacts are touching
+
+
+def _jd_inputs(n=20000, seed=5):
+    """covers every branch of both closures: Re below / above 1000, beta below / above 0.8 and 0.85, alpha = 0 and
+    alpha -> 1 (beta clipped at ROOTVSMALL), Ur = 0 (Re clipped at ROOTVSMALL)"""
+    rng = np.random.default_rng(seed)
+    Ur = np.concatenate([10.0 ** rng.uniform(-8, 1.5, n), [0.0, 0.0, 1e-300, 50.0]])
+    alpha = np.concatenate([rng.uniform(0.0, 0.75, n), [0.0, 1.0, 0.2, 0.15]])
+    alpha[: n // 10] = rng.uniform(0.0, 0.2, n // 10)
+    pd = np.concatenate([10.0 ** rng.uniform(-5, -2, n), [5e-4, 5e-4, 5e-4, 5e-3]])
+    return Ur, alpha, pd
+
+
+@pytest.mark.parametrize("model", [0, 1])
+def test_drag_closure_port_matches_reference_objects_bitwise(oracle_mod, model):
+    """pins the fluid-side restatement (ora_foam_jd_*) to the reference's own ErgunWenYu.C:86-145 / SyamlalOBrien.C:85-144"""
+    if not oracle_mod.have_reference():
+        pytest.skip("oracle/_ref/libsedi_ref.so not built (needs /root/reference)")
+    Ur, alpha, pd = _jd_inputs()
+    for nuf, rhof in ((1.0e-6, 1000.0), (1.5e-5, 1.2)):
+        a = oracle_mod.jd(model, Ur, alpha, pd, nuf, rhof, kind="port")
+        b = oracle_mod.jd(model, Ur, alpha, pd, nuf, rhof, kind="reference")
+        assert np.array_equal(a, b, equal_nan=True)
+        Re = np.maximum((1 - alpha) * Ur * pd / nuf, 1e-150)
+        assert (Re > 1000).any() and (Re < 1000).any() and ((1 - alpha) <= 0.8).any() and ((1 - alpha) > 0.85).any()

@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, GPU call 1: settle the benchmark column, then parity + sweep + bench + ncu of the warp-queue kernel
+# round 2: settle the benchmark column, then sweep + bench + ncu + parity tests of the warp-queue kernel
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
 SEDI_KSTEP_PATH=ell timeout 900 python tools/make_settled_column.py --steps 600000 --chunk 50000 > gpurun_out/settle.log 2>&1; echo "settle rc=$?"; tail -4 gpurun_out/settle.log
