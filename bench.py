@@ -45,7 +45,7 @@ CUBE_GRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 
 WORKLOADS = {
     1: "configs[1]: 1e5 monodisperse spheres (random, phi 0.30) sedimenting in a periodic column, gran/hertzFix/history + wall/granFix floor + fdrag(ErgunWenYu)",
-    2: "configs[2]: 1e6-particle settled random bed, gran/hertzFix/history + wall/granFix + fdrag(ErgunWenYu)",
+    2: "configs[2]: 1e6-particle settled random bed (periodic in x/z, wall/granFix floor), gran/hertzFix/history + fdrag(ErgunWenYu)",
     3: "configs[3]: 1e6-particle cohesive bed (d 50 um) under a sheared wall/granFix lid, gran/hertzFix/history + fix cohesive + fdrag(ErgunWenYu)",
     4: "configs[4]: polydisperse (0.3-0.7 mm) dense periodic packing, hybrid/overlay gran/hertzFix/history + lubricate/poly, 1.25e6 particles per GPU",
 }
@@ -61,7 +61,9 @@ def build_case(cfg, bed, world, rank, scaling, frac=None, size=1.0):
                 return cases.fluidized_bed(dims=(int(100 * s * frac[0]), int(100 * s), int(100 * s * frac[1])))
             if bed == "random":
                 return cases.random_bed(tiles=(5 * s * frac[0], 8 * s, 5 * s * frac[1]))
-            return cases.settled_bed(columns=(5 * s * frac[0], 5 * s * frac[1]))
+            # whole columns only (the settled bed is periodic): 8 cores x (1 x 3) columns = 0.96e6 particles, 4 x (2 x 3), 2 x (2 x 5), 1 x (5 x 5)
+            cols = {8: (1, 3), 4: (2, 3), 2: (2, 5), 1: (5, 5)}[int(round(1.0 / (frac[0] * frac[1])))]
+            return cases.settled_bed(columns=(max(1, round(cols[0] * s)), max(1, round(cols[1] * s))))
         pg = WEAK_GRID[world]
         mult = (1, 1, 1) if scaling == "strong" else pg
         brick = (pg, rank) if world > 1 else None
@@ -75,7 +77,7 @@ def build_case(cfg, bed, world, rank, scaling, frac=None, size=1.0):
             return cases.fluidized_bed(dims=dims, seed=cases.SEED + rank, block=block)
         if bed == "random":
             return cases.random_bed(tiles=(5 * s * mult[0], 8 * s, 5 * s * mult[2]), brick=brick)
-        return cases.settled_bed(columns=(5 * s * mult[0], 5 * s * mult[2]), brick=brick)
+        return cases.settled_bed(columns=(max(1, round(5 * s)) * mult[0], max(1, round(5 * s)) * mult[2]), brick=brick)
     if cfg == 1:
         if frac is not None:
             return cases.random_column(tiles=(2 * s * frac[0], 5 * s, 2 * s * frac[1]))
@@ -451,7 +453,7 @@ def main():
     kname = {1: "gran/hertzFix/history", 2: "gran/hertzFix/history", 3: "gran/hertzFix/history + fix cohesive",
              4: "gran/hertzFix/history + lubricate/poly"}[cfg]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": ("k_step_wq<%s>" if cfg in (1, 2) and not os.environ.get("SEDI_KSTEP_PATH") else "k_step<%s>") % kname,
+                "kernel": ("k_step_sell<%s>" if cfg in (1, 2) and not os.environ.get("SEDI_KSTEP_PATH") else "k_step<%s>") % kname,
                 "avg_launch_us": k_avg_ms * 1e3, "launches_timed": ksteps,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_share_of_step": kms / ms_dev if ms_dev > 0 else None}

@@ -151,6 +151,18 @@ void sedi_enable_diag(void *ptr, int on); /* keep Uri/|Uri|/alpha/Jd per particl
 void sedi_get_coupling_diag(void *ptr, int *cell, double *Uri, double *magUri, double *alphap, double *Jd, double *F);
 /* same as lammps_step but never touches host particle arrays */
 void sedi_step(void *ptr, int n);
+/* the reference's built-in invariants, printed by it every step: "total F before / after" of calcTcFields
+ * (enhancedCloud.C:395-435: sum_c Asrc V (1 - gamma) before and after smoothing) and "total U solid before / after" of
+ * particleToEulerianField (:936-976: sum_p Vp Up, and sum_c Ue V gamma after smoothing).  Off by default (four small
+ * reductions and host round trips per coupling step); vectors of 3, any pointer may be NULL. */
+void sedi_enable_conservation_sums(void *ptr, int on);
+void sedi_get_conservation_sums(void *ptr, double *Ftotal_before, double *Ftotal_after, double *Utotal_before, double *Utotal_after);
+/* enhancedCloud::averageInfo (enhancedCloud.C:1341-1370): total particle volume, sum Vp Up [3], volume-averaged velocity [3] */
+void sedi_average_info(void *ptr, double *totalVolume, double *totalVel, double *averageVel);
+/* the reference's timers (writeCPUTime.H:1-19), accumulated wall-clock seconds: diffusionTimeCount[2] (enhancedCloud.H:228),
+ * particleMoveTime (:234: cell-owner location), cpuTimeSplit[6] (softParticleCloud.H:351-354: assemble, transpose, flatten,
+ * foam->lammps, lammps, lammps->foam; the first three are the all-to-alls this library does not have: 0) */
+void sedi_get_timers(void *ptr, double *diffusionTimeCount, double *particleMoveTime, double *cpuTimeSplit);
 
 /* --- multi-GPU: one process per GPU, brick decomposition of the particle box (LAMMPS `processors Px Py Pz`).
  * The NCCL unique id is produced by rank 0 (sedi_comm_unique_id) and distributed by the host (MPI_Bcast in a real

@@ -125,6 +125,21 @@ class enhancedCloud {
   const std::vector<double> &Omega() const { return Omega_; }  // [C], identically zero (enhancedCloud.C:391)
   const std::vector<double> &gamma() const { return gamma_; }  // [C] solid volume fraction (alpha in alphaEqn.H)
   const std::vector<double> &Ue() const { return Ue_; }        // [C][3] solid velocity (Ua)
+  // ---- the rest of the public surface lammpsFoam.C / writeCPUTime.H use (enhancedCloud.H:206-249, softParticleCloud.H:351-354)
+  int particleCount() const { return lammps_get_global_n(lmp_); }
+  // enhancedCloud::averageInfo() prints these three lines (enhancedCloud.C:1367-1369); returned instead of printed
+  struct AverageInfo { double totalVolume, totalVel[3], averageVel[3]; };
+  AverageInfo averageInfo() const { AverageInfo a; sedi_average_info(lmp_, &a.totalVolume, a.totalVel, a.averageVel); return a; }
+  std::vector<double> diffusionTimeCount() const { std::vector<double> t(2); sedi_get_timers(lmp_, t.data(), 0, 0); return t; }
+  double particleMoveTime() const { double t = 0.0; sedi_get_timers(lmp_, 0, &t, 0); return t; }
+  std::vector<double> cpuTimeSplit() const { std::vector<double> t(6); sedi_get_timers(lmp_, 0, 0, t.data()); return t; }
+  // "total F before / after" and "total U solid before / after" (enhancedCloud.C:434-435, 975-976): call
+  // enableConservationSums(true) once, then read them after calcTcFields() / evolve()
+  void enableConservationSums(bool on) { sedi_enable_conservation_sums(lmp_, on ? 1 : 0); }
+  struct ConservationSums { double Fbefore[3], Fafter[3], Ubefore[3], Uafter[3]; };
+  ConservationSums conservationSums() const { ConservationSums c; sedi_get_conservation_sums(lmp_, c.Fbefore, c.Fafter, c.Ubefore, c.Uafter); return c; }
+  // runTime.timeIndex() of the fluid step that is about to call evolve() (particleHistoryForce only)
+  void setTimeIndex(int timeIndex) { sedi_coupling_time_index(lmp_, timeIndex); }
   int nCells() const { return nCells_; }
   int subSteps() const { return subSteps_; }
   int size() const { return lammps_get_global_n(lmp_); }

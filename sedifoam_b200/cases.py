@@ -502,21 +502,26 @@ def settled_bed(columns=(5, 5), column=None, rho=2650.0, skin_frac=0.25, dt=2.0e
                 head=0.5, brick=None):
     """configs[2]: the 1e6-particle bed of the benchmark -- a random packing SETTLED under gravity and the bench's fluid
     force (column `column`: 5000-sphere random tiles stacked 8 high on a granular floor, periodic in x / z, run to rest
-    with the DEM of this library; tools/make_settled_column.py), repeated `columns` times in x and z (fractions allowed)
-    inside granular side walls.  Every particle sits in a force-carrying contact network (about 2.5 touching pairs per
-    particle), rows are ragged.  Velocities / spins are the column's residual ones.  brick = (procgrid, rank): only that
-    rank's brick (multi-GPU); tags do not depend on who generates a particle."""
+    with the DEM of this library; tools/make_settled_column.py), repeated `columns` (integers) times in x and z.  The bed
+    stays periodic in x and z -- exactly the state it was settled in; side walls one radius outside the cut planes would
+    give the packing 1 % of lateral room and let it slump --, rests on a wall/granFix floor and has free head-room below
+    a wall/granFix lid.  Every particle sits in a force-carrying contact network (about 2.5 touching pairs per particle),
+    rows are ragged.  Velocities / spins are the column's residual ones; the contact history starts from zero (friction
+    re-mobilises within micro-slips).  brick = (procgrid, rank): only that rank's brick (multi-GPU); tags do not depend
+    on who generates a particle."""
     import os
     column = column or os.environ.get("SEDI_COLUMN", "column_5000x8.npz")
     C = load_column(column)
     d = C["d"]
     r = 0.5 * d
     Lx, Lz = C["L"]
-    cols = np.asarray(columns, np.float64)
-    lo = np.array([-r, -r, -r])
-    hi = np.array([cols[0] * Lx + r, (C["top"] + r) * (1.0 + head), cols[1] * Lz + r])
-    xr = [0.0, cols[0] * Lx]
-    zr = [0.0, cols[1] * Lz]
+    gx, gz = int(round(columns[0])), int(round(columns[1]))
+    if gx < 1 or gz < 1 or abs(gx - columns[0]) > 1e-9 or abs(gz - columns[1]) > 1e-9:
+        raise ValueError("settled_bed: whole columns only (the bed is periodic in x and z)")
+    lo = np.array([0.0, -r, 0.0])
+    hi = np.array([gx * Lx, (C["top"] + r) * (1.0 + head), gz * Lz])
+    xr = [0.0, gx * Lx]
+    zr = [0.0, gz * Lz]
     if brick is not None:
         grid, rank = brick
         c = (rank % grid[0], (rank // grid[0]) % grid[1], rank // (grid[0] * grid[1]))
@@ -530,7 +535,6 @@ def settled_bed(columns=(5, 5), column=None, rho=2650.0, skin_frac=0.25, dt=2.0e
             if c[k] < grid[k] - 1:
                 rng_[1] = min(rng_[1], lo[k] + (c[k] + 1) * w + m)
     n0 = len(C["x"])
-    gx, gz = int(np.ceil(cols[0] - 1e-12)), int(np.ceil(cols[1] - 1e-12))
     xs, vs, ws, ts = [], [], [], []
     for ix in range(int(np.floor(xr[0] / Lx + 1e-12)), int(np.ceil(xr[1] / Lx - 1e-12))):
         for iz in range(int(np.floor(zr[0] / Lz + 1e-12)), int(np.ceil(zr[1] / Lz - 1e-12))):
@@ -549,13 +553,11 @@ timestep {dt:.9g}
 fix 1 all nve/sphere
 fix 2 all gravity 9.8 vector 0 -1 0
 fix 3 all fdrag
-{GRAN_WALL.format(id="xw", plane="xplane", lo="%.17g" % lo[0], hi="%.17g" % hi[0], **w)}
 {GRAN_WALL.format(id="yw", plane="yplane", lo="%.17g" % lo[1], hi="%.17g" % hi[1], **w)}
-{GRAN_WALL.format(id="zw", plane="zplane", lo="%.17g" % lo[2], hi="%.17g" % hi[2], **w)}
 """
-    return _base(x, d, rho, lo, hi, ("f", "f", "f"), script, 4.0 * d, v=v, tags=tags,
+    return _base(x, d, rho, lo, hi, ("p", "f", "p"), script, 4.0 * d, v=v, tags=tags,
                  extra=dict(name="settled_bed", Uf=BED_UF, g=(0.0, -9.8, 0.0), dt=dt, substeps=100, packing="settled random",
-                            omega=om, columns=tuple(float(c) for c in cols), column=column, column_meta=C["meta"],
+                            omega=om, columns=(gx, gz), column=column, column_meta=C["meta"],
                             fluid_force_over_weight=C["fow"]))
 
 

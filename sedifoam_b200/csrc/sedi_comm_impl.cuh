@@ -202,7 +202,7 @@ inline void Comm::setup_peer(Engine &e) {
   const char *mode = getenv("SEDI_HALO");
   if (mode && !strcmp(mode, "nccl")) { p2p = false; return; }
   if (nranks > 64) { p2p = false; return; }
-  if (!d_sig) { CK(cudaMalloc((void **)&d_sig, 64 * sizeof(unsigned long long))); CK(cudaMemset(d_sig, 0, 64 * sizeof(unsigned long long))); epoch = 0; }
+  if (!d_sig) { CK(cudaMalloc((void **)&d_sig, 65 * sizeof(unsigned long long))); CK(cudaMemset(d_sig, 0, 65 * sizeof(unsigned long long))); epoch = 0; }   // [64] = this rank's exchange counter
   void *mine[7] = {e.posr[0].p, e.posr[1].p, e.velm[0].p, e.velm[1].p, e.omgt[0].p, e.omgt[1].p, d_sig};
   bool same = p2p;
   for (int k = 0; k < 7; k++) if (mine[k] != exported[k]) same = false;
@@ -441,8 +441,7 @@ inline void Comm::forward(Engine &e, int buf, bool with_flag) {
     memset(&S, 0, sizeof(S));
     S.nranks = nranks; S.me = rank;
     for (int r = 0; r < nranks; r++) S.rsig[r] = (unsigned long long *)peer_base[r][6];
-    epoch++;
-    k_halo_signal_wait<<<1, 64, 0, e.stream>>>(S, d_sig, epoch, e.ctrl.p, with_flag ? 1 : 0);
+    k_halo_signal_wait<<<1, 64, 0, e.stream>>>(S, d_sig, e.ctrl.p, with_flag ? 1 : 0);
     e.launches += 2;
     halo_calls++;
     return;

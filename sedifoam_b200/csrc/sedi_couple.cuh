@@ -288,4 +288,49 @@ __global__ void k_finalize_asrc(int C, const double *gamma, double *Asrc) {
   for (int k = 0; k < 3; k++) { double a = Asrc[3 * (size_t)c + k] * w; a /= w; Asrc[3 * (size_t)c + k] = a; }
 }
 
+// ---- the reference's built-in invariants (printed every step: enhancedCloud.C:395-435 "total F before / after",
+// :936-976 "total U solid before / after") and averageInfo() (:1341-1370).  Deterministic two-stage sums.
+// mode 0: sum f[c][k] ; 1: sum f[c][k] V[c] (1 - gamma[c]) ; 2: sum f[c][k] V[c] gamma[c]
+__global__ void __launch_bounds__(256) k_field_sum_partial(int C, const double *f, const double *cellV, const double *gamma, int mode, double *partial) {
+  __shared__ double sm[3][256];
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  for (int c = blockIdx.x * 256 + threadIdx.x; c < C; c += gridDim.x * 256) {
+    double w = 1.0;
+    if (mode == 1) w = cellV[c] * (1 - gamma[c]);
+    else if (mode == 2) w = cellV[c] * gamma[c];
+    a0 += f[3 * (size_t)c] * w; a1 += f[3 * (size_t)c + 1] * w; a2 += f[3 * (size_t)c + 2] * w;
+  }
+  sm[0][threadIdx.x] = a0; sm[1][threadIdx.x] = a1; sm[2][threadIdx.x] = a2;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) for (int k = 0; k < 3; k++) sm[k][threadIdx.x] += sm[k][threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) for (int k = 0; k < 3; k++) partial[3 * blockIdx.x + k] = sm[k][0];
+}
+// averageInfo: sum Vp, sum Vp U over the owned particles
+__global__ void __launch_bounds__(256) k_particle_sum_partial(int n, const D4 *posr, const D4 *velm, double *partial) {
+  __shared__ double sm[4][256];
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const D4 p = posr[i], v = velm[i];
+    const double d = 2.0 * p.w;
+    const double vol = d * d * d * 3.14159265358979323846 / 6.0;   // softParticle::Vol(), softParticleI.H:270-273
+    a[0] += vol; a[1] += v.x * vol; a[2] += v.y * vol; a[3] += v.z * vol;
+  }
+  for (int k = 0; k < 4; k++) sm[k][threadIdx.x] = a[k];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) for (int k = 0; k < 4; k++) sm[k][threadIdx.x] += sm[k][threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) for (int k = 0; k < 4; k++) partial[4 * blockIdx.x + k] = sm[k][0];
+}
+__global__ void __launch_bounds__(256) k_sum_final(const double *partial, int nb, int ncomp, double *out) {
+  __shared__ double sm[256];
+  for (int k = 0; k < ncomp; k++) {
+    double acc = 0.0;
+    for (int c = threadIdx.x; c < nb; c += 256) acc += partial[(size_t)ncomp * c + k];
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) out[k] = sm[0];
+    __syncthreads();
+  }
+}
+
 }  // namespace sedi

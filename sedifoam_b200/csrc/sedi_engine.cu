@@ -20,6 +20,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -32,6 +33,7 @@
 #include "sedi_step.cuh"
 #include "sedi_rows.cuh"
 #include "sedi_wq.cuh"
+#include "sedi_sell.cuh"
 #include "sedi_couple.cuh"
 #include "sedi_smooth.cuh"
 #include "sedi_halo.cuh"
@@ -228,7 +230,10 @@ class Engine {
   long long nbuilds, pair_evals, steps_done, launches, list_gran_dir, list_type_dir, list_gran_img, list_type_img;
   int chunk;
   bool use_rows;   // pair sweep on the row-block kernel (SEDI_KSTEP_PATH=rows)
-  bool use_wq;     // pair sweep on the warp-queue kernel (default); SEDI_KSTEP_PATH=ell selects the per-row slot walk
+  bool use_wq;     // pair sweep on the warp-queue kernel (SEDI_KSTEP_PATH=wq)
+  bool use_sell;   // pair sweep on the sorted-row kernel (default); SEDI_KSTEP_PATH=ell selects the streamed slot walk
+  bool sell_sort;  // rows sorted by work inside windows at every rebuild (default with the sorted-row kernel; SEDI_SELL_SORT=0/1)
+  Buf<int> order2, crow;
   double last_step_ms;
   bool count_in_kernel;
   // boundary staging
@@ -253,6 +258,14 @@ class Engine {
   Buf<double> cg_r, cg_z, cg_p, cg_Ap, cg_partial, cg_s, cg_tmp;
   Pinned<double> h_cg;
   Comm comm;
+  // the reference's timers (writeCPUTime.H:1-19) and conservation printouts, kept by the library so that a host's log stays comparable:
+  // timers[0..1] diffusionTimeCount (field preparation / solves), [2] particleMoveTime (cell-owner location),
+  // [3..8] cpuTimeSplit: assemble, transpose, flatten (no all-to-alls here: 0), foam->lammps, lammps, lammps->foam
+  double timers[9];
+  bool want_sums;
+  double sums[12];   // Ftotal1, Ftotal2 (calcTcFields), Utotal1, Utotal2 (particleToEulerianField)
+  Buf<double> sum_partial, sum_out;
+  static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
   Engine()
       : device(0), dev_ready(false), loaded(false), setup_done(false), params_dirty(true), cell_valid(false), stream(0), n(0),
@@ -262,6 +275,7 @@ class Engine {
         have_curlU(false), have_gradp(false), have_Uf(false), drag_model(0), force_flags(SEDI_FORCE_DRAG | SEDI_FORCE_PGRAD), nub(1e-6), rhob(1000.0),
         deltaT(1.0), restart_every(0), restart_toggle(0), restart_pending(false), restart_carry(0), inject_pending(false), hist_alloc(false), have_UfOld(false), time_index(0), inlet_option(0), want_diag(false), smooth_b(0.0), smooth_steps(0), smooth_flags(0), smooth_iters_last(0), prof_on(false), prof_ms(0), prof_steps(0) {
     gvec[0] = gvec[1] = gvec[2] = 0.0;
+    memset(timers, 0, sizeof(timers)); memset(sums, 0, sizeof(sums)); want_sums = false;
     memset(inlet_force, 0, sizeof(inlet_force)); memset(inlet_box, 0, sizeof(inlet_box)); memset(inlet_ecc, 0, sizeof(inlet_ecc));
     smooth_D[0] = smooth_D[1] = smooth_D[2] = 1.0;
     memset(&base, 0, sizeof(base));
@@ -275,7 +289,10 @@ class Engine {
     use_rows = false;
     e = getenv("SEDI_KSTEP_PATH");
     if (e && !strcmp(e, "rows")) use_rows = true;
-    use_wq = !(e && (!strcmp(e, "rows") || !strcmp(e, "ell")));
+    use_wq = (e && !strcmp(e, "wq"));
+    use_sell = !(e && (!strcmp(e, "rows") || !strcmp(e, "ell") || !strcmp(e, "wq")));
+    sell_sort = use_sell;
+    if (const char *ss = getenv("SEDI_SELL_SORT")) sell_sort = atoi(ss) != 0;
     e = getenv("SEDI_DEVICE");
     if (e) device = atoi(e);
     else if ((e = getenv("LOCAL_RANK"))) device = atoi(e);
@@ -620,6 +637,19 @@ class Engine {
       return;
     }
     const bool pbc = P.periodic_any != 0;
+    if (use_sell && !tl && cfg().pair != PAIR_NONE) {   // sorted-row kernel: one lane per particle, rows of a warp carry equal work (sedi_sell.cuh)
+      const int ST = SEDI_SELL_THREADS;
+      const int sb = std::max(1, cdiv(nlocal, ST));
+#define SEDI_LAUNCH_SELL(PK) do { if (pbc) k_step_sell<PK, true><<<sb, ST, 0, stream>>>(P, seq); else k_step_sell<PK, false><<<sb, ST, 0, stream>>>(P, seq); } while (0)
+      switch (cfg().pair) {
+        case PAIR_HERTZFIX_HISTORY: SEDI_LAUNCH_SELL(PAIR_HERTZFIX_HISTORY); break;
+        case PAIR_HOOKE_HISTORY: SEDI_LAUNCH_SELL(PAIR_HOOKE_HISTORY); break;
+        default: SEDI_LAUNCH_SELL(PAIR_HOOKE); break;
+      }
+#undef SEDI_LAUNCH_SELL
+      launches++;
+      return;
+    }
     if (use_wq && !tl && cfg().pair != PAIR_NONE) {   // warp-queue kernel: one overlapping contact per lane (sedi_wq.cuh)
       const int WT = SEDI_WQ_THREADS;
       const int wb = std::max(1, cdiv(nlocal, WT));
@@ -695,7 +725,7 @@ class Engine {
     L.rows_valid = true;
   }
 
-  void rebuild() {
+  void rebuild(bool count = true) {
     need_device();
     drop_graphs();
     rows_history_to_ell();
@@ -732,9 +762,20 @@ class Engine {
       k_cell_sort<<<cdiv(nc, T), T, 0, stream>>>(cellstart.p, (int)nc, nlocal_new, order.p, omgt[cur].p);
       launches += 2;
     }
+    // rows sorted by work inside windows (SELL-C-sigma, sedi_sell.cuh): ord = new row -> old row, crow = bin position -> new row
+    const int *ord = order.p;
+    const bool sorted_rows = sell_sort && nlocal_new > 0;
+    if (sorted_rows) {
+      order2.ensure(npad); crow.ensure(npad);
+      Ell &Lprev = ell[ecur];
+      k_window_sort<<<cdiv(nlocal_new, SELL_WINDOW), SELL_WINDOW, 0, stream>>>(nlocal_new, order.p, Lprev.valid ? Lprev.tmask.p : (const unsigned long long *)0,
+                                                                               Lprev.valid ? Lprev.nn.p : (const int *)0, nlocal, order2.p, crow.p);
+      launches++;
+      ord = order2.p;
+    }
     if (nlocal_new) {
       // physical re-ordering into cell order: quads cur -> cur^1, planes get() -> alt()
-      k_permute_quads<<<cdiv(nlocal_new, T), T, 0, stream>>>(order.p, nlocal_new, posr[cur].p, velm[cur].p, omgt[cur].p, posr[cur ^ 1].p,
+      k_permute_quads<<<cdiv(nlocal_new, T), T, 0, stream>>>(ord, nlocal_new, posr[cur].p, velm[cur].p, omgt[cur].p, posr[cur ^ 1].p,
                                                              velm[cur ^ 1].p, omgt[cur ^ 1].p, xhold[0].get(), xhold[1].get(), xhold[2].get(),
                                                              tag2idx.p, maxtag, wmask[icur].p, wmask[icur ^ 1].p, foam[icur].p, foam[icur ^ 1].p);
       PlaneList L;
@@ -743,7 +784,7 @@ class Engine {
       for (int g = 0; g < NPLANES_BASE; g++) for (int d = 0; d < 3; d++) { L.src[L.nplanes] = groups[g][d].get(); L.dst[L.nplanes] = groups[g][d].alt(); L.nplanes++; }
       for (int w = 0; w < c.nwalls; w++) for (int d = 0; d < 3; d++) { L.src[L.nplanes] = wshear[w][d].get(); L.dst[L.nplanes] = wshear[w][d].alt(); L.nplanes++; }
       if (hist_alloc) for (int d = 0; d < 4; d++) { L.src[L.nplanes] = hist[d].get(); L.dst[L.nplanes] = hist[d].alt(); L.nplanes++; }
-      k_permute_planes<<<cdiv(nlocal_new, T), T, 0, stream>>>(order.p, nlocal_new, L);
+      k_permute_planes<<<cdiv(nlocal_new, T), T, 0, stream>>>(ord, nlocal_new, L);
       launches += 2;
     }
     {
@@ -771,7 +812,8 @@ class Engine {
     for (int d = 0; d < 3; d++) { B.nb[d] = bin.nb[d]; if (d < 2) B.tile[d] = bin.tile[d]; B.periodic[d] = bin.periodic[d]; B.lo[d] = bin.lo[d]; B.inv[d] = bin.inv[d]; B.prd[d] = c.boxhi[d] - c.boxlo[d]; }
     B.skin = c.skin;
     memcpy(B.cutneighsq, cutneighsq, sizeof(cutneighsq));
-    B.have_old = (Lo.valid || narr > 0) ? 1 : 0; B.npad_old = Lo.npad; B.oldidx = order.p;
+    B.have_old = (Lo.valid || narr > 0) ? 1 : 0; B.npad_old = Lo.npad; B.oldidx = ord;
+    B.crow = sorted_rows ? crow.p : (const int *)0;
     B.nbr_old = Lo.nbr.p; B.nn_old = Lo.valid ? Lo.nn.p : (const int *)0; B.tmask_old = Lo.tmask.p; B.shear_old = Lo.shear.p; B.omgt_old = omgt[oldq].p;
     B.n_old = Lo.valid ? n_old : 0;
     B.nlocal_rows = nlocal;
@@ -816,7 +858,7 @@ class Engine {
     Ln.valid = true; Lo.valid = false; Lo.rows_valid = false; Lo.hist_in_rows = false;
     build_rows(Ln);
     ecur ^= 1;
-    nbuilds++;
+    if (count) nbuilds++;
     cell_valid = false;
   }
 
@@ -857,6 +899,9 @@ class Engine {
       launch_step(MODE_SETUP, cur, cfg().ntimestep, 0);
       pair_evals += list_pairs_undirected();
     }
+    // the rows are sorted by the work they had under the previous list; the first list has no predecessor, so the same
+    // list is built once more now that its touch masks are known (same positions, same pair set: not a LAMMPS re-neighbouring)
+    if (sell_sort && nlocal + nghost > 0) rebuild(false);
     setup_done = true;
     if (!cfg().dumps.empty()) write_dumps();   // Output::setup writes the initial snapshot
   }
@@ -965,18 +1010,25 @@ class Engine {
       if (prof_on) CK(cudaEventRecord(evk0, stream));
       bool wiggle = false;
       for (size_t k = 0; k < cfg().fixes.size(); k++) if (cfg().fixes[k].kind == FIX_WALL_GRAN && cfg().fixes[k].wiggle) wiggle = true;
-      if (graph_on && !mg && !wiggle && K == chunk && K > 1) {   // odd-sized remainders after a rebuild are launched directly
+      // one CUDA graph per chunk; on several GPUs it includes the halo push / signal kernels of every sub-step (peer-memory
+      // path only: their launches carry no per-call argument).  Odd-sized remainders after a rebuild are launched directly.
+      if (graph_on && (!mg || comm.p2p) && !wiggle && K == chunk && K > 1) {
         const int lastflag = (remaining == K) ? 1 : 0;
         StepGraph *g = 0;
         for (size_t k = 0; k < graphs.size(); k++) if (graphs[k].in == in && graphs[k].K == K && graphs[k].last == lastflag && graphs[k].seq0 == seq) g = &graphs[k];
         if (!g || g->stale) {
-          const long long l0 = launches;
+          const long long l0 = launches, h0 = comm.halo_calls;
           cudaGraph_t gr;
           CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
           int cin = in, cseq = seq;
-          for (int s = 0; s < K; s++) { launch_step((lastflag && s == K - 1) ? MODE_LAST : MODE_FUSED, cin, cfg().ntimestep + s + 1, ++cseq); cin ^= 1; }
+          for (int s = 0; s < K; s++) {
+            const bool lastk = (lastflag && s == K - 1);
+            launch_step(lastk ? MODE_LAST : MODE_FUSED, cin, cfg().ntimestep + s + 1, ++cseq);
+            cin ^= 1;
+            if (mg && !lastk) comm.forward(*this, cin, true);
+          }
           CK(cudaStreamEndCapture(stream, &gr));
-          launches = l0;
+          launches = l0; comm.halo_calls = h0;
           if (g) {  // same topology, new kernel arguments
             cudaGraphExecUpdateResultInfo info;
             if (cudaGraphExecUpdate(g->exec, gr, &info) != cudaSuccess) {
@@ -996,6 +1048,7 @@ class Engine {
         }
         CK(cudaGraphLaunch(g->exec, stream));
         launches += K; seq += K; in ^= (K & 1);
+        if (mg) { const int nfw = K - (lastflag ? 1 : 0); launches += 2 * nfw; comm.halo_calls += nfw; }
       } else
       for (int s = 0; s < K; s++) {
         const bool last = (remaining - s == 1);
@@ -1332,9 +1385,12 @@ class Engine {
     if (!have_mesh) fatal("sedi_locate: call sedi_mesh_box first");
     if (!loaded) load_atoms();
     need_device();
+    const double t0 = now_s();
     if (nlocal) k_locate_cells<<<cdiv(nlocal, 256), 256, 0, stream>>>(posr[cur].p, nlocal, mesh, cell.p);
     launches++;
     cell_valid = true;
+    if (want_sums) { CK(cudaStreamSynchronize(stream)); }   // timing mode: the host's log attributes the time to this call
+    timers[2] += now_s() - t0;
   }
 
   void fluid_force() {
@@ -1433,7 +1489,12 @@ class Engine {
       smooth_iters_last = it;
     }
   }
-  void smooth_device_field(double *f, int ncomp) { for (int k = 0; k < ncomp; k++) smooth_component(f, ncomp, k); }
+  void smooth_device_field(double *f, int ncomp) {
+    const double t0 = now_s();
+    for (int k = 0; k < ncomp; k++) smooth_component(f, ncomp, k);
+    CK(cudaStreamSynchronize(stream));
+    timers[1] += now_s() - t0;
+  }
   // UfSmoothed = Uf (1-gamma) -> smooth -> / (1-gamma)   (enhancedCloud.C:675-690)
   void smooth_uf() {
     if (!have_mesh) fatal("sedi_smooth_uf: call sedi_mesh_box first");
@@ -1454,6 +1515,35 @@ class Engine {
     CK(cudaStreamSynchronize(stream));
   }
 
+  // sum over cells of a [C][3] field with the reference's weights (see k_field_sum_partial); all ranks hold the full field
+  void field_sum(const double *f, int mode, double *out3) {
+    const int C = ncells, nb = std::min(256, cdiv(C, 256));
+    sum_partial.ensure(4 * 256); sum_out.ensure(4);
+    k_field_sum_partial<<<nb, 256, 0, stream>>>(C, f, cellV.p, gamma.p, mode, sum_partial.p);
+    k_sum_final<<<1, 256, 0, stream>>>(sum_partial.p, nb, 3, sum_out.p);
+    CK(cudaMemcpyAsync(out3, sum_out.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    launches += 2;
+  }
+  // enhancedCloud::averageInfo (enhancedCloud.C:1341-1370): total particle volume, sum Vp U, volume-averaged velocity
+  void average_info(double *totalVolume, double *totalVel, double *averageVel) {
+    if (!setup_done) setup();
+    need_device();
+    double h[4] = {0.0, 0.0, 0.0, 0.0};
+    if (nlocal) {
+      const int nb = std::min(256, cdiv(nlocal, 256));
+      sum_partial.ensure(4 * 256); sum_out.ensure(4);
+      k_particle_sum_partial<<<nb, 256, 0, stream>>>(nlocal, posr[cur].p, velm[cur].p, sum_partial.p);
+      k_sum_final<<<1, 256, 0, stream>>>(sum_partial.p, nb, 4, sum_out.p);
+      CK(cudaMemcpyAsync(h, sum_out.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      launches += 2;
+    }
+    comm.allreduce_sum_host(h, 4);
+    if (totalVolume) *totalVolume = h[0];
+    for (int d = 0; d < 3; d++) { if (totalVel) totalVel[d] = h[1 + d]; if (averageVel) averageVel[d] = h[1 + d] / (h[0] + 1.0e-150); }
+  }
+
   void scatter_alpha_u(double *hgamma, double *hUe) {
     if (!setup_done) setup();
     if (!cell_valid) locate();
@@ -1462,6 +1552,7 @@ class Engine {
     CK(cudaMemsetAsync(Ue.p, 0, 3 * C * sizeof(double), stream));
     if (nlocal) k_scatter_alpha_u<<<cdiv(nlocal, 256), 256, 0, stream>>>(posr[cur].p, velm[cur].p, cell.p, nlocal, gamma.p, Ue.p);
     if (comm.nranks > 1) { comm.allreduce_sum_dev(gamma.p, C, stream); comm.allreduce_sum_dev(Ue.p, 3 * C, stream); }
+    if (want_sums) field_sum(Ue.p, 0, sums + 6);   // Utotal1 = sum of Vp Up per cell, before the division by V (:936-941)
     if (smoothing_on(8) || smoothing_on(2)) {  // enhancedCloud.C:932-962 with alphaSmooth / UpSmooth
       k_alpha_u_divV<<<cdiv(C, 256), 256, 0, stream>>>((int)C, cellV.p, gamma.p, Ue.p);
       if (smoothing_on(8)) smooth_device_field(gamma.p, 1);
@@ -1471,6 +1562,7 @@ class Engine {
       k_finalize_alpha_u<<<cdiv(C, 256), 256, 0, stream>>>((int)C, cellV.p, gamma.p, Ue.p);
     }
     launches += 2;
+    if (want_sums) field_sum(Ue.p, 2, sums + 9);   // Utotal2 = sum Ue V gamma after smoothing (:966-970)
     if (hgamma) CK(cudaMemcpyAsync(hgamma, gamma.p, C * sizeof(double), cudaMemcpyDeviceToHost, stream));
     if (hUe) CK(cudaMemcpyAsync(hUe, Ue.p, 3 * C * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
@@ -1484,6 +1576,7 @@ class Engine {
     if (nlocal)
       k_scatter_asrc<<<cdiv(nlocal, 256), 256, 0, stream>>>(posr[cur].p, velm[cur].p, cell.p, nlocal, Uf.p, gamma.p, cellV.p, drag_model, nub, rhob, Asrc.p);
     if (comm.nranks > 1) comm.allreduce_sum_dev(Asrc.p, 3 * C, stream);
+    if (want_sums) field_sum(Asrc.p, 1, sums + 0);   // Ftotal1 = sum Asrc V (1 - gamma) before smoothing (:395-403)
     if (smoothing_on(4)) {  // Asrc (1-gamma) -> smooth -> / (1-gamma)   (enhancedCloud.C:407-416, dragSmooth)
       k_scale_one_minus_gamma<<<cdiv(C, 256), 256, 0, stream>>>((int)C, gamma.p, Asrc.p, 3, 0);
       smooth_device_field(Asrc.p, 3);
@@ -1492,6 +1585,7 @@ class Engine {
       k_finalize_asrc<<<cdiv(C, 256), 256, 0, stream>>>((int)C, gamma.p, Asrc.p);
     }
     launches += 2;
+    if (want_sums) field_sum(Asrc.p, 1, sums + 3);   // Ftotal2 after smoothing (:421-429)
     if (hAsrc) CK(cudaMemcpyAsync(hAsrc, Asrc.p, 3 * C * sizeof(double), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     if (hOmega) memset(hOmega, 0, C * sizeof(double));  // enhancedCloud.C:391
@@ -1869,13 +1963,24 @@ void lammps_get_local_domain(void *ptr, double *dom) {
   for (int d = 0; d < 3; d++) { dom[2 * d] = e->comm.sublo(e->cfg(), d, 0.0); dom[2 * d + 1] = e->comm.subhi(e->cfg(), d, 0.0); }
 }
 void lammps_get_local_info(void *ptr, double *coords, double *velos, int *foamCpuId, int *lmpCpuId, int *tag) {
-  E(ptr)->get_local(coords, velos, foamCpuId, lmpCpuId, tag);
+  Engine *e = E(ptr);
+  const double t0 = Engine::now_s();
+  e->get_local(coords, velos, foamCpuId, lmpCpuId, tag);
+  e->timers[8] += Engine::now_s() - t0;   // cpuTimeSplit[5]: lammps -> foam
 }
 void lammps_put_local_info(void *ptr, int nLocalIn, double *fdrag, double *DuDt, int *foamCpuIdIn, int *tagIn) {
   (void)DuDt;  // ignored by the reference as well (library.cpp:314-367 never reads it)
-  E(ptr)->put_local(nLocalIn, fdrag, foamCpuIdIn, tagIn);
+  Engine *e = E(ptr);
+  const double t0 = Engine::now_s();
+  e->put_local(nLocalIn, fdrag, foamCpuIdIn, tagIn);
+  e->timers[6] += Engine::now_s() - t0;   // cpuTimeSplit[3]: foam -> lammps
 }
-void lammps_step(void *ptr, int n) { Engine *e = E(ptr); e->save_uold_if_ready(); e->run(n); }
+void lammps_step(void *ptr, int n) {
+  Engine *e = E(ptr);
+  const double t0 = Engine::now_s();
+  e->save_uold_if_ready(); e->run(n);
+  e->timers[7] += Engine::now_s() - t0;   // cpuTimeSplit[4]: lammps
+}
 void lammps_set_timestep(void *ptr, double dt) { Engine *e = E(ptr); e->cfg().dt = dt; e->params_dirty = true; }
 double lammps_get_timestep(void *ptr) { return E(ptr)->cfg().dt; }
 void lammps_create_particle(void *ptr, int npAdd, double *position, double *tag, double diameter, double rho, int type,
@@ -1985,7 +2090,29 @@ void sedi_enable_diag(void *ptr, int on) { E(ptr)->want_diag = (on != 0); }
 void sedi_get_coupling_diag(void *ptr, int *cell, double *Uri, double *magUri, double *alphap, double *Jd, double *F) {
   E(ptr)->get_coupling_diag(cell, Uri, magUri, alphap, Jd, F);
 }
-void sedi_step(void *ptr, int n) { Engine *e = E(ptr); e->save_uold_if_ready(); e->run(n); }
+void sedi_step(void *ptr, int n) {
+  Engine *e = E(ptr);
+  const double t0 = Engine::now_s();
+  e->save_uold_if_ready(); e->run(n);
+  e->timers[7] += Engine::now_s() - t0;
+}
+void sedi_enable_conservation_sums(void *ptr, int on) { E(ptr)->want_sums = (on != 0); }
+void sedi_get_conservation_sums(void *ptr, double *Ftotal_before, double *Ftotal_after, double *Utotal_before, double *Utotal_after) {
+  Engine *e = E(ptr);
+  for (int d = 0; d < 3; d++) {
+    if (Ftotal_before) Ftotal_before[d] = e->sums[d];
+    if (Ftotal_after) Ftotal_after[d] = e->sums[3 + d];
+    if (Utotal_before) Utotal_before[d] = e->sums[6 + d];
+    if (Utotal_after) Utotal_after[d] = e->sums[9 + d];
+  }
+}
+void sedi_average_info(void *ptr, double *totalVolume, double *totalVel, double *averageVel) { E(ptr)->average_info(totalVolume, totalVel, averageVel); }
+void sedi_get_timers(void *ptr, double *diffusionTimeCount, double *particleMoveTime, double *cpuTimeSplit) {
+  Engine *e = E(ptr);
+  if (diffusionTimeCount) { diffusionTimeCount[0] = e->timers[0]; diffusionTimeCount[1] = e->timers[1]; }
+  if (particleMoveTime) *particleMoveTime = e->timers[2];
+  if (cpuTimeSplit) for (int k = 0; k < 6; k++) cpuTimeSplit[k] = e->timers[3 + k];
+}
 
 int sedi_comm_init(void *ptr, int rank, int nranks, const void *nccl_unique_id, int id_bytes, const int *procgrid) {
   return E(ptr)->comm.init(*E(ptr), rank, nranks, nccl_unique_id, id_bytes, procgrid);

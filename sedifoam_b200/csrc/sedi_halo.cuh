@@ -222,9 +222,13 @@ __global__ void k_halo_push(const D4 *posr, const D4 *velm, const D4 *omgt, cons
 // all-ranks barrier + rebuild-flag consensus through peer memory: rank r's slot [me] of every rank's signal array
 // receives (epoch << 32 | my flag); then every rank waits until all its slots carry this epoch and takes the max flag.
 struct SignalTable { int nranks, me; unsigned long long *rsig[64]; };
-__global__ void k_halo_signal_wait(const __grid_constant__ SignalTable S, volatile unsigned long long *mysig, unsigned epoch, int *ctrl, int with_flag) {
+// The epoch is a device-resident counter (mysig[64], never written by a peer): all ranks run the same sequence of
+// exchanges, so their counters agree, and the launch has no per-call argument -- a chunk of sub-steps including its halo
+// kernels is one CUDA graph on several GPUs as well.
+__global__ void k_halo_signal_wait(const __grid_constant__ SignalTable S, volatile unsigned long long *mysig, int *ctrl, int with_flag) {
   __shared__ int sflag[64];
   const int r = threadIdx.x;
+  const unsigned epoch = (unsigned)mysig[64] + 1u;
   if (r < S.nranks) {
     const unsigned fl = with_flag ? (unsigned)ctrl[0] : 0u;
     __threadfence_system();
@@ -235,10 +239,13 @@ __global__ void k_halo_signal_wait(const __grid_constant__ SignalTable S, volati
     sflag[r] = (int)(unsigned)(v & 0xffffffffull);
   }
   __syncthreads();
-  if (r == 0 && with_flag) {
-    int m = 0;
-    for (int k = 0; k < S.nranks; k++) m = max(m, sflag[k]);
-    ctrl[0] = m;
+  if (r == 0) {
+    mysig[64] = epoch;
+    if (with_flag) {
+      int m = 0;
+      for (int k = 0; k < S.nranks; k++) m = max(m, sflag[k]);
+      ctrl[0] = m;
+    }
   }
   __threadfence_system();
 }

@@ -44,6 +44,7 @@ struct BuildParams {
   const D4 *omgt_old;
   int nlocal_rows;               // first ghost row (ghost partners are reached through gorder)
   const int *gcellstart, *gorder;  // ghost rows binned by cell (null on a single GPU)
+  const int *crow;               // canonical (bin-ordered) position -> row, when the rows are sorted by work inside windows (null: identity)
   int n_old;                     // rows of the old arrays; oldidx >= n_old marks a particle that migrated in
   const int *arr_nh, *arr_tag;   // history carried by migrated particles
   const D4 *arr_shear;
@@ -273,7 +274,8 @@ __global__ void __launch_bounds__(128) k_build_list(const __grid_constant__ Buil
             const int c = cell_index(bx, by, bz, B.nb, B.tile);
             const int img = (ix + 1) + 3 * (iy + 1) + 9 * (iz + 1);
             const int js = B.cellstart[c], je = B.cellstart[c + 1];
-            for (int j = js; j < je; j++) visit(j, img, ix, iy, iz);
+            if (B.crow) { for (int k = js; k < je; k++) visit(B.crow[k], img, ix, iy, iz); }
+            else for (int j = js; j < je; j++) visit(j, img, ix, iy, iz);
             if (B.gcellstart) {
               const int gs = B.gcellstart[c], ge = B.gcellstart[c + 1];
               for (int k = gs; k < ge; k++) visit(B.nlocal_rows + B.gorder[k], img, ix, iy, iz);

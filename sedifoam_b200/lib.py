@@ -26,7 +26,8 @@ EXPORTED_SYMBOLS = [
     "sedi_synchronize", "sedi_stream", "sedi_last_step_ms", "sedi_timer_start", "sedi_timer_stop_ms", "sedi_profile",
     "sedi_get_profile", "sedi_mesh_box", "sedi_mesh_rectilinear", "sedi_mesh_ncells", "sedi_coupling_config",
     "sedi_put_cell_fields", "sedi_coupling_time_index", "sedi_coupling_inlet", "sedi_get_history_state", "sedi_locate", "sedi_compute_fluid_force", "sedi_scatter_alpha_u", "sedi_calc_tc",
-    "sedi_enable_diag", "sedi_get_coupling_diag", "sedi_step", "sedi_comm_init", "sedi_comm_unique_id", "sedi_comm_rank", "sedi_comm_stat",
+    "sedi_enable_diag", "sedi_get_coupling_diag", "sedi_step", "sedi_enable_conservation_sums", "sedi_get_conservation_sums",
+    "sedi_average_info", "sedi_get_timers", "sedi_comm_init", "sedi_comm_unique_id", "sedi_comm_rank", "sedi_comm_stat",
     "sedi_decomp_grid", "sedi_decomp_owner", "sedi_decomp_links", "sedi_smooth_config", "sedi_smooth_uf", "sedi_smooth_field",
     "sedi_smooth_last_iters",
 ]
@@ -124,6 +125,10 @@ def load_library():
         "sedi_smooth_last_iters": (i, [vp]),
         "sedi_get_coupling_diag": (None, [vp] + [vp] * 6),
         "sedi_step": (None, [vp, i]),
+        "sedi_enable_conservation_sums": (None, [vp, i]),
+        "sedi_get_conservation_sums": (None, [vp, vp, vp, vp, vp]),
+        "sedi_average_info": (None, [vp, vp, vp, vp]),
+        "sedi_get_timers": (None, [vp, vp, vp, vp]),
         "sedi_comm_init": (i, [vp, i, i, vp, i, vp]),
         "sedi_comm_unique_id": (i, [vp, i]),
         "sedi_comm_rank": (i, [vp]),
@@ -443,6 +448,25 @@ class Lammps:
 
     def sedi_step(self, n):
         self.lib.sedi_step(self.h, int(n))
+
+    def enable_conservation_sums(self, on=True):
+        self.lib.sedi_enable_conservation_sums(self.h, 1 if on else 0)
+
+    def conservation_sums(self):
+        """the reference's printed invariants: dict(F_before, F_after, U_before, U_after), vectors of 3"""
+        a = [np.zeros(3) for _ in range(4)]
+        self.lib.sedi_get_conservation_sums(self.h, *[_vp(v) for v in a])
+        return dict(F_before=a[0], F_after=a[1], U_before=a[2], U_after=a[3])
+
+    def average_info(self):
+        vol = np.zeros(1); tv = np.zeros(3); av = np.zeros(3)
+        self.lib.sedi_average_info(self.h, _vp(vol), _vp(tv), _vp(av))
+        return dict(totalVolume=float(vol[0]), totalVel=tv, averageVel=av)
+
+    def timers(self):
+        d = np.zeros(2); m = np.zeros(1); c = np.zeros(6)
+        self.lib.sedi_get_timers(self.h, _vp(d), _vp(m), _vp(c))
+        return dict(diffusionTimeCount=d, particleMoveTime=float(m[0]), cpuTimeSplit=c)
 
     # ---- multi-GPU ---------------------------------------------------------------------------------------------
     @staticmethod

@@ -2,11 +2,11 @@
 # round 2: settle the benchmark column, then sweep + bench + ncu + parity tests of the warp-queue kernel
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
-SEDI_KSTEP_PATH=ell timeout 900 python tools/make_settled_column.py --steps 600000 --chunk 50000 > gpurun_out/settle.log 2>&1; echo "settle rc=$?"; tail -4 gpurun_out/settle.log
+if [ "$SEDI_RESETTLE" = "1" ]; then SEDI_KSTEP_PATH=ell timeout 900 python tools/make_settled_column.py --steps 600000 --chunk 50000 > gpurun_out/settle.log 2>&1; echo "settle rc=$?"; tail -4 gpurun_out/settle.log; fi
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/c1_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/c1_smoke.log
-timeout 900 python tools/kstep_sweep.py --bed settled --envs 'wq=;ell=SEDI_KSTEP_PATH=ell' --out gpurun_out/sweep_settled.json > gpurun_out/sweep_settled.log 2>&1
-timeout 300 python tools/kstep_sweep.py --bed settled --libs sedifoam_b200/libsedi_b200.so --envs 'rows=SEDI_KSTEP_PATH=rows' --out gpurun_out/sweep_settled_rows.json >> gpurun_out/sweep_settled.log 2>&1
-timeout 400 python tools/kstep_sweep.py --bed lattice --libs sedifoam_b200/libsedi_b200.so --envs 'wq=;ell=SEDI_KSTEP_PATH=ell' --out gpurun_out/sweep_lattice.json > gpurun_out/sweep_lattice.log 2>&1
+timeout 900 python tools/kstep_sweep.py --bed settled --envs 'sell=' --out gpurun_out/sweep_settled.json > gpurun_out/sweep_settled.log 2>&1
+timeout 600 python tools/kstep_sweep.py --bed settled --libs sedifoam_b200/libsedi_b200.so --envs 'sell_unsorted=SEDI_SELL_SORT=0;wq=SEDI_KSTEP_PATH=wq;wq_sorted=SEDI_KSTEP_PATH=wq,SEDI_SELL_SORT=1;ell=SEDI_KSTEP_PATH=ell;ell_sorted=SEDI_KSTEP_PATH=ell,SEDI_SELL_SORT=1' --out gpurun_out/sweep_settled_paths.json >> gpurun_out/sweep_settled.log 2>&1
+timeout 400 python tools/kstep_sweep.py --bed lattice --libs sedifoam_b200/libsedi_b200.so --envs 'sell=;wq=SEDI_KSTEP_PATH=wq;ell=SEDI_KSTEP_PATH=ell' --out gpurun_out/sweep_lattice.json > gpurun_out/sweep_lattice.log 2>&1
 grep -h '^{' gpurun_out/sweep_settled.log gpurun_out/sweep_lattice.log | python -c "
 import sys, json
 for l in sys.stdin:
