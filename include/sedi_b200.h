@@ -53,6 +53,9 @@ void lammps_delete_particle(void *ptr, int *deleteList, int nDelete);          /
 /* ---- (2) device-resident engine API -------------------------------------------------------------------- */
 int sedi_abi_version(void);
 int sedi_device_count(void); /* number of CUDA devices visible (0 on a CPU-only box; never aborts) */
+/* the parsed script as JSON (host only): pair / fix / group / dump settings as the engine understood them; returns the
+ * length written, or -(needed size) when cap is too small */
+int sedi_config_json(void *ptr, char *buf, int cap);
 void sedi_set_device(void *ptr, int dev); /* before the first compute call; default: $SEDI_DEVICE, $LOCAL_RANK, 0 */
 
 /* programmatic equivalents of `read_data` (box header + Atoms section: id type diameter density x y z) */

@@ -108,12 +108,13 @@ struct SimConfig {
   int procgrid[3];
   long long ntimestep;
   int freeze_group_bit;  // EXTERNAL: pair styles read the group bit of `fix freeze`
+  int neigh_modify_seen; // LAMMPS' default is `delay 10`; the engine behaves as `delay 0` and says so when the command is absent
   SimConfig() {
     memset(periodic, 0, sizeof(periodic));
     for (int d = 0; d < 3; d++) { boxlo[d] = 0; boxhi[d] = 1; procgrid[d] = 0; }
     have_box = 0; ntypes = 1; skin = 0.3; dt = 0.005; newton_pair = 1; pair = PAIR_NONE;
     memset(&gran, 0, sizeof(gran)); memset(&lub, 0, sizeof(lub)); lub.flagHI = 1; lub.flagVF = 1;
-    nwalls = 0; ntimestep = 0; freeze_group_bit = 0;
+    nwalls = 0; ntimestep = 0; freeze_group_bit = 0; neigh_modify_seen = 0;
     Group g; g.name = "all"; g.bit = 1; groups.push_back(g);
     for (int d = 0; d < 3; d++) boundary_str[d] = "pp";
   }
@@ -398,8 +399,21 @@ class Script {
     }
     else if (c == "atom_modify" || c == "communicate" || c == "comm_modify" || c == "thermo" ||
              c == "thermo_style" || c == "thermo_modify" || c == "dimension" || c == "echo" ||
-             c == "log" || c == "dump_modify" || c == "compute" || c == "neigh_modify") {
-      // accepted, no effect on the hot path (neigh_modify delay 0 every 1 check yes is the only mode implemented)
+             c == "log" || c == "dump_modify" || c == "compute") {
+      // accepted, no effect on the hot path
+    }
+    else if (c == "neigh_modify") {
+      // The engine tests the skin/2 displacement criterion after every sub-step and rebuilds at once: LAMMPS'
+      // `delay 0 every 1 check yes` (every shipped in.lammps, e.g. xiaocase1/in.lammps:13).  Any other setting would
+      // change when the lists are rebuilt and with it the pair sets and the history carry: refused, not ignored.
+      for (size_t k = 1; k + 1 < a.size(); k += 2) {
+        if (a[k] == "delay") { if (atoi(a[k + 1].c_str()) != 0) fatal("neigh_modify delay: only `delay 0` is supported (rebuild check after every step)"); }
+        else if (a[k] == "every") { if (atoi(a[k + 1].c_str()) != 1) fatal("neigh_modify every: only `every 1` is supported"); }
+        else if (a[k] == "check") { if (a[k + 1] != "yes") fatal("neigh_modify check: only `check yes` is supported"); }
+        else if (a[k] == "one" || a[k] == "page" || a[k] == "binsize") { /* memory / bin tuning: no effect on the pair set */ }
+        else fatal("neigh_modify keyword not supported:", a[k].c_str());
+      }
+      cfg.neigh_modify_seen = 1;
     }
     else if (c == "write_restart") { if (a.size() < 2) fatal("Illegal write_restart command"); act.kind = ScriptAction::WRITE_RESTART; act.path = a[1]; }
     else if (c == "read_restart") { if (a.size() < 2) fatal("Illegal read_restart command"); act.kind = ScriptAction::READ_RESTART; act.path = a[1]; }

@@ -230,6 +230,7 @@ class Engine {
   long long nbuilds, pair_evals, steps_done, launches, list_gran_dir, list_type_dir, list_gran_img, list_type_img;
   int chunk;
   bool use_rows;   // pair sweep on the row-block kernel (SEDI_KSTEP_PATH=rows)
+  bool warned_neigh;
   bool use_wq;     // pair sweep on the warp-queue kernel (SEDI_KSTEP_PATH=wq)
   bool use_sell;   // pair sweep on the sorted-row kernel (default); SEDI_KSTEP_PATH=ell selects the streamed slot walk
   bool sell_sort;  // rows sorted by work inside windows at every rebuild (default with the sorted-row kernel; SEDI_SELL_SORT=0/1)
@@ -289,6 +290,7 @@ class Engine {
     use_rows = false;
     e = getenv("SEDI_KSTEP_PATH");
     if (e && !strcmp(e, "rows")) use_rows = true;
+    warned_neigh = false;
     use_wq = (e && !strcmp(e, "wq"));
     use_sell = !(e && (!strcmp(e, "rows") || !strcmp(e, "ell") || !strcmp(e, "wq")));
     sell_sort = use_sell;
@@ -870,6 +872,11 @@ class Engine {
     if (restart_pending) { setup_from_restart(); return; }
     if (!loaded) load_atoms();
     need_device();
+    if (!cfg().neigh_modify_seen && cfg().pair != PAIR_NONE && !warned_neigh) {
+      fprintf(stderr, "WARNING: no neigh_modify command: LAMMPS' default is `delay 10 every 1 check yes`; libsedi_b200 checks the skin/2 "
+                      "criterion after every step (`delay 0`, as every shipped in.lammps sets)\n");
+      warned_neigh = true;
+    }
     dt_init = cfg().dt;
     compute_cutoffs();
     if (cfg().lub.enabled) {  // PairLubricatePoly::init_style, pair_lubricate_poly.cpp:533-559 (vol_T = box volume)
@@ -901,7 +908,12 @@ class Engine {
     }
     // the rows are sorted by the work they had under the previous list; the first list has no predecessor, so the same
     // list is built once more now that its touch masks are known (same positions, same pair set: not a LAMMPS re-neighbouring)
-    if (sell_sort && nlocal + nghost > 0) rebuild(false);
+    if (sell_sort && nlocal + nghost > 0) {
+      const bool ip = inject_pending;   // the list just built carries the injected history: re-attach from it, not from the arrival lists again
+      inject_pending = false;
+      rebuild(false);
+      inject_pending = ip;
+    }
     setup_done = true;
     if (!cfg().dumps.empty()) write_dumps();   // Output::setup writes the initial snapshot
   }
@@ -1990,6 +2002,49 @@ void lammps_create_particle(void *ptr, int npAdd, double *position, double *tag,
 void lammps_delete_particle(void *ptr, int *deleteList, int nDelete) { E(ptr)->delete_particles(deleteList, nDelete); }
 
 int sedi_abi_version(void) { return 1; }
+/* what the script parser understood, as JSON (host only, no device needed): the parser check of tests/test_abi.py compares it with
+ * hand-written expectations for every shipped in.lammps */
+int sedi_config_json(void *ptr, char *buf, int cap) {
+  const sedi::SimConfig &c = E(ptr)->cfg();
+  std::string o = "{";
+  char t[512];
+  snprintf(t, sizeof(t), "\"periodic\": [%d, %d, %d], \"skin\": %.17g, \"dt\": %.17g, \"newton_pair\": %d, \"pair\": %d, \"ntypes\": %d, \"nwalls\": %d, "
+           "\"freeze_group_bit\": %d, \"neigh_modify_seen\": %d, \"procgrid\": [%d, %d, %d], ", c.periodic[0], c.periodic[1], c.periodic[2], c.skin, c.dt, c.newton_pair, c.pair, c.ntypes, c.nwalls,
+           c.freeze_group_bit, c.neigh_modify_seen, c.procgrid[0], c.procgrid[1], c.procgrid[2]);
+  o += t;
+  snprintf(t, sizeof(t), "\"gran\": {\"kn\": %.17g, \"kt\": %.17g, \"gamman\": %.17g, \"gammat\": %.17g, \"xmu\": %.17g, \"dampflag\": %d}, ", c.gran.kn, c.gran.kt,
+           c.gran.gamman, c.gran.gammat, c.gran.xmu, c.gran.dampflag);
+  o += t;
+  snprintf(t, sizeof(t), "\"lub\": {\"enabled\": %d, \"mu\": %.17g, \"flaglog\": %d, \"flagfld\": %d, \"cut_inner\": %.17g, \"cut_global\": %.17g, \"flagHI\": %d, \"flagVF\": %d}, ",
+           c.lub.enabled, c.lub.mu, c.lub.flaglog, c.lub.flagfld, c.lub.cut_inner, c.lub.cut_global, c.lub.flagHI, c.lub.flagVF);
+  o += t;
+  o += "\"groups\": {";
+  for (size_t k = 0; k < c.groups.size(); k++) { snprintf(t, sizeof(t), "%s\"%s\": %d", k ? ", " : "", c.groups[k].name.c_str(), c.groups[k].bit); o += t; }
+  o += "}, \"fixes\": [";
+  for (size_t k = 0; k < c.fixes.size(); k++) {
+    const sedi::FixSpec &f = c.fixes[k];
+    snprintf(t, sizeof(t), "%s{\"id\": \"%s\", \"kind\": %d, \"groupbit\": %d, \"g\": %.17g, \"gdir\": [%.17g, %.17g, %.17g], \"carrier_rho\": %.17g, ", k ? ", " : "", f.id, f.kind,
+             f.groupbit, f.g, f.gdir[0], f.gdir[1], f.gdir[2], f.carrier_rho);
+    o += t;
+    snprintf(t, sizeof(t), "\"ah\": %.17g, \"lam\": %.17g, \"smin\": %.17g, \"smax\": %.17g, \"opt\": %d, ", f.ah, f.lam, f.smin, f.smax, f.opt);
+    o += t;
+    snprintf(t, sizeof(t), "\"wall\": {\"kn\": %.17g, \"kt\": %.17g, \"gamman\": %.17g, \"gammat\": %.17g, \"xmu\": %.17g, \"dampflag\": %d}, \"wallstyle\": %d, \"lo\": %.17g, "
+             "\"hi\": %.17g, \"cylradius\": %.17g, \"wiggle\": %d, \"wshear\": %d, \"axis\": %d, \"amplitude\": %.17g, \"period\": %.17g, \"vshear\": %.17g, \"wall_index\": %d}",
+             f.wall.kn, f.wall.kt, f.wall.gamman, f.wall.gammat, f.wall.xmu, f.wall.dampflag, f.wallstyle, f.lo, f.hi, f.cylradius, f.wiggle, f.wshear, f.axis, f.amplitude,
+             f.period, f.vshear, f.wall_index);
+    o += t;
+  }
+  o += "], \"dumps\": [";
+  for (size_t k = 0; k < c.dumps.size(); k++) {
+    snprintf(t, sizeof(t), "%s{\"id\": \"%s\", \"every\": %lld, \"path\": \"%s\", \"columns\": \"%s\", \"groupbit\": %d}", k ? ", " : "", c.dumps[k].id.c_str(), c.dumps[k].every,
+             c.dumps[k].path.c_str(), c.dumps[k].columns.c_str(), c.dumps[k].groupbit);
+    o += t;
+  }
+  o += "]}";
+  if ((int)o.size() + 1 > cap) return -(int)o.size() - 1;
+  memcpy(buf, o.c_str(), o.size() + 1);
+  return (int)o.size();
+}
 int sedi_device_count(void) {
   int cnt = 0;
   if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -91,7 +91,9 @@ __global__ void __launch_bounds__(SEDI_SELL_THREADS, SEDI_SELL_MINB) k_step_sell
   if (i == 0 && P.mode != MODE_SETUP) atomicAdd(&P.ctrl[1], 1);
   if (i >= P.n) return;
 
-  // ---- own row, list words of the first 16 slots (the first eight unconditionally: they depend on nothing)
+  // ---- own row, list words of the first 16 slots (twelve unconditionally: they depend on nothing; rows have >= 16 slots)
+  __shared__ unsigned s_e[16][SEDI_SELL_THREADS];   // the row's list words, kept for phase 2 (one column per lane: conflict-free)
+  const int tid = threadIdx.x;
   D4 pi = ldg_d4_stream(&P.posr_in[i]);
   D4 vi = ldg_d4_stream(&P.velm_in[i]);
   D4 wi = ldg_d4_stream(&P.omgt_in[i]);
@@ -99,12 +101,22 @@ __global__ void __launch_bounds__(SEDI_SELL_THREADS, SEDI_SELL_MINB) k_step_sell
   const unsigned long long tm_old = HIST ? P.tmask[i] : 0ull;
   unsigned e16[16];
 #pragma unroll
-  for (int k = 0; k < 8; k++) e16[k] = ld_nc_u32(&P.nbr[(size_t)k * P.npad + i]);
+  for (int k = 0; k < 12; k++) e16[k] = ld_nc_u32(&P.nbr[(size_t)k * P.npad + i]);
 #pragma unroll
-  for (int k = 8; k < 16; k++) e16[k] = (k < nni) ? ld_nc_u32(&P.nbr[(size_t)k * P.npad + i]) : 0u;
+  for (int k = 12; k < 16; k++) e16[k] = (k < nni) ? ld_nc_u32(&P.nbr[(size_t)k * P.npad + i]) : 0u;
+  // per-particle inputs of the epilogue: start them towards L1 now, read them after the sweep (one request per 32-byte sector)
+  if ((tid & 3) == 0) {
+    if (P.has_fdrag) { prefetch_l1(&P.fdrag[0][i]); prefetch_l1(&P.fdrag[1][i]); prefetch_l1(&P.fdrag[2][i]); }
+    if (P.mode == MODE_FUSED) { prefetch_l1(&P.xhold[0][i]); prefetch_l1(&P.xhold[1][i]); prefetch_l1(&P.xhold[2][i]); }
+  }
+  if ((tid & 7) == 0 && P.wmask) prefetch_l1(&P.wmask[i]);
   if (bits_flags((unsigned long long)__double_as_longlong(wi.w)) & PFLAG_GHOST) return;  // ghost rows are refreshed by the halo exchange
   const double radi = pi.w, mi = vi.w;
   const int maski = bits_mask((unsigned long long)__double_as_longlong(wi.w));
+#pragma unroll
+  for (int k = 0; k < 16; k++) { if (k >= nni) e16[k] = 0u; s_e[k][tid] = e16[k]; }
+#pragma unroll
+  for (int k = 8; k < 16; k++) if (k < nni) prefetch_l1(&P.posr_in[e16[k] & NB_IDX_MASK]);   // second gather batch: lines on their way while the first is tested
 
   // ---- phase 1: which list entries overlap (pair :131 `rsq >= radsum*radsum` -> no contact)
   unsigned long long touch = 0ull;
@@ -125,7 +137,7 @@ __global__ void __launch_bounds__(SEDI_SELL_THREADS, SEDI_SELL_MINB) k_step_sell
     if (b < nni) {
       D4 p8[8];
 #pragma unroll
-      for (int k = 0; k < 8; k++) { if (b + k >= nni) e16[b + k] = 0u; p8[k] = ldg_d4(&P.posr_in[e16[b + k] & NB_IDX_MASK]); }
+      for (int k = 0; k < 8; k++) p8[k] = ldg_d4(&P.posr_in[e16[b + k] & NB_IDX_MASK]);
 #pragma unroll
       for (int k = 0; k < 8; k++) test_entry(e16[b + k], p8[k], b + k);
     }
@@ -149,12 +161,13 @@ __global__ void __launch_bounds__(SEDI_SELL_THREADS, SEDI_SELL_MINB) k_step_sell
   unsigned long long m = touch;
   int s = 0;
   unsigned e = 0u;
-  if (m) { s = __ffsll((long long)m) - 1; e = ld_nc_u32(&P.nbr[(size_t)s * P.npad + i]); }
+  auto list_word = [&](const int sl) -> unsigned { return sl < 16 ? s_e[sl][tid] : ld_nc_u32(&P.nbr[(size_t)sl * P.npad + i]); };
+  if (m) { s = __ffsll((long long)m) - 1; e = list_word(s); }
   while (m) {
     m &= m - 1;
     int sn = 0;
     unsigned en = 0u;
-    if (m) { sn = __ffsll((long long)m) - 1; en = ld_nc_u32(&P.nbr[(size_t)sn * P.npad + i]); }   // L1 hit: phase 1 read the line
+    if (m) { sn = __ffsll((long long)m) - 1; en = list_word(sn); }
     const size_t slot = (size_t)s * P.npad + i;
     const int j = (int)(e & NB_IDX_MASK);
     D4 pj = ldg_d4(&P.posr_in[j]);

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "lammps_get_initial_np", "lammps_get_initial_info", "lammps_get_local_n", "lammps_get_local_domain",
     "lammps_get_local_info", "lammps_put_local_info", "lammps_step", "lammps_set_timestep", "lammps_get_timestep",
     "lammps_create_particle", "lammps_delete_particle",
-    "sedi_abi_version", "sedi_device_count", "sedi_set_device", "sedi_set_box", "sedi_add_atoms", "sedi_set_omega",
+    "sedi_abi_version", "sedi_config_json", "sedi_device_count", "sedi_set_device", "sedi_set_box", "sedi_add_atoms", "sedi_set_omega",
     "sedi_get_state", "sedi_get_pairs", "sedi_get_wall_shear", "sedi_get_row_stats", "sedi_force_rebuild", "sedi_get_stat", "sedi_reset_stats",
     "sedi_synchronize", "sedi_stream", "sedi_last_step_ms", "sedi_timer_start", "sedi_timer_stop_ms", "sedi_profile",
     "sedi_get_profile", "sedi_mesh_box", "sedi_mesh_rectilinear", "sedi_mesh_ncells", "sedi_coupling_config",
@@ -88,6 +88,7 @@ def load_library():
         "lammps_delete_particle": (None, [vp, vp, i]),
         "sedi_abi_version": (i, []),
         "sedi_device_count": (i, []),
+        "sedi_config_json": (i, [vp, C.c_char_p, i]),
         "sedi_set_device": (None, [vp, i]),
         "sedi_set_box": (None, [vp, vp, vp, i]),
         "sedi_add_atoms": (None, [vp, i] + [vp] * 6),
@@ -191,6 +192,16 @@ class Lammps:
     def commands(self, text):
         for ln in text.strip().splitlines():
             self.command(ln)
+
+    def config(self):
+        """what the script parser understood (dict): pair / fix / group / dump settings"""
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        n = self.lib.sedi_config_json(self.h, buf, len(buf))
+        if n < 0:
+            buf = C.create_string_buffer(-n + 16)
+            n = self.lib.sedi_config_json(self.h, buf, len(buf))
+        return json.loads(buf.value.decode())
 
     def file(self, path):
         self.lib.lammps_file(self.h, str(path).encode())
