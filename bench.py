@@ -46,8 +46,8 @@ CUBE_GRID = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 WORKLOADS = {
     1: "configs[1]: 1e5 monodisperse spheres (random, phi 0.30) sedimenting in a periodic column, gran/hertzFix/history + wall/granFix floor + fdrag(ErgunWenYu)",
     2: "configs[2]: 1e6-particle settled random bed (periodic in x/z, wall/granFix floor), gran/hertzFix/history + fdrag(ErgunWenYu)",
-    3: "configs[3]: 1e6-particle cohesive bed (d 50 um) under a sheared wall/granFix lid, gran/hertzFix/history + fix cohesive + fdrag(ErgunWenYu)",
-    4: "configs[4]: polydisperse (0.3-0.7 mm) dense periodic packing, hybrid/overlay gran/hertzFix/history + lubricate/poly, 1.25e6 particles per GPU",
+    3: "configs[3]: 1e6-particle cohesive bed (d 50 um, settled random packing) under a sheared wall/granFix lid, gran/hertzFix/history + fix cohesive + fdrag(ErgunWenYu)",
+    4: "configs[4]: polydisperse (0.3-0.7 mm) dense periodic random packing, hybrid/overlay gran/hertzFix/history + lubricate/poly (squeeze term, cutoff 1.5 dmax), 1.25e6 particles per GPU",
 }
 
 
@@ -85,9 +85,10 @@ def build_case(cfg, bed, world, rank, scaling, frac=None, size=1.0):
         return cases.random_column(tiles=(2 * s, 5 * s, 2 * s), brick=(pg, rank) if world > 1 else None)
     if cfg == 3:
         if frac is not None:
-            return cases.random_cohesive_bed(tiles=(5 * s * frac[0], 8 * s, 5 * s * frac[1]))
+            cols = {8: (1, 3), 4: (2, 3), 2: (2, 5), 1: (5, 5)}[int(round(1.0 / (frac[0] * frac[1])))]
+            return cases.settled_cohesive_bed(columns=(max(1, round(cols[0] * s)), max(1, round(cols[1] * s))))
         pg = WEAK_GRID[world]
-        return cases.random_cohesive_bed(tiles=(5 * s, 8 * s, 5 * s), brick=(pg, rank) if world > 1 else None)
+        return cases.settled_cohesive_bed(columns=(max(1, round(5 * s)), max(1, round(5 * s))), brick=(pg, rank) if world > 1 else None)
     if cfg == 4:
         if frac is not None:
             return cases.random_poly_lubricated(tiles=(max(1, round(5 * s * frac[0])), max(1, round(10 * s)), max(1, round(5 * s * frac[1]))))

@@ -421,13 +421,16 @@ fix yt all wall/granFix {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 yplane NULL {hi[1]
 
 
 def random_poly_lubricated(tiles=(5, 10, 5), dmin=3.0e-4, dmax=7.0e-4, rho=2650.0, phi=0.55, dt=2.0e-6, kn=1.0e7, e=0.9, mu=0.4,
-                           visc=1.0e-3, seed=SEED, vjit=0.01, brick=None, tile_n=TILE_N):
+                           visc=1.0e-3, seed=SEED, vjit=0.01, brick=None, tile_n=TILE_N, flaglog=0):
     """configs[4]: polydisperse (d ~ U[dmin, dmax]) dense periodic packing at phi = 0.55 with hybrid/overlay
     gran/hertzFix/history + lubricate/poly (full list, cutoff 1.5 dmax).  5 x 10 x 5 tiles = 1.25e6 particles; the 1e7
     weak-scaling point is tiles = (10, 20, 10) on a 2 x 2 x 2 processor grid (brick = (grid, rank)).
     cut_inner = 1.001 dmax: the reference switches lubrication off inside cut_inner (pair_lubricate_poly.cpp:294-297) and
     takes log(1/h) of the gap outside it (:308), so every overlapping pair must lie inside cut_inner or the reference
-    itself produces NaN."""
+    itself produces NaN.  flaglog = 0 (squeeze term only): with flaglog = 1 the reference's log forms give NEGATIVE
+    resistances for gaps larger than the smaller radius (log(1/h) < 0), which a global cutoff of 1.5 dmax cannot avoid in
+    a polydisperse packing -- the reference objects themselves blow up within 40 steps on this bed (spins of 1e10 rad/s,
+    checked with oracle/_ref); the parity tests keep flaglog = 1 on a dilute packing where it is stable."""
     dm = 0.5 * (dmin + dmax)
     T = packing.tile(tile_n, phi, seed, dlo=dmin / dm, dhi=dmax / dm)
     L = T[2] * dm
@@ -440,7 +443,7 @@ def random_poly_lubricated(tiles=(5, 10, 5), dmin=3.0e-4, dmax=7.0e-4, rho=2650.
     script = f"""
 neighbor {skin:.9g} bin
 neigh_modify delay 0
-pair_style hybrid/overlay gran/hertzFix/history {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 lubricate/poly {visc:.9g} 1 1 {1.001 * dmax:.9g} {1.5 * dmax:.9g}
+pair_style hybrid/overlay gran/hertzFix/history {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 lubricate/poly {visc:.9g} {flaglog} 1 {1.001 * dmax:.9g} {1.5 * dmax:.9g}
 pair_coeff * *
 timestep {dt:.9g}
 fix 1 all nve/sphere
@@ -559,6 +562,39 @@ fix 3 all fdrag
                  extra=dict(name="settled_bed", Uf=BED_UF, g=(0.0, -9.8, 0.0), dt=dt, substeps=100, packing="settled random",
                             omega=om, columns=(gx, gz), column=column, column_meta=C["meta"],
                             fluid_force_over_weight=C["fow"]))
+
+
+def settled_cohesive_bed(columns=(5, 5), column=None, d=5.0e-5, rho=2650.0, dt=2.0e-8, kn=1.0e7, e=0.9, mu=0.4, opt=1, vshear=0.01, brick=None):
+    """configs[3]: 1e6-particle cohesive silt bed (d = 50 um) under shear -- the settled random column scaled to the silt
+    diameter, periodic in x / z, wall/granFix floor, a sheared wall/granFix lid pressing on the topmost particles,
+    fix cohesive (opt 1) on every list pair, Hertz-Mindlin pair."""
+    base = settled_bed(columns=columns, column=column, brick=brick)
+    d0 = float(base["diam"][0])
+    sc = d / d0
+    x = base["x"] * sc
+    r = 0.5 * d
+    lo = base["box_lo"] * sc
+    hi = base["box_hi"] * sc
+    C = load_column(base["column"])
+    hi[1] = C["top"] * sc + r - 1.0e-2 * d      # the lid presses on the topmost particles
+    smax = 1.0e-6
+    skin = max(0.25 * d, 2.0 * smax)
+    script = f"""
+neighbor {skin:.9g} bin
+neigh_modify delay 0
+pair_style gran/hertzFix/history {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1
+pair_coeff * *
+timestep {dt:.9g}
+fix 1 all nve/sphere
+fix 2 all gravity 9.8 vector 0 -1 0
+fix 3 all fdrag
+fix 4 all cohesive 1e-20 1e-7 4e-10 {smax:.9g} {opt}
+fix yb all wall/granFix {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 yplane {lo[1]:.17g} NULL
+fix yt all wall/granFix {kn:.9g} NULL {e:.9g} NULL {mu:.9g} 1 yplane NULL {hi[1]:.17g} shear x {vshear:.9g}
+"""
+    return _base(x, d, rho, lo, hi, ("p", "f", "p"), script, 4.0 * d, tags=base["tag"],
+                 extra=dict(name="settled_cohesive_bed", Uf=(0.05, 0.0, 0.0), g=(0.0, -9.8, 0.0), dt=dt, substeps=100,
+                            packing="settled random (scaled)", columns=base["columns"], column=base["column"], fluid_force_over_weight=0.3))
 
 
 def bench_fluid_force(case):

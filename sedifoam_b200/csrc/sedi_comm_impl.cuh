@@ -410,7 +410,7 @@ inline void Comm::borders(Engine &e) {
   CK(cudaMemsetAsync(d_gfill, 0, (size_t)(nc + 2) * sizeof(int), e.stream));
   if (total_recv)
     k_wrap_bin<<<cdiv(total_recv, T), T, 0, e.stream>>>(e.posr[e.cur].p + nl, e.omgt[e.cur].p + nl, total_recv, e.bin, 0, 0, 0, 0, 0, 0, d_gcellid, d_gcount,
-                                                        0, 0, 0, 0, 0, 0, (const int *)0, -1, 0);
+                                                        0, 0, 0, 0, 0, 0, (const int *)0, -1, 0, (int *)0);
   const int ns2 = (int)(nc + 2), nb2 = cdiv(ns2, SCAN_ITEMS);
   k_scan_local<<<nb2, 1024, 0, e.stream>>>(d_gcount, d_gstart, ns2, e.blocksum.p);
   k_scan_sums<<<1, 1024, 0, e.stream>>>(e.blocksum.p, nb2);

@@ -639,10 +639,14 @@ class Engine {
       return;
     }
     const bool pbc = P.periodic_any != 0;
-    if (use_sell && !tl && cfg().pair != PAIR_NONE) {   // sorted-row kernel: one lane per particle, rows of a warp carry equal work (sedi_sell.cuh)
+    if (use_sell && cfg().pair != PAIR_NONE) {   // sorted-row kernel: one lane per particle, rows of a warp carry equal work (sedi_sell.cuh)
       const int ST = SEDI_SELL_THREADS;
       const int sb = std::max(1, cdiv(nlocal, ST));
-#define SEDI_LAUNCH_SELL(PK) do { if (pbc) k_step_sell<PK, true><<<sb, ST, 0, stream>>>(P, seq); else k_step_sell<PK, false><<<sb, ST, 0, stream>>>(P, seq); } while (0)
+#define SEDI_LAUNCH_SELL(PK)                                                                                  \
+  do {                                                                                                        \
+    if (tl) { if (pbc) k_step_sell<PK, true, true><<<sb, ST, 0, stream>>>(P, seq); else k_step_sell<PK, false, true><<<sb, ST, 0, stream>>>(P, seq); } \
+    else { if (pbc) k_step_sell<PK, true, false><<<sb, ST, 0, stream>>>(P, seq); else k_step_sell<PK, false, false><<<sb, ST, 0, stream>>>(P, seq); } \
+  } while (0)
       switch (cfg().pair) {
         case PAIR_HERTZFIX_HISTORY: SEDI_LAUNCH_SELL(PAIR_HERTZFIX_HISTORY); break;
         case PAIR_HOOKE_HISTORY: SEDI_LAUNCH_SELL(PAIR_HOOKE_HISTORY); break;
@@ -745,7 +749,10 @@ class Engine {
       k_wrap_bin<<<cdiv(n_tmp, T), T, 0, stream>>>(posr[cur].p, omgt[cur].p, n_tmp, bin, c.boxhi[0], c.boxhi[1], c.boxhi[2], c.boxhi[0] - c.boxlo[0],
                                                    c.boxhi[1] - c.boxlo[1], c.boxhi[2] - c.boxlo[2], cellid.p, cellcount.p,
                                                    c.periodic[0], c.periodic[1], c.periodic[2], c.boxlo[0], c.boxlo[1], c.boxlo[2],
-                                                   comm.nranks > 1 ? leave.p : (const int *)0, trash, comm.nranks > 1 ? 0 : 1);
+                                                   comm.nranks > 1 ? leave.p : (const int *)0, trash, comm.nranks > 1 ? 0 : 1, ctrl.p + 2);
+      CK(cudaMemcpyAsync(h_ctrl.p + 2, ctrl.p + 2, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      if (h_ctrl.p[2] & 4) fatal("Out of range atoms: a particle moved more than a box length (or became NaN) since the last neighbour rebuild -- the run is unstable");
     }
     const int nscan = (int)(nc + 2);
     const int nblk = cdiv(nscan, SCAN_ITEMS);
@@ -771,7 +778,8 @@ class Engine {
       order2.ensure(npad); crow.ensure(npad);
       Ell &Lprev = ell[ecur];
       k_window_sort<<<cdiv(nlocal_new, SELL_WINDOW), SELL_WINDOW, 0, stream>>>(nlocal_new, order.p, Lprev.valid ? Lprev.tmask.p : (const unsigned long long *)0,
-                                                                               Lprev.valid ? Lprev.nn.p : (const int *)0, nlocal, order2.p, crow.p);
+                                                                               Lprev.valid ? Lprev.nn.p : (const int *)0,
+                                                                               (Lprev.valid && want_type_list()) ? Lprev.nt.p : (const int *)0, nlocal, order2.p, crow.p);
       launches++;
       ord = order2.p;
     }

@@ -62,7 +62,7 @@ __device__ __forceinline__ int bin_coord(double x, double lo, double inv, int nb
 // B describes the bins (which cover the local sub-domain plus its ghost shell on a multi-GPU run).
 __global__ void k_wrap_bin(D4 *posr, const D4 *omgt, int n, BinParams B, double hi0, double hi1, double hi2, double prd0,
                            double prd1, double prd2, int *cellid, int *cellcount, int per0, int per1, int per2, double blo0,
-                           double blo1, double blo2, const int *leave, int trash_cell, int do_wrap) {
+                           double blo1, double blo2, const int *leave, int trash_cell, int do_wrap, int *err) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   D4 p = posr[i];
@@ -79,6 +79,10 @@ __global__ void k_wrap_bin(D4 *posr, const D4 *omgt, int n, BinParams B, double 
     if (per1) { if (p.y < blo1) { p.y += prd1; ch = true; } if (p.y >= hi1) { p.y -= prd1; p.y = fmax(p.y, blo1); ch = true; } }
     if (per2) { if (p.z < blo2) { p.z += prd2; ch = true; } if (p.z >= hi2) { p.z -= prd2; p.z = fmax(p.z, blo2); ch = true; } }
     if (ch) posr[i] = p;
+    // still outside a periodic box after one wrap, or not a number: the particle moved more than a box length since the last
+    // rebuild -- the run has blown up (LAMMPS: "Out of range atoms - cannot compute").  Reported, not binned into one cell.
+    if (err && ((per0 && !(p.x >= blo0 && p.x < hi0)) || (per1 && !(p.y >= blo1 && p.y < hi1)) || (per2 && !(p.z >= blo2 && p.z < hi2)) ||
+                !(p.x == p.x) || !(p.y == p.y) || !(p.z == p.z))) atomicOr(err, 4);
   }
   const int cx = bin_coord(p.x, B.lo[0], B.inv[0], B.nb[0]);
   const int cy = bin_coord(p.y, B.lo[1], B.inv[1], B.nb[1]);

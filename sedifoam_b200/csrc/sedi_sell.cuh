@@ -37,6 +37,12 @@ namespace sedi {
 #ifndef SEDI_SELL_PF
 #define SEDI_SELL_PF 1     // prefetch the next overlapping entry's partner lines / history quad to L1
 #endif
+#ifndef SEDI_SELL_DB
+#define SEDI_SELL_DB 1     // 1: operands of the next overlapping entry are gathered into registers while this one is evaluated (needs ~30 more registers)
+#endif
+#ifndef SEDI_SELL_PFH
+#define SEDI_SELL_PFH 1    // 1: the history quads of all slots that overlapped one sub-step ago are requested (L2) at the top of the kernel
+#endif
 static const int SELL_WINDOW = 512;   // sigma of SELL-C-sigma: rows are sorted by work inside windows of this many rows
 
 // ---- row ordering: stable sort of every window of bin-ordered rows by the work the row had under the previous list ----
@@ -44,7 +50,7 @@ static const int SELL_WINDOW = 512;   // sigma of SELL-C-sigma: rows are sorted 
 // order2[r] : physical new row r -> old row                             (what the permutation kernels and the history re-attachment use)
 // crow[k]   : canonical position k -> physical new row                  (how the list build reaches the rows of a bin)
 __global__ void __launch_bounds__(SELL_WINDOW) k_window_sort(int n, const int *order, const unsigned long long *tmask_old, const int *nn_old,
-                                                             int nrows_old, int *order2, int *crow) {
+                                                             const int *nt_old, int nrows_old, int *order2, int *crow) {
   __shared__ unsigned s[SELL_WINDOW];
   const int t = threadIdx.x;
   const int k = blockIdx.x * SELL_WINDOW + t;
@@ -53,8 +59,14 @@ __global__ void __launch_bounds__(SELL_WINDOW) k_window_sort(int n, const int *o
     const int o = order[k];
     unsigned key = 0u;
     if (tmask_old && o < nrows_old) {
-      const unsigned a = (unsigned)__popcll(tmask_old[o]), b = (unsigned)nn_old[o];
-      key = (a < 63u ? a : 63u) * 64u + (b < 63u ? b : 63u);
+      const unsigned a = (unsigned)__popcll(tmask_old[o]);
+      if (nt_old) {   // type-cut-off list in use (fix cohesive / lubricate/poly): the row length dominates the work
+        const unsigned b = ((unsigned)nn_old[o] + (unsigned)nt_old[o]) >> 1;
+        key = (b < 63u ? b : 63u) * 64u + (a < 63u ? a : 63u);
+      } else {
+        const unsigned b = (unsigned)nn_old[o];
+        key = (a < 63u ? a : 63u) * 64u + (b < 63u ? b : 63u);
+      }
     }
     comp = ((4095u - key) << 10) | (unsigned)t;   // heavy rows first; ties keep the bin order (the composite is unique)
   }
@@ -80,8 +92,10 @@ __global__ void __launch_bounds__(SELL_WINDOW) k_window_sort(int n, const int *o
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------------------------
-template <int PAIR, bool PBC>
-__global__ void __launch_bounds__(SEDI_SELL_THREADS, SEDI_SELL_MINB) k_step_sell(const __grid_constant__ StepParams P, const int seq) {
+// TYPELIST compiles the work of the type-cut-off list in (fix cohesive, pair lubricate/poly): a third walk over the row
+// (both segments), see below; the plain granular instantiation carries none of it.
+template <int PAIR, bool PBC, bool TYPELIST>
+__global__ void __launch_bounds__(SEDI_SELL_THREADS, TYPELIST ? 6 : SEDI_SELL_MINB) k_step_sell(const __grid_constant__ StepParams P, const int seq) {
   constexpr bool HIST = (PAIR == PAIR_HERTZFIX_HISTORY || PAIR == PAIR_HOOKE_HISTORY);
   if (P.mode != MODE_SETUP) {
     const int fl = *(volatile int *)&P.ctrl[0];
@@ -98,6 +112,7 @@ __global__ void __launch_bounds__(SEDI_SELL_THREADS, SEDI_SELL_MINB) k_step_sell
   D4 vi = ldg_d4_stream(&P.velm_in[i]);
   D4 wi = ldg_d4_stream(&P.omgt_in[i]);
   const int nni = ld_nc_s32(&P.nn[i]);
+  const int nti = TYPELIST ? ld_nc_s32(&P.nt[i]) : 0;
   const unsigned long long tm_old = HIST ? P.tmask[i] : 0ull;
   unsigned e16[16];
 #pragma unroll
@@ -110,6 +125,9 @@ __global__ void __launch_bounds__(SEDI_SELL_THREADS, SEDI_SELL_MINB) k_step_sell
     if (P.mode == MODE_FUSED) { prefetch_l1(&P.xhold[0][i]); prefetch_l1(&P.xhold[1][i]); prefetch_l1(&P.xhold[2][i]); }
   }
   if ((tid & 7) == 0 && P.wmask) prefetch_l1(&P.wmask[i]);
+#if SEDI_SELL_PFH
+  if (HIST) for (unsigned long long hm = tm_old; hm; hm &= hm - 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.shear[(size_t)(__ffsll((long long)hm) - 1) * P.npad + i]));
+#endif
   if (bits_flags((unsigned long long)__double_as_longlong(wi.w)) & PFLAG_GHOST) return;  // ghost rows are refreshed by the halo exchange
   const double radi = pi.w, mi = vi.w;
   const int maski = bits_mask((unsigned long long)__double_as_longlong(wi.w));
@@ -158,45 +176,35 @@ __global__ void __launch_bounds__(SEDI_SELL_THREADS, SEDI_SELL_MINB) k_step_sell
   HzCoef hc; hc.c_sn = P.c_sn; hc.c_ccel = P.c_ccel; hc.c_damp = P.c_damp; hc.c_kts = P.c_kts; hc.c_ctd = P.c_ctd; hc.c_ekt = P.c_ekt; hc.xmu = P.xmu;
   GranCoef gc; gc.kn = P.kn; gc.kt = P.kt; gc.gamman = P.gamman; gc.gammat = P.gammat; gc.xmu = P.xmu; gc.beta = P.beta;
   double fx = 0.0, fy = 0.0, fz = 0.0, tx = 0.0, ty = 0.0, tz = 0.0;   // pair accumulators (force_clear)
-  unsigned long long m = touch;
-  int s = 0;
-  unsigned e = 0u;
   auto list_word = [&](const int sl) -> unsigned { return sl < 16 ? s_e[sl][tid] : ld_nc_u32(&P.nbr[(size_t)sl * P.npad + i]); };
-  if (m) { s = __ffsll((long long)m) - 1; e = list_word(s); }
-  while (m) {
-    m &= m - 1;
-    int sn = 0;
-    unsigned en = 0u;
-    if (m) { sn = __ffsll((long long)m) - 1; en = list_word(sn); }
-    const size_t slot = (size_t)s * P.npad + i;
-    const int j = (int)(e & NB_IDX_MASK);
-    D4 pj = ldg_d4(&P.posr_in[j]);
-    const D4 vj = ldg_d4(&P.velm_in[j]);
-    const D4 wj = ldg_d4(&P.omgt_in[j]);
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    if (HIST && ((tm_old >> s) & 1ull)) { const D4 h = ld_d4(&P.shear[slot]); s0 = h.x; s1 = h.y; s2 = h.z; }
-#if SEDI_SELL_PF
-    if (m) {   // the next contact's lines start towards L1 while this one is evaluated
-      const int jn = (int)(en & NB_IDX_MASK);
-      prefetch_l1(&P.posr_in[jn]); prefetch_l1(&P.velm_in[jn]); prefetch_l1(&P.omgt_in[jn]);
-      if (HIST && ((tm_old >> sn) & 1ull)) prefetch_l1(&P.shear[(size_t)sn * P.npad + i]);
-    }
-#endif
-    const int img = (int)((e >> NB_IMG_SHIFT) & 31u);
+  // gathers of one overlapping entry: partner position / velocity / spin and the history quad of the slot
+  struct Opnd { D4 pj, vj, wj; double h0, h1, h2; };
+  auto gather = [&](const unsigned ew, const int sl, Opnd &o) {
+    const int j = (int)(ew & NB_IDX_MASK);
+    o.pj = ldg_d4(&P.posr_in[j]);
+    o.vj = ldg_d4(&P.velm_in[j]);
+    o.wj = ldg_d4(&P.omgt_in[j]);
+    o.h0 = o.h1 = o.h2 = 0.0;
+    if (HIST && ((tm_old >> sl) & 1ull)) { const D4 h = ld_d4(&P.shear[(size_t)sl * P.npad + i]); o.h0 = h.x; o.h1 = h.y; o.h2 = h.z; }
+  };
+  // contact law, history write-back, accumulation for one overlapping entry whose operands have been gathered
+  auto evaluate = [&](const unsigned ew, const int sl, const Opnd &o) {
+    D4 pj = o.pj;
+    const int img = (int)((ew >> NB_IMG_SHIFT) & 31u);
     if (PBC && img != NB_IMG_NONE) {
       pj.x = pj.x + P.imgshift[img][0]; pj.y = pj.y + P.imgshift[img][1]; pj.z = pj.z + P.imgshift[img][2];
     }
     const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
     const double rsq = delx * delx + dely * dely + delz * delz;
-    const double radj = pj.w, mj = vj.w;
+    const double radj = pj.w, mj = o.vj.w;
     const double radsum = radi + radj;
-    const int maskj = bits_mask((unsigned long long)__double_as_longlong(wj.w));
+    const int maskj = bits_mask((unsigned long long)__double_as_longlong(o.wj.w));
     double meff = (PAIR == PAIR_HERTZFIX_HISTORY) ? div_nr(mi * mj, mi + mj) : (mi * mj) / (mi + mj);
     if (maski & P.freeze_groupbit) meff = mj;
     if (maskj & P.freeze_groupbit) meff = mi;
-    const double vrx = vi.x - vj.x, vry = vi.y - vj.y, vrz = vi.z - vj.z;
-    const double wsx = radi * wi.x + radj * wj.x, wsy = radi * wi.y + radj * wj.y, wsz = radi * wi.z + radj * wj.z;
-    double fox, foy, foz, tox, toy, toz;
+    const double vrx = vi.x - o.vj.x, vry = vi.y - o.vj.y, vrz = vi.z - o.vj.z;
+    const double wsx = radi * wi.x + radj * o.wj.x, wsy = radi * wi.y + radj * o.wj.y, wsz = radi * wi.z + radj * o.wj.z;
+    double s0 = o.h0, s1 = o.h1, s2 = o.h2, fox, foy, foz, tox, toy, toz;
     if (PAIR == PAIR_HERTZFIX_HISTORY) {
       hertzfix_fast(delx, dely, delz, rsq, vrx, vry, vrz, wsx, wsy, wsz, meff, radsum, div_nr(radi * radj, radsum), hc, P.dtv, shearupdate,
                     s0, s1, s2, fox, foy, foz, tox, toy, toz);
@@ -206,17 +214,106 @@ __global__ void __launch_bounds__(SEDI_SELL_THREADS, SEDI_SELL_MINB) k_step_sell
       else hooke_contact(delx, dely, delz, rsq, vr, ws, meff, radsum, gc, fo, to);
       s0 = sh.x; s1 = sh.y; s2 = sh.z; fox = fo.x; foy = fo.y; foz = fo.z; tox = to.x; toy = to.y; toz = to.z;
     }
-    if (HIST) { D4 h; h.x = s0; h.y = s1; h.z = s2; h.w = 0.0; st_d4(&P.shear[slot], h); }
+    if (HIST) { D4 h; h.x = s0; h.y = s1; h.z = s2; h.w = 0.0; st_d4(&P.shear[(size_t)sl * P.npad + i], h); }
     // reference: f[i] += F ; torque[i] -= radi * tor   (pair :259-271)
     fx += fox; fy += foy; fz += foz;
     tx -= radi * tox; ty -= radi * toy; tz -= radi * toz;
+  };
+  unsigned long long m = touch;
+#if SEDI_SELL_DB
+  // register double buffer: the operands of the next overlapping entry are gathered while this one is evaluated
+  if (m) {
+    int s = __ffsll((long long)m) - 1;
+    unsigned e = list_word(s);
+    Opnd cur;
+    gather(e, s, cur);
+    while (true) {
+      m &= m - 1;
+      if (!m) { evaluate(e, s, cur); break; }
+      const int sn = __ffsll((long long)m) - 1;
+      const unsigned en = list_word(sn);
+      Opnd nxt;
+      gather(en, sn, nxt);
+      evaluate(e, s, cur);
+      cur = nxt; s = sn; e = en;
+    }
+  }
+#else
+  int s = 0;
+  unsigned e = 0u;
+  if (m) { s = __ffsll((long long)m) - 1; e = list_word(s); }
+  while (m) {
+    m &= m - 1;
+    int sn = 0;
+    unsigned en = 0u;
+    if (m) { sn = __ffsll((long long)m) - 1; en = list_word(sn); }
+    Opnd cur;
+    gather(e, s, cur);
+#if SEDI_SELL_PF
+    if (m) {   // the next contact's lines start towards L1 while this one is evaluated
+      const int jn = (int)(en & NB_IDX_MASK);
+      prefetch_l1(&P.posr_in[jn]); prefetch_l1(&P.velm_in[jn]); prefetch_l1(&P.omgt_in[jn]);
+      if (HIST && ((tm_old >> sn) & 1ull)) prefetch_l1(&P.shear[(size_t)sn * P.npad + i]);
+    }
+#endif
+    evaluate(e, s, cur);
     s = sn; e = en;
   }
+#endif
   if (HIST && touch != tm_old) P.tmask[i] = touch;
+
+  // ---- phase T (TYPELIST): fix cohesive / pair lubricate/poly over the entries of the type-cut-off list -- the granular segment
+  // [0, nni) and the type-only segment [hcap, hcap + nti) --, four partner positions in flight at a time.  Rows of a warp have
+  // (nearly) the same length, so the per-lane walk keeps the lanes busy.
+  double lfx = 0.0, lfy = 0.0, lfz = 0.0, ltx = 0.0, lty = 0.0, ltz = 0.0;  // lubricate/poly
+  double cfx = 0.0, cfy = 0.0, cfz = 0.0;                               // fix cohesive
+  if (TYPELIST) {
+    const CoheCoef co = cohesive_coef<TYPELIST>(P);
+    const int tagi = bits_tag((unsigned long long)__double_as_longlong(wi.w));
+    const int ntot = nni + nti;
+    for (int sb = 0; sb < ntot; sb += 4) {
+      unsigned e4[4];
+      D4 p4[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int q = sb + k;
+        e4[k] = (q < ntot) ? (q < nni ? list_word(q) : ld_nc_u32(&P.nbr[(size_t)(P.hcap + (q - nni)) * P.npad + i])) : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) p4[k] = ldg_d4(&P.posr_in[e4[k] & NB_IDX_MASK]);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const unsigned ew = e4[k];
+        if (!(ew & NB_FLAG_TYPE)) continue;
+        D4 pj = p4[k];
+        const int img = (int)((ew >> NB_IMG_SHIFT) & 31u);
+        if (PBC && img != NB_IMG_NONE) {
+          pj.x = pj.x + P.imgshift[img][0]; pj.y = pj.y + P.imgshift[img][1]; pj.z = pj.z + P.imgshift[img][2];
+        }
+        const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
+        const double rsq = delx * delx + dely * dely + delz * delz;
+        const double radj = pj.w;
+        const double radsum = radi + radj;
+        const int j = (int)(ew & NB_IDX_MASK);
+        if (P.has_cohesive) cohesive_entry(P, co, j, img, tagi, maski, radsum, rsq, delx, dely, delz, cfx, cfy, cfz);
+        if (P.lub_enabled && P.lub_flagHI && rsq < P.lub_cutsq) lubricate_entry(P, j, pi, vi, wi, radj, rsq, delx, dely, delz, lfx, lfy, lfz, ltx, lty, ltz);
+      }
+    }
+    if (P.lub_enabled) {  // isotropic FLD terms (:213-221) are applied before the pair terms in the reference
+      double ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
+      if (P.lub_flagfld) {
+        ax -= P.lub_R0 * radi * vi.x; ay -= P.lub_R0 * radi * vi.y; az -= P.lub_R0 * radi * vi.z;
+        const double radi3 = radi * radi * radi;
+        bx -= P.lub_RT0 * radi3 * wi.x; by -= P.lub_RT0 * radi3 * wi.y; bz -= P.lub_RT0 * radi3 * wi.z;
+      }
+      fx += ax + lfx; fy += ay + lfy; fz += az + lfz;
+      tx += bx + ltx; ty += by + lty; tz += bz + ltz;
+    }
+  }
   double fd0 = 0.0, fd1 = 0.0, fd2 = 0.0, xh0 = 0.0, xh1 = 0.0, xh2 = 0.0;
   if (P.has_fdrag) { fd0 = ld_nc_f64(&P.fdrag[0][i]); fd1 = ld_nc_f64(&P.fdrag[1][i]); fd2 = ld_nc_f64(&P.fdrag[2][i]); }
   if (P.mode == MODE_FUSED) { xh0 = ld_nc_f64(&P.xhold[0][i]); xh1 = ld_nc_f64(&P.xhold[1][i]); xh2 = ld_nc_f64(&P.xhold[2][i]); }
-  step_epilogue<PAIR, false>(P, i, seq, pi, vi, wi, fx, fy, fz, tx, ty, tz, 0.0, 0.0, 0.0, fd0, fd1, fd2, xh0, xh1, xh2, touch);
+  step_epilogue<PAIR, TYPELIST>(P, i, seq, pi, vi, wi, fx, fy, fz, tx, ty, tz, cfx, cfy, cfz, fd0, fd1, fd2, xh0, xh1, xh2, touch);
 }
 
 }  // namespace sedi
