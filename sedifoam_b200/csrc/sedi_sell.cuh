@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(SEDI_SELL_THREADS, TYPELIST ? 6 : SEDI_SELL_MI
     const CoheCoef co = cohesive_coef<TYPELIST>(P);
     const int tagi = bits_tag((unsigned long long)__double_as_longlong(wi.w));
     const int ntot = nni + nti;
+    const double inv_radi = 1.0 / radi;
     for (int sb = 0; sb < ntot; sb += 4) {
       unsigned e4[4];
       D4 p4[4];
@@ -295,8 +296,8 @@ __global__ void __launch_bounds__(SEDI_SELL_THREADS, TYPELIST ? 6 : SEDI_SELL_MI
         const double radj = pj.w;
         const double radsum = radi + radj;
         const int j = (int)(ew & NB_IDX_MASK);
-        if (P.has_cohesive) cohesive_entry(P, co, j, img, tagi, maski, radsum, rsq, delx, dely, delz, cfx, cfy, cfz);
-        if (P.lub_enabled && P.lub_flagHI && rsq < P.lub_cutsq) lubricate_entry(P, j, pi, vi, wi, radj, rsq, delx, dely, delz, lfx, lfy, lfz, ltx, lty, ltz);
+        if (P.has_cohesive) cohesive_entry_fast(P, co, j, img, tagi, maski, radsum, rsq, delx, dely, delz, cfx, cfy, cfz);
+        if (P.lub_enabled && P.lub_flagHI && rsq < P.lub_cutsq) lubricate_entry_fast(P, j, pi, vi, wi, inv_radi, radj, rsq, delx, dely, delz, lfx, lfy, lfz, ltx, lty, ltz);
       }
     }
     if (P.lub_enabled) {  // isotropic FLD terms (:213-221) are applied before the pair terms in the reference
