@@ -73,11 +73,6 @@ struct StepParams {
   const unsigned *nbr;
   D4 *shear;                  // [slot * npad + i], .w unused
   unsigned long long *tmask;  // touching-slot mask per particle
-  // row-contiguous form of the list (k_step_rows): entries of row i are [off[i], off[i+1]), in ELL slot order
-  const int *off;
-  const unsigned *cnbr;        // list words, same encoding as nbr
-  const unsigned char *crow;   // owner row & 255 of every entry
-  double *hx, *hy, *hz;        // contact history planes, one value per directed entry
   double *f[3], *tq[3];       // stored force/torque (written by SETUP/LAST, read by the initial-integrate kernel)
   double *fdrag[3], *dudt[3], *vold[3];
   double *xhold[3];

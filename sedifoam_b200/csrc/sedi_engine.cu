@@ -31,7 +31,6 @@
 #include "sedi_device.cuh"
 #include "sedi_neigh.cuh"
 #include "sedi_step.cuh"
-#include "sedi_rows.cuh"
 #include "sedi_wq.cuh"
 #include "sedi_sell.cuh"
 #include "sedi_couple.cuh"
@@ -107,15 +106,7 @@ struct Ell {  // directed neighbour list + contact history, slot-major
   Buf<D4> shear;
   int npad, cap, tcap;    // cap: granular slots (<= 64, each with a history quad); tcap: type-only slots
   bool valid;
-  // row-contiguous form of the same list (k_step_rows): offsets, list words, owner-row byte, history planes
-  Buf<int> off;
-  Buf<unsigned> cnbr;
-  Buf<unsigned char> crow;
-  Buf<double> hx, hy, hz;
-  long long nentries;
-  bool rows_valid;     // the row form exists
-  bool hist_in_rows;   // the live contact history is in hx/hy/hz (the ELL quads are stale)
-  Ell() : npad(0), cap(0), tcap(0), valid(false), nentries(0), rows_valid(false), hist_in_rows(false) {}
+  Ell() : npad(0), cap(0), tcap(0), valid(false) {}
 };
 
 // small pack / unpack kernels of the C-ABI boundary -------------------------------------------------------
@@ -229,7 +220,6 @@ class Engine {
   long long pair_evals_unique;
   long long nbuilds, pair_evals, steps_done, launches, list_gran_dir, list_type_dir, list_gran_img, list_type_img;
   int chunk;
-  bool use_rows;   // pair sweep on the row-block kernel (SEDI_KSTEP_PATH=rows)
   bool warned_neigh;
   bool use_wq;     // pair sweep on the warp-queue kernel (SEDI_KSTEP_PATH=wq)
   bool use_sell;   // pair sweep on the sorted-row kernel (default); SEDI_KSTEP_PATH=ell selects the streamed slot walk
@@ -287,12 +277,10 @@ class Engine {
     graph_on = true;
     e = getenv("SEDI_GRAPH");
     if (e && atoi(e) == 0) graph_on = false;
-    use_rows = false;
     e = getenv("SEDI_KSTEP_PATH");
-    if (e && !strcmp(e, "rows")) use_rows = true;
     warned_neigh = false;
     use_wq = (e && !strcmp(e, "wq"));
-    use_sell = !(e && (!strcmp(e, "rows") || !strcmp(e, "ell") || !strcmp(e, "wq")));
+    use_sell = !(e && (!strcmp(e, "ell") || !strcmp(e, "wq")));
     sell_sort = use_sell;
     if (const char *ss = getenv("SEDI_SELL_SORT")) sell_sort = atoi(ss) != 0;
     e = getenv("SEDI_DEVICE");
@@ -310,7 +298,7 @@ class Engine {
     // device memory is released with the process; explicit frees keep long-lived hosts clean
     for (int k = 0; k < 2; k++) { posr[k].release(); velm[k].release(); omgt[k].release(); wmask[k].release(); foam[k].release();
       ell[k].nbr.release(); ell[k].nn.release(); ell[k].nt.release(); ell[k].tmask.release(); ell[k].shear.release();
-      ell[k].off.release(); ell[k].cnbr.release(); ell[k].crow.release(); ell[k].hx.release(); ell[k].hy.release(); ell[k].hz.release(); }
+    }
     Plane2 *groups[] = {f, tq, fdrag, dudt, vold, uold, xhold};
     for (size_t g = 0; g < sizeof(groups) / sizeof(groups[0]); g++) for (int d = 0; d < 3; d++) { groups[g][d].b[0].release(); groups[g][d].b[1].release(); }
     for (int w = 0; w < MAX_WALLS; w++) for (int d = 0; d < 3; d++) { wshear[w][d].b[0].release(); wshear[w][d].b[1].release(); }
@@ -438,7 +426,7 @@ class Engine {
     cur = 0; icur = 0; ecur = 0;
     drop_graphs();
     hist_alloc = false;   // history-force state restarts with the atom table (softParticle.C:63-64: n0 = 0, sumDeltaFb = 0)
-    ell[0].valid = ell[1].valid = false; ell[0].rows_valid = ell[1].rows_valid = false; ell[0].hist_in_rows = ell[1].hist_in_rows = false;
+    ell[0].valid = ell[1].valid = false;
     if (n) {
       CK(cudaMemcpyAsync(posr[0].p, hp.data(), n * sizeof(D4), cudaMemcpyHostToDevice, stream));
       CK(cudaMemcpyAsync(velm[0].p, hv.data(), n * sizeof(D4), cudaMemcpyHostToDevice, stream));
@@ -596,7 +584,6 @@ class Engine {
     P.n = nlocal;
     Ell &L = ell[ecur];
     P.npad = L.npad; P.nn = L.nn.p; P.nt = L.nt.p; P.hcap = L.cap; P.nbr = L.nbr.p; P.shear = L.shear.p; P.tmask = L.tmask.p;
-    P.off = L.off.p; P.cnbr = L.cnbr.p; P.crow = L.crow.p; P.hx = L.hx.p; P.hy = L.hy.p; P.hz = L.hz.p;
     P.posr_in = posr[in].p; P.velm_in = velm[in].p; P.omgt_in = omgt[in].p;
     P.posr_out = posr[in ^ 1].p; P.velm_out = velm[in ^ 1].p; P.omgt_out = omgt[in ^ 1].p;
     for (int d = 0; d < 3; d++) {
@@ -626,18 +613,6 @@ class Engine {
     const int KT = SEDI_KSTEP_THREADS;
     const int blocks = std::max(1, cdiv(nlocal, KT));   // an empty brick still counts its sub-steps (ctrl[1])
     const bool tl = P.has_cohesive || P.lub_enabled;
-    if (ell[ecur].rows_valid && !tl && cfg().pair != PAIR_NONE) {   // row-block kernel: one directed entry per thread
-      const int RT = SEDI_ROWS_THREADS;
-      const int rb = std::max(1, cdiv(nlocal, RT));
-      ell[ecur].hist_in_rows = true;   // from here on the live history is in the planes
-      switch (cfg().pair) {
-        case PAIR_HERTZFIX_HISTORY: k_step_rows<PAIR_HERTZFIX_HISTORY><<<rb, RT, 0, stream>>>(P, seq); break;
-        case PAIR_HOOKE_HISTORY: k_step_rows<PAIR_HOOKE_HISTORY><<<rb, RT, 0, stream>>>(P, seq); break;
-        default: k_step_rows<PAIR_HOOKE><<<rb, RT, 0, stream>>>(P, seq); break;
-      }
-      launches++;
-      return;
-    }
     const bool pbc = P.periodic_any != 0;
     if (use_sell && cfg().pair != PAIR_NONE) {   // sorted-row kernel: one lane per particle, rows of a warp carry equal work (sedi_sell.cuh)
       const int ST = SEDI_SELL_THREADS;
@@ -694,47 +669,9 @@ class Engine {
   }
 
   // ---- neighbour rebuild (EXTERNAL Verlet: pre_exchange history save, pbc, exchange, borders, Neighbor::build) ---
-  // bring the contact history back into the ELL quads (re-attachment at the next rebuild, migration packing and
-  // sedi_get_pairs read it there)
-  void rows_history_to_ell() {
-    Ell &L = ell[ecur];
-    if (!L.valid || !L.rows_valid || !L.hist_in_rows) return;
-    if (nlocal && L.nentries)
-      k_rows_history_to_ell<<<cdiv(nlocal, 128), 128, 0, stream>>>(nlocal, L.npad, L.nn.p, L.off.p, L.tmask.p, L.hx.p, L.hy.p, L.hz.p, L.shear.p);
-    launches++;
-    L.hist_in_rows = false;
-  }
-
-  // compact the fresh ELL list (and the history re-attached to it) into the row-contiguous form
-  void build_rows(Ell &L) {
-    L.rows_valid = false; L.hist_in_rows = false; L.nentries = 0;
-    const SimConfig &c = cfg();
-    if (!use_rows || c.pair == PAIR_NONE || want_type_list()) return;
-    const int T = 256;
-    const int nscan = nlocal + 1;
-    L.off.ensure((size_t)nscan + 1);
-    CK(cudaMemsetAsync(L.nn.p + nlocal, 0, sizeof(int), stream));   // nn has npad_ell + 1 slots
-    const int nblk = cdiv(nscan, SCAN_ITEMS);
-    blocksum.ensure((size_t)nblk + 1);
-    k_scan_local<<<nblk, 1024, 0, stream>>>(L.nn.p, L.off.p, nscan, blocksum.p);
-    k_scan_sums<<<1, 1024, 0, stream>>>(blocksum.p, nblk);
-    k_scan_add<<<cdiv(nscan, T), T, 0, stream>>>(L.off.p, nscan, blocksum.p, 0);
-    CK(cudaMemcpyAsync(h_ctrl.p + 5, L.off.p + nlocal, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
-    L.nentries = h_ctrl.p[5];
-    const size_t cap_e = (size_t)L.nentries + 256;
-    L.cnbr.ensure(cap_e); L.crow.ensure(cap_e); L.hx.ensure(cap_e); L.hy.ensure(cap_e); L.hz.ensure(cap_e);
-    if (nlocal)
-      k_rows_fill<<<cdiv(nlocal, 128), 128, 0, stream>>>(nlocal, L.npad, L.nn.p, L.off.p, L.nbr.p, L.shear.p, L.tmask.p, L.cnbr.p, L.crow.p,
-                                                         L.hx.p, L.hy.p, L.hz.p);
-    launches += 4;
-    L.rows_valid = true;
-  }
-
   void rebuild(bool count = true) {
     need_device();
     drop_graphs();
-    rows_history_to_ell();
     const SimConfig &c = cfg();
     const int T = 256;
     const int n_old = nlocal + nghost;  // rows that are valid in quads[cur] (ghost rows are dropped by the sort)
@@ -865,8 +802,7 @@ class Engine {
     }
     list_gran_dir = (long long)h_counters.p[0]; list_type_dir = (long long)h_counters.p[1];
     list_gran_img = (long long)h_counters.p[2]; list_type_img = (long long)h_counters.p[3];
-    Ln.valid = true; Lo.valid = false; Lo.rows_valid = false; Lo.hist_in_rows = false;
-    build_rows(Ln);
+    Ln.valid = true; Lo.valid = false;
     ecur ^= 1;
     if (count) nbuilds++;
     cell_valid = false;
@@ -1203,7 +1139,6 @@ class Engine {
   long long get_pairs(int *ti, int *tj, unsigned *meta, int *touch, double *shear, long long capacity) {
     if (!setup_done) setup();
     need_device();
-    rows_history_to_ell();
     Ell &L = ell[ecur];
     const int n = nlocal;
     std::vector<int> hn(n), ht(n), rs(n + 1, 0);
