@@ -268,14 +268,15 @@ inline int Comm::migrate(Engine &e) {
   const int NL = dev.nlinks;
   if (nl) k_pbc_wrap<<<cdiv(nl, T), T, 0, e.stream>>>(e.posr[e.cur].p, e.omgt[e.cur].p, nl, c.periodic[0], c.periodic[1], c.periodic[2],
                                                       c.boxlo[0], c.boxlo[1], c.boxlo[2], c.boxhi[0], c.boxhi[1], c.boxhi[2]);
-  migrec = 24 + 3 * c.nwalls + 2 + 4 * MIG_MAXH;
+  const int npl = e.hist_alloc ? 16 : 12;   // the history-force state (enhancedCloud.C:197-234) migrates with its particle
+  migrec = 12 + npl + 3 * c.nwalls + 2 + 4 * MIG_MAXH;
   const int want_cap = std::max(2048, nl / 40);
   if ((size_t)want_cap * MAX_LINKS > cap_mig) {
     if (d_migrows) { CK(cudaFree(d_migrows)); CK(cudaFree(d_migsend)); CK(cudaFree(d_migrecv)); }
     cap_mig = (size_t)want_cap * MAX_LINKS; migcap = want_cap;
     CK(cudaMalloc((void **)&d_migrows, cap_mig * sizeof(int)));
-    CK(cudaMalloc((void **)&d_migsend, cap_mig * (size_t)(24 + 3 * MAX_WALLS + 2 + 4 * MIG_MAXH) * sizeof(double)));
-    CK(cudaMalloc((void **)&d_migrecv, cap_mig * (size_t)(24 + 3 * MAX_WALLS + 2 + 4 * MIG_MAXH) * sizeof(double)));
+    CK(cudaMalloc((void **)&d_migsend, cap_mig * (size_t)(28 + 3 * MAX_WALLS + 2 + 4 * MIG_MAXH) * sizeof(double)));
+    CK(cudaMalloc((void **)&d_migrecv, cap_mig * (size_t)(28 + 3 * MAX_WALLS + 2 + 4 * MIG_MAXH) * sizeof(double)));
   }
   int *d_cnt = d_small, *d_rcnt = d_small + 32, *d_err = d_small + 64;
   CK(cudaMemsetAsync(d_small, 0, 96 * sizeof(int), e.stream));
@@ -302,10 +303,11 @@ inline int Comm::migrate(Engine &e) {
   Ell &Lo = e.ell[e.ecur];
   MigPlanes M;
   memset(&M, 0, sizeof(M));
-  M.nwalls = c.nwalls; M.npad = Lo.npad; M.rec = migrec;
+  M.nwalls = c.nwalls; M.npad = Lo.npad; M.rec = migrec; M.npl = npl;
   M.posr = e.posr[e.cur].p; M.velm = e.velm[e.cur].p; M.omgt = e.omgt[e.cur].p;
   Plane2 *groups[] = {e.fdrag, e.dudt, e.vold, e.uold};
   for (int g = 0; g < 4; g++) for (int d = 0; d < 3; d++) M.pl[3 * g + d] = groups[g][d].get();
+  if (e.hist_alloc) for (int d = 0; d < 4; d++) M.pl[12 + d] = e.hist[d].get();
   for (int w = 0; w < c.nwalls; w++) for (int d = 0; d < 3; d++) M.ws[3 * w + d] = e.wshear[w][d].get();
   M.foam = e.foam[e.icur].p; M.wmask = e.wmask[e.icur].p;
   if (Lo.valid) { M.nn = Lo.nn.p; M.nbr = Lo.nbr.p; M.tmask = Lo.tmask.p; M.shear = Lo.shear.p; }
@@ -331,9 +333,10 @@ inline int Comm::migrate(Engine &e) {
     }
     MigDst Dd;
     memset(&Dd, 0, sizeof(Dd));
-    Dd.nwalls = c.nwalls; Dd.rec = migrec;
+    Dd.nwalls = c.nwalls; Dd.rec = migrec; Dd.npl = npl;
     Dd.posr = e.posr[e.cur].p; Dd.velm = e.velm[e.cur].p; Dd.omgt = e.omgt[e.cur].p;
     for (int g = 0; g < 4; g++) for (int d = 0; d < 3; d++) Dd.pl[3 * g + d] = groups[g][d].get();
+    if (e.hist_alloc) for (int d = 0; d < 4; d++) Dd.pl[12 + d] = e.hist[d].get();
     for (int w = 0; w < c.nwalls; w++) for (int d = 0; d < 3; d++) Dd.ws[3 * w + d] = e.wshear[w][d].get();
     Dd.foam = e.foam[e.icur].p; Dd.wmask = e.wmask[e.icur].p; Dd.leave = e.leave.p;
     Dd.arr_nh = d_arr_nh; Dd.arr_tag = d_arr_tag; Dd.arr_shear = d_arr_shear;

@@ -384,10 +384,12 @@ class Engine {
     // every rank reads the whole atom table (as LAMMPS' read_data does) and keeps the atoms of its own brick
     std::vector<D4> hp, hv, hw;
     maxtag = 0;
+    loaded_index.clear();
+    const bool have_keep = keep_local.size() == a.size();
     for (size_t i = 0; i < a.size(); i++) {
       if (a.tag[i] < 0) fatal("Negative atom tag");
       maxtag = std::max(maxtag, a.tag[i]);
-      if (comm.nranks > 1) {
+      if (comm.nranks > 1 && !(have_keep && keep_local[i])) {
         double xw[3] = {a.x[3 * i], a.x[3 * i + 1], a.x[3 * i + 2]};
         for (int d = 0; d < 3; d++) if (cfg().periodic[d]) {
           const double lo = cfg().boxlo[d], hi = cfg().boxhi[d], prd = hi - lo;
@@ -405,7 +407,9 @@ class Engine {
       long long sb = (long long)b;
       memcpy(&w.w, &sb, 8);
       hp.push_back(p); hv.push_back(v); hw.push_back(w);
+      loaded_index.push_back((int)i);
     }
+    keep_local.clear();
     {
       double mt = (double)maxtag;
       comm.allreduce_max_host(&mt, 1);
@@ -676,7 +680,10 @@ class Engine {
     const int T = 256;
     const int n_old = nlocal + nghost;  // rows that are valid in quads[cur] (ghost rows are dropped by the sort)
     int narr = 0;
-    if (comm.nranks > 1) narr = comm.migrate(*this);  // leavers flagged in leave[], arrivals appended at rows >= n_old
+    // leavers flagged in leave[], arrivals appended at rows >= n_old.  Not at the re-upload after an injection / deletion / restart:
+    // its rows carry their contact history as arrival lists by upload order; a row that has strayed out of its brick (by less than
+    // skin / 2) stays with its owner until the next regular rebuild, as between any two re-neighbourings
+    if (comm.nranks > 1 && !inject_pending) narr = comm.migrate(*this);
     const int n_tmp = n_old + narr;
     const long long nc = ncells_bin();
     const int trash = (int)nc;                         // cell id of rows that leave the sort (ghosts, migrated-away)
@@ -1277,6 +1284,9 @@ class Engine {
   RowCarryBox *restart_carry;
   std::vector<std::string> restart_wall_ids;
   // particle injection / deletion: state of the surviving particles carried across the re-upload
+  std::vector<char> keep_local;     // per atom of script.atoms: 1 = came from this rank's device rows (stays here whatever the brick says: the
+                                    // next migration moves it), 0 = new / read from a file (kept only by the brick that owns its position)
+  std::vector<int> loaded_index;    // device row (upload order) -> index in script.atoms
   bool inject_pending;
   Buf<int> inj_nh, inj_tag;
   Buf<D4> inj_shear;
@@ -1354,7 +1364,6 @@ class Engine {
     if ((force_flags & SEDI_FORCE_ADDEDMASS) && !have_DDtU) fatal("added-mass force needs DDtU");
     if ((force_flags & SEDI_FORCE_LIFT) && !have_curlU) fatal("lift force needs curlU");
     if (force_flags & SEDI_FORCE_HISTORY) {
-      if (comm.nranks > 1) fatal("particleHistoryForce: the per-particle history state does not migrate between GPUs yet (single GPU only)");
       if (!hist_alloc) {  // softParticle starts with n0 = 0, sumDeltaFb = 0 (softParticle.C:63-64)
         for (int d = 0; d < 4; d++) for (int b = 0; b < 2; b++) { hist[d].b[b].ensure(npad); CK(cudaMemsetAsync(hist[d].b[b].p, 0, (size_t)npad * sizeof(double), stream)); }
         hist_alloc = true;
@@ -1600,7 +1609,7 @@ class Engine {
     if (hist_alloc) for (int d = 0; d < 4; d++) p.push_back(hist[d].get());
     return p;
   }
-  bool carry_enabled() const { return setup_done && comm.nranks == 1 && !getenv("SEDI_INJECT_RESET"); }
+  bool carry_enabled() const { return setup_done && !getenv("SEDI_INJECT_RESET"); }
   void save_rows(RowCarry &R) {
     const int m = nlocal;
     R.n = m;
@@ -1637,25 +1646,29 @@ class Engine {
       }
     }
   }
-  // keep[k] = old row of the k-th atom of the new table, -1 for an injected particle
+  // keep[t] = old row (index into R) of the t-th atom of the new table, -1 for an injected particle.  The device rows are
+  // the atoms this rank kept at the upload (loaded_index: row -> table index).
   void restore_rows(const RowCarry &R, const std::vector<int> &keep) {
-    const int m = (int)keep.size();
+    const int m = nlocal;
     if (!m) return;
+    if ((int)loaded_index.size() != m) fatal("internal: restore_rows without an upload map");
     if (R.nplanes > 18 + 3 * cfg().nwalls && !hist_alloc) {  // history-force planes existed before the re-upload
       for (int d = 0; d < 4; d++) for (int b = 0; b < 2; b++) { hist[d].b[b].ensure(npad); CK(cudaMemsetAsync(hist[d].b[b].p, 0, (size_t)npad * sizeof(double), stream)); hist[d].cur = 0; }
       hist_alloc = true;
     }
+    std::vector<int> old(m);
+    for (int i = 0; i < m; i++) old[i] = keep[loaded_index[i]];
     std::vector<double *> ptrs = carry_plane_ptrs();
     std::vector<double> tmp((size_t)m);
     for (size_t k = 0; k < ptrs.size() && k < R.planes.size(); k++) {
-      for (int i = 0; i < m; i++) tmp[i] = keep[i] >= 0 ? R.planes[k][keep[i]] : 0.0;
+      for (int i = 0; i < m; i++) tmp[i] = old[i] >= 0 ? R.planes[k][old[i]] : 0.0;
       CK(cudaMemcpy(ptrs[k], tmp.data(), (size_t)m * sizeof(double), cudaMemcpyHostToDevice));
     }
     std::vector<unsigned> wm(m); std::vector<int> fo(m), nh(m), ht((size_t)m * MIG_MAXH, 0);
     std::vector<D4> hs((size_t)m * MIG_MAXH);
     memset(hs.data(), 0, hs.size() * sizeof(D4));
     for (int i = 0; i < m; i++) {
-      const int o = keep[i];
+      const int o = old[i];
       wm[i] = o >= 0 ? R.wmask[o] : 0u; fo[i] = o >= 0 ? R.foam[o] : 0; nh[i] = o >= 0 ? R.nh[o] : 0;
       for (int q = 0; q < nh[i]; q++) {
         const size_t so = (size_t)o * MIG_MAXH + q, sn = (size_t)i * MIG_MAXH + q;
@@ -1702,8 +1715,11 @@ class Engine {
     if (dir && path.size() && path[0] != '/') return std::string(dir) + "/" + path;
     return path;
   }
-  void write_restart(const std::string &path) {
-    if (comm.nranks > 1) fatal("write_restart: single GPU only in this version");
+  // Several GPUs: every rank writes its own rows to "<file>.<rank>" (same layout); read_restart reads all parts on every
+  // rank and each brick keeps what it owns, so the number of GPUs may change between write and read.
+  void write_restart(const std::string &path_in) {
+    std::string path = path_in;
+    if (comm.nranks > 1) { char suf[32]; snprintf(suf, sizeof(suf), ".%d", comm.rank); path += suf; }
     if (!setup_done) setup();
     RowCarry R;
     save_rows(R);
@@ -1717,7 +1733,7 @@ class Engine {
     const long long step = c.ntimestep; wr(fp, &step, 8);
     wr(fp, &c.dt, 8); wr(fp, &dt_init, 8);
     wr(fp, &c.ntypes, 4); wr(fp, c.periodic, 12); wr(fp, c.boxlo, 24); wr(fp, c.boxhi, 24);
-    const int n = (int)a.size(), nw = c.nwalls, hh = hist_alloc ? 1 : 0;
+    const int n = (int)a.size(), nw = c.nwalls, hh = (hist_alloc ? 1 : 0) | (comm.nranks << 8);   // bits 8.. : number of parts
     wr(fp, &n, 4); wr(fp, &nw, 4); wr(fp, &hh, 4); wr(fp, &time_index, 4);
     for (size_t k = 0; k < c.fixes.size(); k++) if (c.fixes[k].kind == FIX_WALL_GRAN) {
       const int len = (int)strlen(c.fixes[k].id), wi = c.fixes[k].wall_index;
@@ -1733,45 +1749,62 @@ class Engine {
     fclose(fp);
   }
   void read_restart(const std::string &path) {
-    if (comm.nranks > 1) fatal("read_restart: single GPU only in this version");
-    FILE *fp = fopen(resolve_path(path).c_str(), "rb");
-    if (!fp) fatal("Cannot open restart file", path.c_str());
-    char magic[8]; rd(fp, magic, 8);
-    if (memcmp(magic, "SEDIRST1", 8)) fatal("read_restart: not a libsedi_b200 restart file", path.c_str());
+    // one file, or the parts "<file>.0" ... "<file>.<P-1>" a multi-GPU run wrote (P is in the header of every part)
+    std::string first = resolve_path(path);
+    FILE *probe = fopen(first.c_str(), "rb");
+    bool parts = false;
+    if (!probe) { first = resolve_path(path) + ".0"; probe = fopen(first.c_str(), "rb"); parts = true; }
+    if (!probe) fatal("Cannot open restart file", path.c_str());
+    fclose(probe);
     SimConfig &c = cfg();
-    long long step; rd(fp, &step, 8); c.ntimestep = step;
-    double dt_file, dt0; rd(fp, &dt_file, 8); rd(fp, &dt0, 8); c.dt = dt_file;
-    rd(fp, &c.ntypes, 4); rd(fp, c.periodic, 12); rd(fp, c.boxlo, 24); rd(fp, c.boxhi, 24); c.have_box = 1;
-    for (int d = 0; d < 3; d++) c.boundary_str[d] = c.periodic[d] ? "pp" : "ff";
-    int n, nw, hh, tix; rd(fp, &n, 4); rd(fp, &nw, 4); rd(fp, &hh, 4); rd(fp, &tix, 4);
-    if (n < 0 || nw < 0 || nw > MAX_WALLS) fatal("read_restart: corrupt header");
-    time_index = tix;
-    restart_wall_ids.assign(nw, std::string());
-    for (int k = 0; k < nw; k++) {
-      int wi, len; rd(fp, &wi, 4); rd(fp, &len, 4);
-      if (wi < 0 || wi >= nw || len < 0 || len > 4096) fatal("read_restart: corrupt wall table");
-      std::string id(len, ' '); rd(fp, &id[0], len); restart_wall_ids[wi] = id;
-    }
     AtomData &a = script.atoms;
     a = AtomData();
-    a.tag.resize(n); a.type.resize(n); script.mask.resize(n); a.x.resize(3 * (size_t)n); a.v.resize(3 * (size_t)n); a.omega.resize(3 * (size_t)n);
-    a.radius.resize(n); a.rmass.resize(n);
-    rd(fp, a.tag.data(), 4 * (size_t)n); rd(fp, a.type.data(), 4 * (size_t)n); rd(fp, script.mask.data(), 4 * (size_t)n);
-    rd(fp, a.x.data(), 24 * (size_t)n); rd(fp, a.v.data(), 24 * (size_t)n); rd(fp, a.omega.data(), 24 * (size_t)n);
-    rd(fp, a.radius.data(), 8 * (size_t)n); rd(fp, a.rmass.data(), 8 * (size_t)n);
+    script.mask.clear();
     if (!restart_carry) restart_carry = new RowCarryBox();
     RowCarry &R = restart_carry->R;
     R = RowCarry();
-    R.n = n;
-    int np; rd(fp, &np, 4);
-    if (np != 18 + 3 * nw + 4 * hh) fatal("read_restart: corrupt plane table");
-    R.nplanes = np;
-    R.planes.assign(np, std::vector<double>((size_t)n));
-    for (int k = 0; k < np; k++) rd(fp, R.planes[k].data(), 8 * (size_t)n);
-    R.wmask.resize(n); R.foam.resize(n); R.nh.resize(n); R.htag.resize((size_t)n * MIG_MAXH); R.hshear.resize((size_t)n * MIG_MAXH * 3);
-    rd(fp, R.wmask.data(), 4 * (size_t)n); rd(fp, R.foam.data(), 4 * (size_t)n);
-    rd(fp, R.nh.data(), 4 * (size_t)n); rd(fp, R.htag.data(), 4 * (size_t)n * MIG_MAXH); rd(fp, R.hshear.data(), 24 * (size_t)n * MIG_MAXH);
-    fclose(fp);
+    int nparts = 1, np_all = -1;
+    for (int part = 0; part < nparts; part++) {
+      std::string fn = resolve_path(path);
+      if (parts) { char suf[32]; snprintf(suf, sizeof(suf), ".%d", part); fn += suf; }
+      FILE *fp = fopen(fn.c_str(), "rb");
+      if (!fp) fatal("Cannot open restart file", fn.c_str());
+      char magic[8]; rd(fp, magic, 8);
+      if (memcmp(magic, "SEDIRST1", 8)) fatal("read_restart: not a libsedi_b200 restart file", fn.c_str());
+      long long step; rd(fp, &step, 8); c.ntimestep = step;
+      double dt_file, dt0; rd(fp, &dt_file, 8); rd(fp, &dt0, 8); c.dt = dt_file;
+      rd(fp, &c.ntypes, 4); rd(fp, c.periodic, 12); rd(fp, c.boxlo, 24); rd(fp, c.boxhi, 24); c.have_box = 1;
+      for (int d = 0; d < 3; d++) c.boundary_str[d] = c.periodic[d] ? "pp" : "ff";
+      int n, nw, hh, tix; rd(fp, &n, 4); rd(fp, &nw, 4); rd(fp, &hh, 4); rd(fp, &tix, 4);
+      if (n < 0 || nw < 0 || nw > MAX_WALLS) fatal("read_restart: corrupt header");
+      if (parts) nparts = std::max(1, hh >> 8);
+      hh &= 1;
+      time_index = tix;
+      restart_wall_ids.assign(nw, std::string());
+      for (int k = 0; k < nw; k++) {
+        int wi, len; rd(fp, &wi, 4); rd(fp, &len, 4);
+        if (wi < 0 || wi >= nw || len < 0 || len > 4096) fatal("read_restart: corrupt wall table");
+        std::string id(len, ' '); rd(fp, &id[0], len); restart_wall_ids[wi] = id;
+      }
+      const size_t n0 = a.tag.size(), nn = n0 + (size_t)n;
+      a.tag.resize(nn); a.type.resize(nn); script.mask.resize(nn); a.x.resize(3 * nn); a.v.resize(3 * nn); a.omega.resize(3 * nn);
+      a.radius.resize(nn); a.rmass.resize(nn);
+      rd(fp, a.tag.data() + n0, 4 * (size_t)n); rd(fp, a.type.data() + n0, 4 * (size_t)n); rd(fp, script.mask.data() + n0, 4 * (size_t)n);
+      rd(fp, a.x.data() + 3 * n0, 24 * (size_t)n); rd(fp, a.v.data() + 3 * n0, 24 * (size_t)n); rd(fp, a.omega.data() + 3 * n0, 24 * (size_t)n);
+      rd(fp, a.radius.data() + n0, 8 * (size_t)n); rd(fp, a.rmass.data() + n0, 8 * (size_t)n);
+      int np; rd(fp, &np, 4);
+      if (np != 18 + 3 * nw + 4 * hh) fatal("read_restart: corrupt plane table");
+      if (np_all < 0) { np_all = np; R.nplanes = np; R.planes.assign(np, std::vector<double>()); }
+      if (np != np_all) fatal("read_restart: the parts disagree on the per-atom planes");
+      for (int k = 0; k < np; k++) { R.planes[k].resize(nn); rd(fp, R.planes[k].data() + n0, 8 * (size_t)n); }
+      R.wmask.resize(nn); R.foam.resize(nn); R.nh.resize(nn); R.htag.resize(nn * MIG_MAXH); R.hshear.resize(nn * MIG_MAXH * 3);
+      rd(fp, R.wmask.data() + n0, 4 * (size_t)n); rd(fp, R.foam.data() + n0, 4 * (size_t)n);
+      rd(fp, R.nh.data() + n0, 4 * (size_t)n); rd(fp, R.htag.data() + n0 * MIG_MAXH, 4 * (size_t)n * MIG_MAXH);
+      rd(fp, R.hshear.data() + n0 * MIG_MAXH * 3, 24 * (size_t)n * MIG_MAXH);
+      fclose(fp);
+      R.n = (int)nn;
+    }
+    keep_local.clear();   // every brick keeps the atoms it owns
     loaded = false; setup_done = false; restart_pending = true;
   }
   // first setup after read_restart: the fixes are known now, so the stored per-atom state can be matched to them
@@ -1801,7 +1834,8 @@ class Engine {
   }
 
   void sync_host_atoms() {
-    if (!loaded || !nlocal) return;
+    if (!loaded) return;
+    if (!nlocal) { script.atoms = AtomData(); script.mask.clear(); return; }   // an empty brick owns no atoms
     const int m = nlocal;
     std::vector<double> x(3 * (size_t)m), v(3 * (size_t)m), w(3 * (size_t)m), r(m), ms(m);
     std::vector<int> tg(m), ty(m), mk(m);
@@ -1817,6 +1851,7 @@ class Engine {
     sync_host_atoms();
     std::vector<int> keep;
     for (size_t i = 0; i < script.atoms.size(); i++) keep.push_back((int)i);
+    std::vector<char> kl(script.atoms.size(), carry ? 1 : 0);   // rows that live on this GPU stay here; new particles go to the brick that owns them
     const int active = cfg().find_group("active");  // library.cpp:447-450: mask = 1 | bit("active")
     for (int m = 0; m < np; m++) {
       script.add_atom((int)tagd[m], type, diameter, rho, pos + 3 * (size_t)m, vel);
@@ -1825,8 +1860,10 @@ class Engine {
       script.atoms.rmass.back() = 4.0 * SEDI_PI_LIBRARY / 3.0 * rad * rad * rad * rho;
       script.mask.back() = 1 | active;
       keep.push_back(-1);
+      kl.push_back(0);
     }
     loaded = false; setup_done = false;
+    keep_local = kl;
     if (carry) reinject(R, keep);
   }
   void delete_particles(const int *list, int nd) {  // list holds atom tags (library.cpp:507-621)
@@ -1848,6 +1885,7 @@ class Engine {
     }
     script.atoms = b; script.mask = mk;
     loaded = false; setup_done = false;
+    keep_local.assign(b.size(), carry ? 1 : 0);
     if (carry) reinject(R, keep);
   }
 };

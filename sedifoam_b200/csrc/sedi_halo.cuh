@@ -60,15 +60,16 @@ __global__ void k_mig_classify(const D4 *posr, const D4 *omgt, int n, DecompDev 
 
 struct MigPlanes {
   int nwalls, npad, rec;           // rec = doubles per record
+  int npl;                         // planes carried: 12, or 16 with the history-force state
   const D4 *posr, *velm, *omgt;
-  const double *pl[12];            // fdrag, dudt, vold, uold (3 each)
+  const double *pl[16];            // fdrag, dudt, vold, uold (3 each) [+ sumDeltaFb xyz, n0: particleHistoryForce state, softParticle.H:104-107]
   const double *ws[MAX_WALLS * 3];
   const int *foam; const unsigned *wmask;
   const int *nn; const unsigned *nbr; const unsigned long long *tmask; const D4 *shear;  // old list (may be null)
   int *tag2idx; int maxtag;
 };
 
-// record layout (doubles): [0..11] quads, [12..23] planes, [24..24+3w) wall shear, then {foam|wmask}, nhist, MIG_MAXH x {tag, sx, sy, sz}
+// record layout (doubles): [0..11] quads, [12..12+npl) planes, then 3w wall shear, {foam|wmask}, nhist, MIG_MAXH x {tag, sx, sy, sz}
 __global__ void k_mig_pack(int nlinks, int cap, const int *count, const int *rows, MigPlanes M, double *out, int *err) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int L = t / cap, k = t % cap;
@@ -77,8 +78,8 @@ __global__ void k_mig_pack(int nlinks, int cap, const int *count, const int *row
   double *r = out + ((size_t)L * cap + k) * M.rec;
   const D4 p = M.posr[i], v = M.velm[i], w = M.omgt[i];
   r[0] = p.x; r[1] = p.y; r[2] = p.z; r[3] = p.w; r[4] = v.x; r[5] = v.y; r[6] = v.z; r[7] = v.w; r[8] = w.x; r[9] = w.y; r[10] = w.z; r[11] = w.w;
-  for (int q = 0; q < 12; q++) r[12 + q] = M.pl[q][i];
-  int o = 24;
+  for (int q = 0; q < M.npl; q++) r[12 + q] = M.pl[q][i];
+  int o = 12 + M.npl;
   for (int q = 0; q < 3 * M.nwalls; q++) r[o++] = M.ws[q][i];
   long long iw = ((long long)(unsigned)M.foam[i]) | ((long long)M.wmask[i] << 32);
   r[o++] = __longlong_as_double(iw);
@@ -104,9 +105,9 @@ __global__ void k_mig_pack(int nlinks, int cap, const int *count, const int *row
 }
 
 struct MigDst {
-  int nwalls, rec;
+  int nwalls, rec, npl;
   D4 *posr, *velm, *omgt;
-  double *pl[12];
+  double *pl[16];
   double *ws[MAX_WALLS * 3];
   int *foam; unsigned *wmask; int *leave;
   int *arr_nh, *arr_tag; D4 *arr_shear;
@@ -120,8 +121,8 @@ __global__ void k_mig_unpack(int narr, const double *in, int row0, MigDst M) {
   D4 p, v, w;
   p.x = r[0]; p.y = r[1]; p.z = r[2]; p.w = r[3]; v.x = r[4]; v.y = r[5]; v.z = r[6]; v.w = r[7]; w.x = r[8]; w.y = r[9]; w.z = r[10]; w.w = r[11];
   M.posr[i] = p; M.velm[i] = v; M.omgt[i] = w;
-  for (int q = 0; q < 12; q++) M.pl[q][i] = r[12 + q];
-  int o = 24;
+  for (int q = 0; q < M.npl; q++) M.pl[q][i] = r[12 + q];
+  int o = 12 + M.npl;
   for (int q = 0; q < 3 * M.nwalls; q++) M.ws[q][i] = r[o++];
   const long long iw = __double_as_longlong(r[o++]);
   M.foam[i] = (int)(unsigned)(iw & 0xFFFFFFFFll); M.wmask[i] = (unsigned)(iw >> 32);

@@ -25,6 +25,140 @@ SCEN = {
 }
 
 
+def _gather(eng, world, keys=("x", "v", "omega")):
+    st = eng.atoms()
+    parts = [None] * world
+    dist.all_gather_object(parts, {k: st[k] for k in ("tag",) + tuple(keys)})
+    tag = np.concatenate([p["tag"] for p in parts])
+    o = np.argsort(tag)
+    return {k: np.concatenate([p[k] for p in parts])[o] for k in ("tag",) + tuple(keys)}
+
+
+def _close(a, b, tol=1e-11):
+    return all(np.abs(a[k] - b[k]).max() <= tol * max(np.abs(b[k]).max(), 1e-300) for k in ("x", "v", "omega")) and np.array_equal(a["tag"], b["tag"])
+
+
+def features(rank, world, lr):
+    """multi-GPU features without a CPU oracle of their own: the several-GPU engine against the SAME engine on one GPU
+    (which the single-GPU suite checks against the reference objects): restart written as per-rank parts and read back,
+    particle injection / deletion keeping contact and wall history, and the history-force state migrating with its
+    particle.  Tolerance 1e-11 relative (ghost partners of a bin arrive in no fixed order, so sums may differ in the last bits)."""
+    import tempfile
+    ok = True
+    tmp = [tempfile.mkdtemp(prefix="sedi_mg_") if rank == 0 else None]
+    dist.broadcast_object_list(tmp, src=0)
+    os.environ["SEDI_DUMP_DIR"] = tmp[0]
+
+    def engines(case, grid=None):
+        multi = sb.Lammps(device=lr)
+        cases.apply(case, multi)
+        uid = [sb.Lammps.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        multi.comm_init(rank, world, uid[0], grid)
+        single = sb.Lammps(device=lr)
+        cases.apply(case, single)
+        return multi, single
+
+    # ---- restart: run, write parts, continue; read the parts into fresh engines, continue; equal end states
+    case = cases.settled_bed(columns=(3, 2), column="column_256x4.npz")
+    m, s1 = engines(case)
+    fd = cases.bench_fluid_force(case)
+    for e in (m, s1):
+        e.setup()
+    loc = m.get_local_info(); m.put_local_info(fd[loc["tag"] - 1], loc["tag"]); s1.put_local_info(fd, case["tag"])
+    m.step(120); s1.step(120)
+    m.command("write_restart mg.rst"); s1.command("write_restart sg.rst")
+    m.step(80); s1.step(80)
+    a_multi, a_single = _gather(m, world), s1.atoms()
+    good = _close(a_multi, a_single)
+    m.close(); s1.close()
+    m2, s2 = engines(case)
+    script_tail = [ln for ln in case["script"].strip().splitlines()]
+    for e, f in ((m2, "mg.rst"), (s2, "sg.rst")):
+        e.command("read_restart " + f)
+        for ln in script_tail:
+            e.command(ln)
+        e.step(80)
+    b_multi, b_single = _gather(m2, world), s2.atoms()
+    good = good and _close(b_multi, a_multi) and _close(b_single, a_single, tol=0.0) and _close(b_multi, b_single)
+    # a restart written by 2 GPUs read by 1 GPU
+    s3 = sb.Lammps(device=lr)
+    cases.apply(case, s3)
+    s3.command("read_restart mg.rst")
+    for ln in script_tail:
+        s3.command(ln)
+    s3.step(80)
+    good = good and _close(s3.atoms(), a_single)
+    if rank == 0:
+        print("[mgpu restart] parts written / read on %d GPUs, resumed runs agree -> %s" % (world, "OK" if good else "FAIL"), flush=True)
+    ok = ok and good
+    for e in (m2, s2, s3):
+        e.close()
+
+    # ---- injection / deletion with history kept: an intruder far above the bed comes and goes, the bed must not notice
+    m, s1 = engines(case)
+    u, _ = engines(case)
+    for e in (m, s1, u):
+        e.setup()
+    for e in (m, u):
+        loc = e.get_local_info(); e.put_local_info(fd[loc["tag"] - 1], loc["tag"])
+    s1.put_local_info(fd, case["tag"])
+    for e in (m, s1, u):
+        e.step(100)
+    top = float(case["box_hi"][1]) - 4.0 * float(case["diam"][0])
+    newtag = int(case["tag"].max()) + 1
+    pos = np.array([[0.5 * case["box_hi"][0], top, 0.5 * case["box_hi"][2]]])
+    for e in (m, s1):
+        e.create_particle(pos, [newtag], float(case["diam"][0]), 2650.0, 1, [0.0, 0.0, 0.0])
+        e.step(30)
+        e.delete_particle([newtag])
+        e.step(70)
+    u.step(100)
+    gm, gu, gs = _gather(m, world), _gather(u, world), s1.atoms()
+    good = _close(gm, gu) and _close(gm, gs) and len(gm["tag"]) == len(case["tag"])
+    if rank == 0:
+        print("[mgpu inject] create + delete on %d GPUs leaves the bed where the undisturbed run puts it -> %s" % (world, "OK" if good else "FAIL"), flush=True)
+    ok = ok and good
+    for e in (m, s1, u):
+        e.close()
+
+    # ---- history force (reduced-order Basset term): per-particle state migrates between bricks
+    case = cases.sediment_column(dims=(14, 20, 12), phi=0.45, jitter_frac=0.08)
+    rng = np.random.default_rng(5)
+    case["v"] = rng.normal(scale=0.15, size=case["x"].shape)     # particles cross the brick faces
+    m, s1 = engines(case, (world, 1, 1))
+    C = int(np.prod(case["mesh_n"]))
+    for e in (m, s1):
+        e.mesh_box(case["mesh_lo"], case["mesh_hi"], case["mesh_n"])
+        e.coupling_config(sb.DRAG_ERGUN_WENYU, sb.FORCE_DRAG | sb.FORCE_PGRAD | sb.FORCE_HISTORY, case["nub"], case["rhob"], case["g"], 4.0e-4)
+        e.setup()
+    arrivals = 0
+    for k in range(6):
+        Uf = rng.normal(scale=0.05, size=(C, 3)); gam = rng.uniform(0.2, 0.5, size=C); gp = rng.normal(scale=50.0, size=(C, 3))
+        bufs = [Uf, gam, gp]
+        dist.broadcast_object_list(bufs, src=0)
+        for e in (m, s1):
+            e.put_cell_fields(bufs[0], bufs[1], bufs[2])
+            e.coupling_time_index(1 + k)
+            e.compute_fluid_force()
+            e.sedi_step(200)
+        arrivals += m.comm_stat("arrivals")
+    good = _close(_gather(m, world), s1.atoms())
+    hs_m = m.history_state(); hs_s = s1.history_state()
+    parts = [None] * world
+    dist.all_gather_object(parts, dict(tag=m.atoms()["tag"], S=hs_m[0], n0=hs_m[1]))
+    tag = np.concatenate([p["tag"] for p in parts]); o = np.argsort(tag)
+    S = np.concatenate([p["S"] for p in parts])[o]; n0 = np.concatenate([p["n0"] for p in parts])[o]
+    good = good and np.abs(S - hs_s[0]).max() <= 1e-10 * max(np.abs(hs_s[0]).max(), 1e-300) and np.abs(n0 - hs_s[1]).max() < 1e-9 and np.abs(hs_s[0]).max() > 0
+    tot = torch.tensor([arrivals], device="cuda"); dist.all_reduce(tot)
+    good = good and int(tot.item()) > 0
+    if rank == 0:
+        print("[mgpu history force] state follows %d migrated particles, forces and state equal the single-GPU run -> %s" % (int(tot.item()), "OK" if good else "FAIL"), flush=True)
+    ok = ok and good
+    m.close(); s1.close()
+    return ok
+
+
 def main():
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(lr)
@@ -93,6 +227,7 @@ def main():
             ok = ok and good
         eng.close()
         dist.barrier()
+    ok = features(rank, world, lr) and ok
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()
