@@ -81,21 +81,23 @@ def features(rank, world, lr):
     a_multi, a_single = _gather(m, world), s1.atoms()
     good = _close(a_multi, a_single)
     m.close(); s1.close()
-    m2, s2 = engines(case)
-    script_tail = [ln for ln in case["script"].strip().splitlines()]
-    for e, f in ((m2, "mg.rst"), (s2, "sg.rst")):
-        e.command("read_restart " + f)
-        for ln in script_tail:
-            e.command(ln)
-        e.step(80)
+    def fresh(fname, multi):   # a new engine that knows nothing but the restart file and the script
+        e = sb.Lammps(device=lr)
+        e.command("atom_style sphere")
+        if multi:
+            uid = [sb.Lammps.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            e.comm_init(rank, world, uid[0], None)
+        e.command("read_restart " + fname)
+        e.commands(case["script"])
+        return e
+
+    m2, s2 = fresh("mg.rst", True), fresh("sg.rst", False)
+    m2.step(80); s2.step(80)
     b_multi, b_single = _gather(m2, world), s2.atoms()
     good = good and _close(b_multi, a_multi) and _close(b_single, a_single, tol=0.0) and _close(b_multi, b_single)
     # a restart written by 2 GPUs read by 1 GPU
-    s3 = sb.Lammps(device=lr)
-    cases.apply(case, s3)
-    s3.command("read_restart mg.rst")
-    for ln in script_tail:
-        s3.command(ln)
+    s3 = fresh("mg.rst", False)
     s3.step(80)
     good = good and _close(s3.atoms(), a_single)
     if rank == 0:
