@@ -84,11 +84,11 @@ def features(rank, world, lr):
     def fresh(fname, multi):   # a new engine that knows nothing but the restart file and the script
         e = sb.Lammps(device=lr)
         e.command("atom_style sphere")
+        e.command("read_restart " + fname)      # box, boundary, atoms and per-atom state come from the file
         if multi:
             uid = [sb.Lammps.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
             e.comm_init(rank, world, uid[0], None)
-        e.command("read_restart " + fname)
         e.commands(case["script"])
         return e
 
