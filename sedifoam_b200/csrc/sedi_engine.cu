@@ -221,6 +221,7 @@ class Engine {
   long long nbuilds, pair_evals, steps_done, launches, list_gran_dir, list_type_dir, list_gran_img, list_type_img;
   int chunk;
   bool warned_neigh;
+  int sm_count;
   bool use_wq;     // pair sweep on the warp-queue kernel (SEDI_KSTEP_PATH=wq)
   bool use_sell;   // pair sweep on the sorted-row kernel (default); SEDI_KSTEP_PATH=ell selects the streamed slot walk
   bool sell_sort;  // rows sorted by work inside windows at every rebuild (default with the sorted-row kernel; SEDI_SELL_SORT=0/1)
@@ -278,7 +279,7 @@ class Engine {
     e = getenv("SEDI_GRAPH");
     if (e && atoi(e) == 0) graph_on = false;
     e = getenv("SEDI_KSTEP_PATH");
-    warned_neigh = false;
+    warned_neigh = false; sm_count = 148;
     use_wq = (e && !strcmp(e, "wq"));
     use_sell = !(e && (!strcmp(e, "ell") || !strcmp(e, "wq")));
     sell_sort = use_sell;
@@ -328,6 +329,7 @@ class Engine {
             e != cudaSuccess ? cudaGetErrorString(e) : "");
     if (device >= cnt) device = device % cnt;
     CK(cudaSetDevice(device));
+    { cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, device)); sm_count = pr.multiProcessorCount; }
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventCreate(&evk0)); CK(cudaEventCreate(&evk1));
     CK(cudaEventCreate(&evt0)); CK(cudaEventCreate(&evt1));
@@ -620,7 +622,11 @@ class Engine {
     const bool pbc = P.periodic_any != 0;
     if (use_sell && cfg().pair != PAIR_NONE) {   // sorted-row kernel: one lane per particle, rows of a warp carry equal work (sedi_sell.cuh)
       const int ST = SEDI_SELL_THREADS;
+#if SEDI_SELL_PERSIST
+      const int sb = std::max(1, std::min(cdiv(nlocal, ST), sm_count * (tl ? 6 : SEDI_SELL_MINB)));   // one resident wave, grid-stride loop
+#else
       const int sb = std::max(1, cdiv(nlocal, ST));
+#endif
 #define SEDI_LAUNCH_SELL(PK)                                                                                  \
   do {                                                                                                        \
     if (tl) { if (pbc) k_step_sell<PK, true, true><<<sb, ST, 0, stream>>>(P, seq); else k_step_sell<PK, false, true><<<sb, ST, 0, stream>>>(P, seq); } \

@@ -43,7 +43,10 @@ namespace sedi {
 #ifndef SEDI_SELL_PFH
 #define SEDI_SELL_PFH 1    // 1: the history quads of all slots that overlapped one sub-step ago are requested (L2) at the top of the kernel
 #endif
-static const int SELL_WINDOW = 512;   // sigma of SELL-C-sigma: rows are sorted by work inside windows of this many rows
+#ifndef SEDI_SELL_WINDOW
+#define SEDI_SELL_WINDOW 512
+#endif
+static const int SELL_WINDOW = SEDI_SELL_WINDOW;   // sigma of SELL-C-sigma: rows are sorted by work inside windows of this many rows (<= 1024)
 
 // ---- row ordering: stable sort of every window of bin-ordered rows by the work the row had under the previous list ----
 // order[k]  : canonical (bin-ordered) position k -> old row            (input, from the counting sort)
@@ -95,19 +98,11 @@ __global__ void __launch_bounds__(SELL_WINDOW) k_window_sort(int n, const int *o
 // TYPELIST compiles the work of the type-cut-off list in (fix cohesive, pair lubricate/poly): done inside the distance-test
 // walk while the partner position is in registers, plus a walk over the type-only segment of the row; the plain granular
 // instantiation carries none of it.
+// one DEM sub-step of row i (one lane)
 template <int PAIR, bool PBC, bool TYPELIST>
-__global__ void __launch_bounds__(SEDI_SELL_THREADS, TYPELIST ? 6 : SEDI_SELL_MINB) k_step_sell(const __grid_constant__ StepParams P, const int seq) {
+__device__ __forceinline__ void sell_row(const StepParams &P, const int seq, const int i, unsigned (*s_e)[SEDI_SELL_THREADS]) {
   constexpr bool HIST = (PAIR == PAIR_HERTZFIX_HISTORY || PAIR == PAIR_HOOKE_HISTORY);
-  if (P.mode != MODE_SETUP) {
-    const int fl = *(volatile int *)&P.ctrl[0];
-    if (fl != 0 && fl < seq) return;  // an earlier step of this chunk asked for a neighbour rebuild: become a no-op
-  }
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0 && P.mode != MODE_SETUP) atomicAdd(&P.ctrl[1], 1);
-  if (i >= P.n) return;
-
   // ---- own row, list words of the first 16 slots (twelve unconditionally: they depend on nothing; rows have >= 16 slots)
-  __shared__ unsigned s_e[16][SEDI_SELL_THREADS];   // the row's list words, kept for phase 2 (one column per lane: conflict-free)
   const int tid = threadIdx.x;
   D4 pi = ldg_d4_stream(&P.posr_in[i]);
   D4 vi = ldg_d4_stream(&P.velm_in[i]);
@@ -304,6 +299,42 @@ __global__ void __launch_bounds__(SEDI_SELL_THREADS, TYPELIST ? 6 : SEDI_SELL_MI
   if (P.has_fdrag) { fd0 = ld_nc_f64(&P.fdrag[0][i]); fd1 = ld_nc_f64(&P.fdrag[1][i]); fd2 = ld_nc_f64(&P.fdrag[2][i]); }
   if (P.mode == MODE_FUSED) { xh0 = ld_nc_f64(&P.xhold[0][i]); xh1 = ld_nc_f64(&P.xhold[1][i]); xh2 = ld_nc_f64(&P.xhold[2][i]); }
   step_epilogue<PAIR, TYPELIST>(P, i, seq, pi, vi, wi, fx, fy, fz, tx, ty, tz, cfx, cfy, cfz, fd0, fd1, fd2, xh0, xh1, xh2, touch);
+}
+
+
+#ifndef SEDI_SELL_PERSIST
+#define SEDI_SELL_PERSIST 0   // 1: persistent grid (one wave of CTAs), grid-stride loop over the rows, next row's lines prefetched to L2
+#endif
+template <int PAIR, bool PBC, bool TYPELIST>
+__global__ void __launch_bounds__(SEDI_SELL_THREADS, TYPELIST ? 6 : SEDI_SELL_MINB) k_step_sell(const __grid_constant__ StepParams P, const int seq) {
+  if (P.mode != MODE_SETUP) {
+    const int fl = *(volatile int *)&P.ctrl[0];
+    if (fl != 0 && fl < seq) return;  // an earlier step of this chunk asked for a neighbour rebuild: become a no-op
+  }
+  __shared__ unsigned s_e[16][SEDI_SELL_THREADS];   // the row's list words, kept for phase 2 (one column per lane: conflict-free)
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 == 0 && P.mode != MODE_SETUP) atomicAdd(&P.ctrl[1], 1);
+#if SEDI_SELL_PERSIST
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = i0; i < P.n; i += stride) {
+    const int in = i + stride;
+    if (in < P.n) {   // the next row of this lane: its lines start towards L2 while this row is processed
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.posr_in[in]));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.velm_in[in]));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.omgt_in[in]));
+      if ((threadIdx.x & 7) == 0) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.nn[in]));
+#pragma unroll
+        for (int k = 0; k < 12; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.nbr[(size_t)k * P.npad + in]));
+      }
+      if ((threadIdx.x & 3) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.tmask[in]));
+    }
+    sell_row<PAIR, PBC, TYPELIST>(P, seq, i, s_e);
+  }
+#else
+  if (i0 >= P.n) return;
+  sell_row<PAIR, PBC, TYPELIST>(P, seq, i0, s_e);
+#endif
 }
 
 }  // namespace sedi
