@@ -93,6 +93,12 @@ struct Comm {
   void *exported[7];              // the local pointers the current mappings were made from
   std::vector<int> rstart;        // per link: first ghost row of my segment in the peer's arrays
   unsigned epoch;
+  // ghost refresh fused into the sub-step kernel: row -> (link, position) entries and the push tables of both buffers, on the device
+  unsigned char *d_bcnt; int *d_bpos, *d_bcount, *d_bfill; BorderEnt *d_bent; size_t cap_brow, cap_bent;
+  PushTable *d_push[2];
+  bool fused_push;                // SEDI_HALO_FUSED=0 keeps the separate k_halo_push launch
+  void build_row_table(Engine &e);
+  void make_push_table(PushTable &H, int buf) const;
   void setup_peer(Engine &e);
   void close_peer();
   Comm();
@@ -126,7 +132,8 @@ struct Comm {
   void setup_decomp(Engine &e);
   int migrate(Engine &e);                 // returns the number of particles that arrived
   void borders(Engine &e);                // send lists, ghost rows, ghost bins
-  void forward(Engine &e, int buf, bool with_flag);  // per-sub-step ghost refresh (+ rebuild-flag consensus)
+  // per-sub-step ghost refresh (+ rebuild-flag consensus); pushed: the sub-step kernel has written the ghost rows itself
+  void forward(Engine &e, int buf, bool with_flag, bool pushed = false);
 };
 
 }  // namespace sedi

@@ -61,7 +61,10 @@ inline Comm::Comm()
     : rank(0), nranks(1), nccl_lib(0), nccl_comm(0), total_send(0), total_recv(0), d_small(0), h_small(0), d_sendrows(0), cap_sendrows(0),
       d_blockcnt(0), d_blockoff(0), d_blocksum(0), cap_block(0), d_sendbuf(0), d_recvbuf(0), cap_sendbuf(0), cap_recvbuf(0), d_migrows(0),
       d_migsend(0), d_migrecv(0), cap_mig(0), migcap(0), migrec(0), d_arr_nh(0), d_arr_tag(0), d_arr_shear(0), cap_arr(0), d_gcellid(0),
-      d_gcount(0), d_gstart(0), d_gfill(0), d_gorder(0), cap_g(0), cap_gcells(0), narr_last(0), halo_calls(0), p2p(false), d_sig(0), epoch(0) {
+      d_gcount(0), d_gstart(0), d_gfill(0), d_gorder(0), cap_g(0), cap_gcells(0), narr_last(0), halo_calls(0), p2p(false), d_sig(0), epoch(0),
+      d_bcnt(0), d_bpos(0), d_bcount(0), d_bfill(0), d_bent(0), cap_brow(0), cap_bent(0), fused_push(true) {
+  d_push[0] = d_push[1] = 0;
+  if (const char *f = getenv("SEDI_HALO_FUSED")) fused_push = atoi(f) != 0;
   memset(peer_base, 0, sizeof(peer_base)); memset(exported, 0, sizeof(exported));
   grid[0] = grid[1] = grid[2] = 1; coord[0] = coord[1] = coord[2] = 0;
   memset(&dev, 0, sizeof(dev));
@@ -107,7 +110,7 @@ inline void Comm::destroy() {
   if (d_sig) { cudaFree(d_sig); d_sig = 0; }
   if (nccl_comm) { nccl_dyn::CommDestroy((ncclComm_t)nccl_comm); nccl_comm = 0; }
   void *ptrs[] = {d_small, d_sendrows, d_blockcnt, d_blockoff, d_blocksum, d_sendbuf, d_recvbuf, d_migrows, d_migsend, d_migrecv, d_arr_nh,
-                  d_arr_tag, d_arr_shear, d_gcellid, d_gcount, d_gstart, d_gfill, d_gorder};
+                  d_arr_tag, d_arr_shear, d_gcellid, d_gcount, d_gstart, d_gfill, d_gorder, d_bcnt, d_bpos, d_bcount, d_bfill, d_bent, d_push[0], d_push[1]};
   for (size_t k = 0; k < sizeof(ptrs) / sizeof(ptrs[0]); k++) if (ptrs[k]) cudaFree(ptrs[k]);
   if (h_small) cudaFreeHost(h_small);
 }
@@ -398,6 +401,7 @@ inline void Comm::borders(Engine &e) {
     CK(cudaMemcpyAsync(h_small + 32, d_rcnt, 32 * sizeof(int), cudaMemcpyDeviceToHost, e.stream));
     CK(cudaStreamSynchronize(e.stream));
     for (int L = 0; L < NL; L++) rstart[L] = h_small[32 + L];
+    if (fused_push) build_row_table(e);
   }
   forward(e, e.cur, false);
   // bin the ghost rows (index lists, no physical re-ordering)
@@ -426,20 +430,65 @@ inline void Comm::borders(Engine &e) {
 }
 
 // ---- Comm::forward_comm(): ghost x, v, omega every sub-step, plus the rebuild-flag consensus ---------------------------
-inline void Comm::forward(Engine &e, int buf, bool with_flag) {
+inline void Comm::make_push_table(PushTable &H, int buf) const {
+  const int NL = dev.nlinks;
+  memset(&H, 0, sizeof(H));
+  H.nlinks = NL;
+  for (int L = 0; L < NL; L++) {
+    H.base[L] = sendbase[L]; H.rstart[L] = rstart[L];
+    for (int d = 0; d < 3; d++) H.shift[L][d] = links[L].shift[d];
+    const int pr = links[L].peer;
+    H.rposr[L] = (D4 *)peer_base[pr][0 + buf]; H.rvelm[L] = (D4 *)peer_base[pr][2 + buf]; H.romgt[L] = (D4 *)peer_base[pr][4 + buf];
+  }
+  H.base[NL] = total_send;
+}
+
+// row -> (link, position) entries of the border rows, and the two push tables, for the ghost refresh fused into the sub-step kernel
+inline void Comm::build_row_table(Engine &e) {
+  const int nl = e.nlocal, T = 256, NL = dev.nlinks;
+  if ((size_t)e.npad + 1 > cap_brow) {
+    if (d_bcnt) { CK(cudaFree(d_bcnt)); CK(cudaFree(d_bpos)); CK(cudaFree(d_bcount)); CK(cudaFree(d_bfill)); }
+    cap_brow = (size_t)e.npad + 1;
+    CK(cudaMalloc((void **)&d_bcnt, cap_brow)); CK(cudaMalloc((void **)&d_bpos, cap_brow * sizeof(int)));
+    CK(cudaMalloc((void **)&d_bcount, cap_brow * sizeof(int))); CK(cudaMalloc((void **)&d_bfill, cap_brow * sizeof(int)));
+  }
+  if ((size_t)total_send + 1 > cap_bent) {
+    if (d_bent) CK(cudaFree(d_bent));
+    cap_bent = (size_t)total_send + total_send / 4 + 1024;
+    CK(cudaMalloc((void **)&d_bent, cap_bent * sizeof(BorderEnt)));
+  }
+  if (!d_push[0]) { CK(cudaMalloc((void **)&d_push[0], sizeof(PushTable))); CK(cudaMalloc((void **)&d_push[1], sizeof(PushTable))); }
+  CK(cudaMemsetAsync(d_bcount, 0, cap_brow * sizeof(int), e.stream));
+  CK(cudaMemsetAsync(d_bfill, 0, cap_brow * sizeof(int), e.stream));
+  CK(cudaMemsetAsync(d_bcnt, 0, cap_brow, e.stream));
+  if (total_send) k_border_rowcount<<<cdiv(total_send, T), T, 0, e.stream>>>(d_sendrows, total_send, d_bcount);
+  const int nscan = nl + 1, nblk = cdiv(nscan, SCAN_ITEMS);
+  e.blocksum.ensure((size_t)nblk + 1);
+  k_scan_local<<<nblk, 1024, 0, e.stream>>>(d_bcount, d_bpos, nscan, e.blocksum.p);
+  k_scan_sums<<<1, 1024, 0, e.stream>>>(e.blocksum.p, nblk);
+  k_scan_add<<<cdiv(nscan, T), T, 0, e.stream>>>(d_bpos, nscan, e.blocksum.p, 0);
+  HaloTable H;
+  memset(&H, 0, sizeof(H));
+  H.nlinks = NL;
+  for (int L = 0; L < NL; L++) H.base[L] = sendbase[L];
+  H.base[NL] = total_send;
+  if (total_send) k_border_rowfill<<<cdiv(total_send, T), T, 0, e.stream>>>(d_sendrows, H, d_bpos, d_bfill, d_bent);
+  if (nl) k_border_pack_cnt<<<cdiv(nl, T), T, 0, e.stream>>>(nl, d_bcount, d_bcnt, d_small + 64);
+  for (int b = 0; b < 2; b++) {
+    PushTable P;
+    make_push_table(P, b);
+    CK(cudaMemcpyAsync(d_push[b], &P, sizeof(PushTable), cudaMemcpyHostToDevice, e.stream));
+    CK(cudaStreamSynchronize(e.stream));   // P is a stack object
+  }
+  e.launches += 6;
+}
+
+inline void Comm::forward(Engine &e, int buf, bool with_flag, bool pushed) {
   const int T = 256, NL = dev.nlinks;
   if (p2p) {
     PushTable H;
-    memset(&H, 0, sizeof(H));
-    H.nlinks = NL;
-    for (int L = 0; L < NL; L++) {
-      H.base[L] = sendbase[L]; H.rstart[L] = rstart[L];
-      for (int d = 0; d < 3; d++) H.shift[L][d] = links[L].shift[d];
-      const int pr = links[L].peer;
-      H.rposr[L] = (D4 *)peer_base[pr][0 + buf]; H.rvelm[L] = (D4 *)peer_base[pr][2 + buf]; H.romgt[L] = (D4 *)peer_base[pr][4 + buf];
-    }
-    H.base[NL] = total_send;
-    if (total_send) k_halo_push<<<cdiv(total_send, T), T, 0, e.stream>>>(e.posr[buf].p, e.velm[buf].p, e.omgt[buf].p, d_sendrows, H);
+    make_push_table(H, buf);
+    if (total_send && !pushed) k_halo_push<<<cdiv(total_send, T), T, 0, e.stream>>>(e.posr[buf].p, e.velm[buf].p, e.omgt[buf].p, d_sendrows, H);
     SignalTable S;
     memset(&S, 0, sizeof(S));
     S.nranks = nranks; S.me = rank;

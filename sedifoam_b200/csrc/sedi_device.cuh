@@ -53,6 +53,18 @@ struct FixDev {
   double aux;
 };
 
+// ---- ghost refresh fused into the sub-step kernel (multi-GPU, peer-memory path): the border rows of this brick are written
+// straight into the neighbours' ghost rows by the thread that has just integrated them (step_epilogue)
+static const int MAX_LINKS = 26;
+struct PushTable {
+  int nlinks;
+  int base[MAX_LINKS + 1];
+  int rstart[MAX_LINKS];       // first ghost row, in the peer's arrays, of the segment this link fills
+  double shift[MAX_LINKS][3];
+  D4 *rposr[MAX_LINKS], *rvelm[MAX_LINKS], *romgt[MAX_LINKS];   // the peer's arrays of the buffer being written
+};
+struct BorderEnt { int link, pos; };   // a border row's entry: link and position in that link's send list
+
 struct StepParams {
   int n;        // rows in the particle arrays (owned + ghost)
   int npad;     // ELL leading dimension
@@ -78,6 +90,11 @@ struct StepParams {
   double *xhold[3];
   double *wshear[MAX_WALLS][3];
   unsigned *wmask;            // per-particle wall-touch bits
+  // fused ghost refresh (null on one GPU / NCCL halo): entries of row i are bent[bpos[i] .. bpos[i] + bcnt[i])
+  const unsigned char *bcnt;
+  const int *bpos;
+  const BorderEnt *bent;
+  const PushTable *push;      // device copy of the table for the buffer this launch writes
   int *ctrl;                  // [0] rebuild-needed flag, [1] steps completed, [2] error flags
   unsigned long long *counters;  // [0] directed pair visits, [1] directed touching pairs
   double dtv, dtf, dt_live, trigger_sq;

@@ -598,6 +598,9 @@ class Engine {
       for (int w = 0; w < cfg().nwalls; w++) P.wshear[w][d] = wshear[w][d].get();
     }
     P.wmask = wmask[icur].p;
+    if (comm.nranks > 1 && comm.p2p && comm.fused_push && mode == MODE_FUSED) {   // the kernel refreshes the neighbours' ghost rows itself
+      P.bcnt = comm.d_bcnt; P.bpos = comm.d_bpos; P.bent = comm.d_bent; P.push = comm.d_push[in ^ 1];
+    }
     const SimConfig &c = cfg();
     for (size_t k = 0; k < c.fixes.size(); k++) {
       const FixSpec &s = c.fixes[k];
@@ -623,14 +626,15 @@ class Engine {
     if (use_sell && cfg().pair != PAIR_NONE) {   // sorted-row kernel: one lane per particle, rows of a warp carry equal work (sedi_sell.cuh)
       const int ST = SEDI_SELL_THREADS;
 #if SEDI_SELL_PERSIST
-      const int sb = std::max(1, std::min(cdiv(nlocal, ST), sm_count * (tl ? 6 : SEDI_SELL_MINB)));   // one resident wave, grid-stride loop
+      const int sb = std::max(1, std::min(cdiv(nlocal, ST), sm_count * (P.lub_enabled ? 6 : SEDI_SELL_MINB)));   // one resident wave, grid-stride loop
 #else
       const int sb = std::max(1, cdiv(nlocal, ST));
 #endif
 #define SEDI_LAUNCH_SELL(PK)                                                                                  \
   do {                                                                                                        \
-    if (tl) { if (pbc) k_step_sell<PK, true, true><<<sb, ST, 0, stream>>>(P, seq); else k_step_sell<PK, false, true><<<sb, ST, 0, stream>>>(P, seq); } \
-    else { if (pbc) k_step_sell<PK, true, false><<<sb, ST, 0, stream>>>(P, seq); else k_step_sell<PK, false, false><<<sb, ST, 0, stream>>>(P, seq); } \
+    if (P.lub_enabled) { if (pbc) k_step_sell<PK, true, 2><<<sb, ST, 0, stream>>>(P, seq); else k_step_sell<PK, false, 2><<<sb, ST, 0, stream>>>(P, seq); } \
+    else if (tl) { if (pbc) k_step_sell<PK, true, 1><<<sb, ST, 0, stream>>>(P, seq); else k_step_sell<PK, false, 1><<<sb, ST, 0, stream>>>(P, seq); } \
+    else { if (pbc) k_step_sell<PK, true, 0><<<sb, ST, 0, stream>>>(P, seq); else k_step_sell<PK, false, 0><<<sb, ST, 0, stream>>>(P, seq); } \
   } while (0)
       switch (cfg().pair) {
         case PAIR_HERTZFIX_HISTORY: SEDI_LAUNCH_SELL(PAIR_HERTZFIX_HISTORY); break;
@@ -994,7 +998,7 @@ class Engine {
             const bool lastk = (lastflag && s == K - 1);
             launch_step(lastk ? MODE_LAST : MODE_FUSED, cin, cfg().ntimestep + s + 1, ++cseq);
             cin ^= 1;
-            if (mg && !lastk) comm.forward(*this, cin, true);
+            if (mg && !lastk) comm.forward(*this, cin, true, comm.p2p && comm.fused_push);
           }
           CK(cudaStreamEndCapture(stream, &gr));
           launches = l0; comm.halo_calls = h0;
@@ -1023,7 +1027,7 @@ class Engine {
         const bool last = (remaining - s == 1);
         launch_step(last ? MODE_LAST : MODE_FUSED, in, cfg().ntimestep + s + 1, ++seq);
         in ^= 1;
-        if (mg && !last) comm.forward(*this, in, true);  // ghost x, v, omega of the new positions + rebuild consensus
+        if (mg && !last) comm.forward(*this, in, true, comm.p2p && comm.fused_push);  // ghost x, v, omega of the new positions (written by the step kernel itself on the peer-memory path) + rebuild consensus
       }
       if (prof_on) CK(cudaEventRecord(evk1, stream));
       CK(cudaMemcpyAsync(h_ctrl.p, ctrl.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, stream));

@@ -11,7 +11,6 @@
 
 namespace sedi {
 
-static const int MAX_LINKS = 26;
 static const int MIG_MAXH = 16;  // contact-history entries carried by a migrating particle
 
 struct DecompDev {
@@ -197,13 +196,27 @@ __global__ void k_halo_pack(const D4 *posr, const D4 *velm, const D4 *omgt, cons
 // ---- fused pack + send over NVLink peer memory -----------------------------------------------------------------------
 // The ghost rows of every neighbour brick are mapped into this process (CUDA IPC); the border rows are written
 // straight into them (posr + shift, velm, omgt | GHOST), no staging buffer, no NCCL call, no unpack kernel.
-struct PushTable {
-  int nlinks;
-  int base[MAX_LINKS + 1];
-  int rstart[MAX_LINKS];       // first ghost row, in the peer's arrays, of the segment this link fills
-  double shift[MAX_LINKS][3];
-  D4 *rposr[MAX_LINKS], *rvelm[MAX_LINKS], *romgt[MAX_LINKS];   // the peer's arrays of the buffer being written
-};
+// row -> entries table of the fused ghost refresh (built once per rebuild from the per-link send lists)
+__global__ void k_border_rowcount(const int *sendrows, int total, int *cnt) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < total) atomicAdd(&cnt[sendrows[e]], 1);
+}
+__global__ void k_border_rowfill(const int *sendrows, HaloTable H, const int *bpos, int *fill, BorderEnt *bent) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= H.base[H.nlinks]) return;
+  int L = 0;
+  while (L + 1 < H.nlinks && e >= H.base[L + 1]) L++;
+  const int i = sendrows[e];
+  BorderEnt b; b.link = L; b.pos = e - H.base[L];
+  bent[bpos[i] + atomicAdd(&fill[i], 1)] = b;   // order inside a row is irrelevant: every entry has its own destination
+}
+__global__ void k_border_pack_cnt(int n, const int *cnt, unsigned char *bcnt, int *err) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = cnt[i];
+  if (c > 255) atomicOr(err, 32);
+  bcnt[i] = (unsigned char)c;
+}
 __global__ void k_halo_push(const D4 *posr, const D4 *velm, const D4 *omgt, const int *sendrows, const __grid_constant__ PushTable H) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= H.base[H.nlinks]) return;

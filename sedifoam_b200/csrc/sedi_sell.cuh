@@ -44,7 +44,7 @@ namespace sedi {
 #define SEDI_SELL_PFH 1    // 1: the history quads of all slots that overlapped one sub-step ago are requested (L2) at the top of the kernel
 #endif
 #ifndef SEDI_SELL_WINDOW
-#define SEDI_SELL_WINDOW 512
+#define SEDI_SELL_WINDOW 1024
 #endif
 static const int SELL_WINDOW = SEDI_SELL_WINDOW;   // sigma of SELL-C-sigma: rows are sorted by work inside windows of this many rows (<= 1024)
 
@@ -95,11 +95,13 @@ __global__ void __launch_bounds__(SELL_WINDOW) k_window_sort(int n, const int *o
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------------------------
-// TYPELIST compiles the work of the type-cut-off list in (fix cohesive, pair lubricate/poly): done inside the distance-test
-// walk while the partner position is in registers, plus a walk over the type-only segment of the row; the plain granular
-// instantiation carries none of it.
+// TYPELIST compiles the work of the type-cut-off list in (fix cohesive, pair lubricate/poly): a third walk over the row
+// (both segments), see below -- doing it inside the distance-test walk was measured slower (configs[4]: 1478 instead of
+// 1044 us per launch: eight partner positions plus the lubrication operands do not fit the registers); the plain
+// granular instantiation carries none of it.
 // one DEM sub-step of row i (one lane)
-template <int PAIR, bool PBC, bool TYPELIST>
+// TYPELIST: 0 none, 1 fix cohesive only, 2 pair lubricate/poly (and fix cohesive if present)
+template <int PAIR, bool PBC, int TYPELIST>
 __device__ __forceinline__ void sell_row(const StepParams &P, const int seq, const int i, unsigned (*s_e)[SEDI_SELL_THREADS]) {
   constexpr bool HIST = (PAIR == PAIR_HERTZFIX_HISTORY || PAIR == PAIR_HOOKE_HISTORY);
   // ---- own row, list words of the first 16 slots (twelve unconditionally: they depend on nothing; rows have >= 16 slots)
@@ -134,16 +136,8 @@ __device__ __forceinline__ void sell_row(const StepParams &P, const int seq, con
 
   // ---- phase 1: which list entries overlap (pair :131 `rsq >= radsum*radsum` -> no contact)
   unsigned long long touch = 0ull;
-  double lfx = 0.0, lfy = 0.0, lfz = 0.0, ltx = 0.0, lty = 0.0, ltz = 0.0;  // lubricate/poly (TYPELIST)
-  double cfx = 0.0, cfy = 0.0, cfz = 0.0;                               // fix cohesive (TYPELIST)
-  const CoheCoef co = cohesive_coef<TYPELIST>(P);
-  const int tagi = bits_tag((unsigned long long)__double_as_longlong(wi.w));
-  const double inv_radi = TYPELIST ? 1.0 / radi : 0.0;
-  (void)tagi; (void)inv_radi;
-  // distance test of one list entry; TYPELIST: the entry's fix cohesive / lubricate/poly work is done here as well, while the
-  // partner position is in registers (s < 0: an entry of the type-only segment, no granular test)
   auto test_entry = [&](const unsigned e, const D4 &pj_in, const int s) {
-    if (!(e & (TYPELIST ? (NB_FLAG_GRAN | NB_FLAG_TYPE) : NB_FLAG_GRAN))) return;
+    if (!(e & NB_FLAG_GRAN)) return;
     D4 pj = pj_in;
     const int img = (int)((e >> NB_IMG_SHIFT) & 31u);
     if (PBC && img != NB_IMG_NONE) {  // periodic image = LAMMPS ghost: position is fl(x_j + shift)
@@ -152,12 +146,7 @@ __device__ __forceinline__ void sell_row(const StepParams &P, const int seq, con
     const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
     const double rsq = delx * delx + dely * dely + delz * delz;
     const double radsum = radi + pj.w;
-    if ((!TYPELIST || (s >= 0 && (e & NB_FLAG_GRAN))) && rsq < radsum * radsum) touch |= (1ull << s);
-    if (TYPELIST && (e & NB_FLAG_TYPE)) {
-      const int j = (int)(e & NB_IDX_MASK);
-      if (P.has_cohesive) cohesive_entry_fast(P, co, j, img, tagi, maski, radsum, rsq, delx, dely, delz, cfx, cfy, cfz);
-      if (P.lub_enabled && P.lub_flagHI && rsq < P.lub_cutsq) lubricate_entry_fast(P, j, pi, vi, wi, inv_radi, pj.w, rsq, delx, dely, delz, lfx, lfy, lfz, ltx, lty, ltz);
-    }
+    if (rsq < radsum * radsum) touch |= (1ull << s);
   };
 #pragma unroll
   for (int b = 0; b < 16; b += 8) {
@@ -271,20 +260,45 @@ __device__ __forceinline__ void sell_row(const StepParams &P, const int seq, con
 #endif
   if (HIST && touch != tm_old) P.tmask[i] = touch;
 
-  // ---- TYPELIST: the type-only segment [hcap, hcap + nti) of the row (partners beyond the granular cut-off: lubricate/poly's
-  // full list, fix cohesive with a large smax), four partner positions in flight at a time; then the isotropic FLD terms
+  // ---- phase T (TYPELIST): fix cohesive / pair lubricate/poly over the entries of the type-cut-off list -- the granular segment
+  // [0, nni) and the type-only segment [hcap, hcap + nti) --, four partner positions in flight at a time.  Rows of a warp have
+  // (nearly) the same length, so the per-lane walk keeps the lanes busy.
+  double lfx = 0.0, lfy = 0.0, lfz = 0.0, ltx = 0.0, lty = 0.0, ltz = 0.0;  // lubricate/poly
+  double cfx = 0.0, cfy = 0.0, cfz = 0.0;                               // fix cohesive
   if (TYPELIST) {
-    for (int sb = 0; sb < nti; sb += 4) {
+    const CoheCoef co = cohesive_coef<(TYPELIST != 0)>(P);
+    const int tagi = bits_tag((unsigned long long)__double_as_longlong(wi.w));
+    const int ntot = nni + nti;
+    const double inv_radi = 1.0 / radi;
+    for (int sb = 0; sb < ntot; sb += 4) {
       unsigned e4[4];
       D4 p4[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) e4[k] = (sb + k < nti) ? ld_nc_u32(&P.nbr[(size_t)(P.hcap + sb + k) * P.npad + i]) : 0u;
+      for (int k = 0; k < 4; k++) {
+        const int q = sb + k;
+        e4[k] = (q < ntot) ? (q < nni ? list_word(q) : ld_nc_u32(&P.nbr[(size_t)(P.hcap + (q - nni)) * P.npad + i])) : 0u;
+      }
 #pragma unroll
       for (int k = 0; k < 4; k++) p4[k] = ldg_d4(&P.posr_in[e4[k] & NB_IDX_MASK]);
 #pragma unroll
-      for (int k = 0; k < 4; k++) test_entry(e4[k] & ~NB_FLAG_GRAN, p4[k], -1);
+      for (int k = 0; k < 4; k++) {
+        const unsigned ew = e4[k];
+        if (!(ew & NB_FLAG_TYPE)) continue;
+        D4 pj = p4[k];
+        const int img = (int)((ew >> NB_IMG_SHIFT) & 31u);
+        if (PBC && img != NB_IMG_NONE) {
+          pj.x = pj.x + P.imgshift[img][0]; pj.y = pj.y + P.imgshift[img][1]; pj.z = pj.z + P.imgshift[img][2];
+        }
+        const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
+        const double rsq = delx * delx + dely * dely + delz * delz;
+        const double radj = pj.w;
+        const double radsum = radi + radj;
+        const int j = (int)(ew & NB_IDX_MASK);
+        if (P.has_cohesive) cohesive_entry_fast(P, co, j, img, tagi, maski, radsum, rsq, delx, dely, delz, cfx, cfy, cfz);
+        if (TYPELIST == 2 && P.lub_enabled && P.lub_flagHI && rsq < P.lub_cutsq) lubricate_entry_fast(P, j, pi, vi, wi, inv_radi, radj, rsq, delx, dely, delz, lfx, lfy, lfz, ltx, lty, ltz);
+      }
     }
-    if (P.lub_enabled) {  // isotropic FLD terms (pair_lubricate_poly.cpp:213-221) are applied before the pair terms in the reference
+    if (TYPELIST == 2 && P.lub_enabled) {  // isotropic FLD terms (:213-221) are applied before the pair terms in the reference
       double ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
       if (P.lub_flagfld) {
         ax -= P.lub_R0 * radi * vi.x; ay -= P.lub_R0 * radi * vi.y; az -= P.lub_R0 * radi * vi.z;
@@ -298,15 +312,15 @@ __device__ __forceinline__ void sell_row(const StepParams &P, const int seq, con
   double fd0 = 0.0, fd1 = 0.0, fd2 = 0.0, xh0 = 0.0, xh1 = 0.0, xh2 = 0.0;
   if (P.has_fdrag) { fd0 = ld_nc_f64(&P.fdrag[0][i]); fd1 = ld_nc_f64(&P.fdrag[1][i]); fd2 = ld_nc_f64(&P.fdrag[2][i]); }
   if (P.mode == MODE_FUSED) { xh0 = ld_nc_f64(&P.xhold[0][i]); xh1 = ld_nc_f64(&P.xhold[1][i]); xh2 = ld_nc_f64(&P.xhold[2][i]); }
-  step_epilogue<PAIR, TYPELIST>(P, i, seq, pi, vi, wi, fx, fy, fz, tx, ty, tz, cfx, cfy, cfz, fd0, fd1, fd2, xh0, xh1, xh2, touch);
+  step_epilogue<PAIR, (TYPELIST != 0)>(P, i, seq, pi, vi, wi, fx, fy, fz, tx, ty, tz, cfx, cfy, cfz, fd0, fd1, fd2, xh0, xh1, xh2, touch);
 }
 
 
 #ifndef SEDI_SELL_PERSIST
 #define SEDI_SELL_PERSIST 0   // 1: persistent grid (one wave of CTAs), grid-stride loop over the rows, next row's lines prefetched to L2
 #endif
-template <int PAIR, bool PBC, bool TYPELIST>
-__global__ void __launch_bounds__(SEDI_SELL_THREADS, TYPELIST ? 6 : SEDI_SELL_MINB) k_step_sell(const __grid_constant__ StepParams P, const int seq) {
+template <int PAIR, bool PBC, int TYPELIST>
+__global__ void __launch_bounds__(SEDI_SELL_THREADS, TYPELIST == 2 ? 6 : SEDI_SELL_MINB) k_step_sell(const __grid_constant__ StepParams P, const int seq) {
   if (P.mode != MODE_SETUP) {
     const int fl = *(volatile int *)&P.ctrl[0];
     if (fl != 0 && fl < seq) return;  // an earlier step of this chunk asked for a neighbour rebuild: become a no-op
