@@ -154,6 +154,11 @@ void sedi_enable_diag(void *ptr, int on); /* keep Uri/|Uri|/alpha/Jd per particl
 void sedi_get_coupling_diag(void *ptr, int *cell, double *Uri, double *magUri, double *alphap, double *Jd, double *F);
 /* same as lammps_step but never touches host particle arrays */
 void sedi_step(void *ptr, int n);
+/* OpenFOAM lagrangian fields of the cloud (softParticle::writeFields, lammpsFoam/softParticleIO.C:157-197): positions (with
+ * owner cell), d, tag, lmpCpuId, type, U, ensembleU -- plus density and n0, which readFields (:113-152) requires -- as ASCII
+ * IOField files in `dir`; `location` is the FoamFile header's location string, e.g. "0.1/lagrangian/cloud" (may be NULL).
+ * On several GPUs every rank writes "<field>.<rank>". */
+void sedi_write_lagrangian(void *ptr, const char *dir, const char *location);
 /* the reference's built-in invariants, printed by it every step: "total F before / after" of calcTcFields
  * (enhancedCloud.C:395-435: sum_c Asrc V (1 - gamma) before and after smoothing) and "total U solid before / after" of
  * particleToEulerianField (:936-976: sum_p Vp Up, and sum_c Ue V gamma after smoothing).  Off by default (four small

@@ -1843,6 +1843,68 @@ class Engine {
     delete restart_carry; restart_carry = 0;
   }
 
+  // ---- OpenFOAM lagrangian fields (softParticle::writeFields, softParticleIO.C:157-197): positions (with the owner cell),
+  // d, tag, lmpCpuId, type, U, ensembleU in OpenFOAM's ASCII IOField layout under <dir>/ (the host passes
+  // "<time>/lagrangian/<cloudName>").  density and n0 are written too: readFields (:113-152) demands them although the
+  // reference's writeFields forgets to write them.  Rows in ascending tag; particles outside the mesh keep cell -1.
+  void write_lagrangian(const char *dir, const char *location) {
+    if (!setup_done) setup();
+    if (have_mesh && !cell_valid) locate();
+    const int m = nlocal;
+    std::vector<double> x(3 * (size_t)m), v(3 * (size_t)m), r(m), ms(m), n0(m, 0.0);
+    std::vector<int> tg(m), ty(m), cl(m, -1);
+    if (m) {
+      get_state(x.data(), v.data(), 0, 0, 0, r.data(), ms.data(), tg.data(), ty.data(), 0);
+      if (have_mesh) { CK(cudaMemcpyAsync(cl.data(), cell.p, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, stream)); CK(cudaStreamSynchronize(stream)); }
+      if (hist_alloc) get_history_state(0, n0.data());
+    }
+    std::vector<int> ord(m);
+    for (int i = 0; i < m; i++) ord[i] = i;
+    std::sort(ord.begin(), ord.end(), [&](int a, int b) { return tg[a] < tg[b]; });
+    const std::string base = std::string(dir) + (comm.nranks > 1 ? "/processor" + std::to_string(comm.rank) : std::string());
+    auto open_field = [&](const char *name, const char *cls) -> FILE * {
+      const std::string path = std::string(dir) + "/" + name + (comm.nranks > 1 ? "." + std::to_string(comm.rank) : std::string());
+      FILE *fp = fopen(path.c_str(), "w");
+      if (!fp) fatal("Cannot open lagrangian field file", path.c_str());
+      fprintf(fp, "/*--------------------------------*- C++ -*----------------------------------*\\\n"
+                  "| =========                 |                                                 |\n"
+                  "| \\\\      /  F ield         | OpenFOAM: The Open Source CFD Toolbox           |\n"
+                  "\\*---------------------------------------------------------------------------*/\n"
+                  "FoamFile\n{\n    version     2.0;\n    format      ascii;\n    class       %s;\n    location    \"%s\";\n    object      %s;\n}\n"
+                  "// * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * //\n\n%d\n(\n", cls, location, name, m);
+      return fp;
+    };
+    auto close_field = [&](FILE *fp) { fprintf(fp, ")\n\n\n// ************************************************************************* //\n"); fclose(fp); };
+    (void)base;
+    FILE *fp = open_field("positions", "Cloud<softParticle>");
+    for (int q = 0; q < m; q++) { const int i = ord[q]; fprintf(fp, "(%.15g %.15g %.15g) %d\n", x[3 * (size_t)i], x[3 * (size_t)i + 1], x[3 * (size_t)i + 2], cl[i]); }
+    close_field(fp);
+    fp = open_field("d", "scalarField");
+    for (int q = 0; q < m; q++) fprintf(fp, "%.15g\n", 2.0 * r[ord[q]]);
+    close_field(fp);
+    fp = open_field("density", "scalarField");
+    for (int q = 0; q < m; q++) { const int i = ord[q]; fprintf(fp, "%.15g\n", 3.0 * ms[i] / (4.0 * SEDI_PI_LIBRARY * r[i] * r[i] * r[i])); }   // library.cpp:200
+    close_field(fp);
+    fp = open_field("n0", "scalarField");
+    for (int q = 0; q < m; q++) fprintf(fp, "%.15g\n", n0[ord[q]]);
+    close_field(fp);
+    fp = open_field("tag", "labelField");
+    for (int q = 0; q < m; q++) fprintf(fp, "%d\n", tg[ord[q]]);
+    close_field(fp);
+    fp = open_field("lmpCpuId", "labelField");
+    for (int q = 0; q < m; q++) fprintf(fp, "%d\n", comm.rank);
+    close_field(fp);
+    fp = open_field("type", "labelField");
+    for (int q = 0; q < m; q++) fprintf(fp, "%d\n", ty[ord[q]]);
+    close_field(fp);
+    fp = open_field("U", "vectorField");
+    for (int q = 0; q < m; q++) { const int i = ord[q]; fprintf(fp, "(%.15g %.15g %.15g)\n", v[3 * (size_t)i], v[3 * (size_t)i + 1], v[3 * (size_t)i + 2]); }
+    close_field(fp);
+    fp = open_field("ensembleU", "vectorField");   // never assigned by the reference: stays (0 0 0) (softParticle.C:56)
+    for (int q = 0; q < m; q++) fprintf(fp, "(0 0 0)\n");
+    close_field(fp);
+  }
+
   void sync_host_atoms() {
     if (!loaded) return;
     if (!nlocal) { script.atoms = AtomData(); script.mask.clear(); return; }   // an empty brick owns no atoms
@@ -2142,6 +2204,7 @@ void sedi_step(void *ptr, int n) {
   e->save_uold_if_ready(); e->run(n);
   e->timers[7] += Engine::now_s() - t0;
 }
+void sedi_write_lagrangian(void *ptr, const char *dir, const char *location) { E(ptr)->write_lagrangian(dir, location ? location : ""); }
 void sedi_enable_conservation_sums(void *ptr, int on) { E(ptr)->want_sums = (on != 0); }
 void sedi_get_conservation_sums(void *ptr, double *Ftotal_before, double *Ftotal_after, double *Utotal_before, double *Utotal_after) {
   Engine *e = E(ptr);

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "sedi_get_profile", "sedi_mesh_box", "sedi_mesh_rectilinear", "sedi_mesh_ncells", "sedi_coupling_config",
     "sedi_put_cell_fields", "sedi_coupling_time_index", "sedi_coupling_inlet", "sedi_get_history_state", "sedi_locate", "sedi_compute_fluid_force", "sedi_scatter_alpha_u", "sedi_calc_tc",
     "sedi_enable_diag", "sedi_get_coupling_diag", "sedi_step", "sedi_enable_conservation_sums", "sedi_get_conservation_sums",
-    "sedi_average_info", "sedi_get_timers", "sedi_comm_init", "sedi_comm_unique_id", "sedi_comm_rank", "sedi_comm_stat",
+    "sedi_average_info", "sedi_get_timers", "sedi_write_lagrangian", "sedi_comm_init", "sedi_comm_unique_id", "sedi_comm_rank", "sedi_comm_stat",
     "sedi_decomp_grid", "sedi_decomp_owner", "sedi_decomp_links", "sedi_smooth_config", "sedi_smooth_uf", "sedi_smooth_field",
     "sedi_smooth_last_iters",
 ]
@@ -130,6 +130,7 @@ def load_library():
         "sedi_get_conservation_sums": (None, [vp, vp, vp, vp, vp]),
         "sedi_average_info": (None, [vp, vp, vp, vp]),
         "sedi_get_timers": (None, [vp, vp, vp, vp]),
+        "sedi_write_lagrangian": (None, [vp, C.c_char_p, C.c_char_p]),
         "sedi_comm_init": (i, [vp, i, i, vp, i, vp]),
         "sedi_comm_unique_id": (i, [vp, i]),
         "sedi_comm_rank": (i, [vp]),
@@ -459,6 +460,10 @@ class Lammps:
 
     def sedi_step(self, n):
         self.lib.sedi_step(self.h, int(n))
+
+    def write_lagrangian(self, directory, location=None):
+        """OpenFOAM lagrangian field files of the cloud (softParticleIO.C:157-197) into `directory`"""
+        self.lib.sedi_write_lagrangian(self.h, str(directory).encode(), None if location is None else location.encode())
 
     def enable_conservation_sums(self, on=True):
         self.lib.sedi_enable_conservation_sums(self.h, 1 if on else 0)

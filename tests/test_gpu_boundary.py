@@ -518,3 +518,108 @@ def test_restart_resumes_exactly(oracle_mod, tmp_path):
             os.environ.pop("SEDI_DUMP_DIR", None)
         else:
             os.environ["SEDI_DUMP_DIR"] = old
+
+
+def _read_foam_field(path):
+    """entries of an OpenFOAM ASCII IOField file written by sedi_write_lagrangian"""
+    txt = open(path).read()
+    assert "FoamFile" in txt and "format      ascii;" in txt
+    body = txt[txt.index("// * * *"):]
+    lines = [ln.strip() for ln in body.splitlines()[1:] if ln.strip() and not ln.startswith("//")]
+    n = int(lines[0])
+    assert lines[1] == "(" and lines[2 + n] == ")"
+    return n, lines[2:2 + n], txt
+
+
+def test_lagrangian_fields_openfoam_layout(oracle_mod, tmp_path):
+    """softParticle::writeFields (softParticleIO.C:157-197): positions with the owner cell, d, tag, lmpCpuId, type, U, ensembleU
+    (+ density, n0 that readFields :113-152 requires) as OpenFOAM ASCII IOFields; values equal the device state.  No
+    OpenFOAM here to read them back: the layout follows the IOField / Cloud positions text format (parity unpinned)."""
+    case = cases.fluidized_bed(dims=(6, 7, 5), vjit=0.05)
+    e = make_engine(case)
+    e.mesh_box(case["mesh_lo"], case["mesh_hi"], case["mesh_n"])
+    e.step(40)
+    e.locate()
+    e.write_lagrangian(tmp_path, "0.1/lagrangian/cloud")
+    st = e.atoms()
+    n = len(st["tag"])
+    cell = oracle_mod.cell_owner(st["x"], case["mesh_lo"], case["mesh_hi"], case["mesh_n"])
+    m, rows, txt = _read_foam_field(tmp_path / "positions")
+    assert m == n and "class       Cloud<softParticle>;" in txt and 'location    "0.1/lagrangian/cloud";' in txt
+    got = np.array([[float(v) for v in r.replace("(", "").replace(")", "").split()] for r in rows])
+    assert np.allclose(got[:, :3], st["x"], rtol=1e-14, atol=0) and np.array_equal(got[:, 3].astype(int), cell)
+    for name, cls, want in (("d", "scalarField", 2.0 * st["radius"]), ("tag", "labelField", st["tag"]), ("type", "labelField", st["type"]),
+                            ("lmpCpuId", "labelField", np.zeros(n)), ("n0", "scalarField", np.zeros(n)),
+                            ("density", "scalarField", 3.0 * st["rmass"] / (4.0 * 3.14159265358917323846 * st["radius"] ** 3))):
+        m, rows, txt = _read_foam_field(tmp_path / name)
+        assert m == n and ("class       %s;" % cls) in txt
+        assert np.allclose(np.array([float(r) for r in rows]), want, rtol=1e-14, atol=0), name
+    for name, want in (("U", st["v"]), ("ensembleU", np.zeros((n, 3)))):
+        m, rows, txt = _read_foam_field(tmp_path / name)
+        assert m == n and "class       vectorField;" in txt
+        got = np.array([[float(v) for v in r.strip("()").split()] for r in rows])
+        assert np.allclose(got, want, rtol=1e-14, atol=0), name
+
+
+def test_particle_outside_the_mesh_is_ignored_by_the_coupling(oracle_mod):
+    """the reference deletes a particle that hits a non-processor patch from the Foam cloud while it lives on in LAMMPS
+    (softParticle.C:177-184) -- after which its own lammps_put_local_info indexes out of range.  Decision
+    here: such a particle gets owner cell -1, no fluid force, and takes no part in the scatters; the DEM keeps it."""
+    case = cases.fluidized_bed(dims=(6, 7, 5), vjit=0.0)
+    hi = case["mesh_hi"].copy()
+    hi[1] = case["x"][:, 1].max() - 1.6 * case["diam"][0]        # the mesh ends below the two top layers
+    nc = case["mesh_n"].copy(); nc[1] = max(1, nc[1] // 2)
+    e = make_engine(case)
+    e.mesh_box(case["mesh_lo"], hi, nc)
+    e.coupling_config(DRAG_ERGUN_WENYU, FORCE_DRAG | FORCE_PGRAD, case["nub"], case["rhob"], case["g"], 2.0e-4)
+    C = int(np.prod(nc))
+    e.put_cell_fields(np.tile([0.0, 0.3, 0.0], (C, 1)), np.full(C, 0.4), np.tile([0.0, -9800.0, 0.0], (C, 1)))
+    e.setup()
+    e.enable_diag(True)
+    e.compute_fluid_force()
+    dg = e.coupling_diag()
+    st = e.atoms()
+    out = st["x"][:, 1] >= hi[1]
+    assert out.sum() == 2 * 6 * 5 and np.array_equal(dg["cell"] < 0, out)
+    assert np.all(dg["F"][out] == 0.0) and np.all(np.abs(dg["F"][~out, 1]) > 0.0)
+    g, Ue = e.scatter_alpha_u()
+    V = np.prod((hi - case["mesh_lo"]) / nc)
+    assert abs((g * V).sum() / (np.pi / 6 * (2 * st["radius"][~out]) ** 3).sum() - 1.0) < 1e-12     # only the inside particles are scattered
+    e.step(20)
+    assert e.get_local_n() == len(case["tag"])                                                  # the DEM keeps every particle
+
+
+def test_reference_printouts_and_timers(oracle_mod):
+    """what lammpsFoam.C / writeCPUTime.H read besides the fields (enhancedCloud.H:206-249): averageInfo, the two
+    conservation printouts ("total F before / after", "total U solid before / after", enhancedCloud.C:395-435, 936-976)
+    and the timers.  Sums against numpy on the same state; smoothing conserves them (the reference's built-in invariant)."""
+    case = cases.fluidized_bed(dims=(8, 9, 7), vjit=0.1)
+    e = make_engine(case)
+    e.mesh_box(case["mesh_lo"], case["mesh_hi"], case["mesh_n"])
+    e.coupling_config(DRAG_ERGUN_WENYU, FORCE_DRAG | FORCE_PGRAD, case["nub"], case["rhob"], case["g"], 2.0e-4)
+    e.smooth_config(2.0 * case["diam"][0] * 2, 2)
+    rng = np.random.default_rng(3)
+    Uf, gamma, gradp, _, _ = _fields(case, rng)
+    e.put_cell_fields(Uf, gamma, gradp)
+    e.enable_conservation_sums(True)
+    e.step(30)
+    st = e.atoms()
+    vol = np.pi / 6.0 * (2.0 * st["radius"]) ** 3
+    ai = e.average_info()
+    assert abs(ai["totalVolume"] / vol.sum() - 1.0) < 1e-13
+    assert np.allclose(ai["totalVel"], (vol[:, None] * st["v"]).sum(axis=0), rtol=1e-11, atol=1e-25)
+    assert np.allclose(ai["averageVel"], ai["totalVel"] / ai["totalVolume"], rtol=1e-13)
+    g, Ue = e.scatter_alpha_u()
+    A, Om = e.calc_tc()
+    s = e.conservation_sums()
+    scaleU = np.abs(vol[:, None] * st["v"]).sum()
+    assert np.abs(s["U_before"] - (vol[:, None] * st["v"]).sum(axis=0)).max() < 1e-11 * scaleU
+    assert np.abs(s["U_after"] - s["U_before"]).max() < 1e-9 * scaleU          # diffusion smoothing conserves sum(gamma Ue V)
+    V = np.prod((case["mesh_hi"] - case["mesh_lo"]) / case["mesh_n"])
+    assert np.abs(s["U_after"] - (Ue * (g * V)[:, None]).sum(axis=0)).max() < 1e-11 * scaleU
+    scaleF = np.abs(A * V * (1 - g)[:, None]).sum()
+    assert np.abs(s["F_after"] - (A * V * (1 - g)[:, None]).sum(axis=0)).max() < 1e-11 * scaleF
+    assert np.abs(s["F_after"] - s["F_before"]).max() < 1e-9 * scaleF and scaleF > 0
+    t = e.timers()
+    assert t["cpuTimeSplit"][4] > 0.0 and t["particleMoveTime"] > 0.0 and t["diffusionTimeCount"][1] > 0.0
+    assert np.all(t["cpuTimeSplit"][:3] == 0.0)                                 # no all-to-alls here
