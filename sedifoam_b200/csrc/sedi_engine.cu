@@ -19,6 +19,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <unistd.h>
+
 #include <algorithm>
 #include <chrono>
 #include <string>
@@ -222,6 +224,8 @@ class Engine {
   int chunk;
   bool warned_neigh;
   int sm_count;
+  MPI_Comm mpi_world;   // the communicator handed to lammps_open / new LAMMPS(0, NULL, comm) (library.h:29, softParticleCloud.C:60-62)
+  bool comm_tried;
   bool use_wq;     // pair sweep on the warp-queue kernel (SEDI_KSTEP_PATH=wq)
   bool use_sell;   // pair sweep on the sorted-row kernel (default); SEDI_KSTEP_PATH=ell selects the streamed slot walk
   bool sell_sort;  // rows sorted by work inside windows at every rebuild (default with the sorted-row kernel; SEDI_SELL_SORT=0/1)
@@ -279,7 +283,7 @@ class Engine {
     e = getenv("SEDI_GRAPH");
     if (e && atoi(e) == 0) graph_on = false;
     e = getenv("SEDI_KSTEP_PATH");
-    warned_neigh = false; sm_count = 148;
+    warned_neigh = false; sm_count = 148; mpi_world = (MPI_Comm)0; comm_tried = false;
     use_wq = (e && !strcmp(e, "wq"));
     use_sell = !(e && (!strcmp(e, "ell") || !strcmp(e, "wq")));
     sell_sort = use_sell;
@@ -828,8 +832,70 @@ class Engine {
   // undirected granular list size as LAMMPS counts it (owned-ghost image pairs are stored by both owners)
   long long list_pairs_undirected() const { return (list_gran_dir - list_gran_img) / 2 + list_gran_img; }
 
+  // ---- multi-GPU bootstrap without a host call (softParticleCloud.C:60-62 only hands an MPI_Comm to LAMMPS) ------
+  // One rank <-> one GPU.  The NCCL unique id goes from rank 0 to the others
+  //   * over the communicator itself when the library is built with -DSEDI_HAVE_MPI (MPI_Bcast), or
+  //   * launcher environment + a rendezvous file when SEDI_AUTO_COMM=1 (RANK / WORLD_SIZE of torchrun, OMPI_COMM_WORLD_*,
+  //     PMI_*, SLURM_*): "$SEDI_BOOTSTRAP_DIR/sedi_nccl_<MASTER_PORT or job id>_<n-th engine of the process>".
+  // A host that calls sedi_comm_init itself (bench.py, the tests) is left alone.
+  static int env_int(const char *const *names, int dflt) {
+    for (int k = 0; names[k]; k++) if (const char *v = getenv(names[k])) return atoi(v);
+    return dflt;
+  }
+  void auto_comm() {
+    if (comm_tried || comm.nranks > 1) return;
+    comm_tried = true;
+    int world = 1, rank = 0;
+    bool via_mpi = false;
+#ifdef SEDI_HAVE_MPI
+    { int init = 0; MPI_Initialized(&init); if (init) { MPI_Comm_size(mpi_world, &world); MPI_Comm_rank(mpi_world, &rank); via_mpi = world > 1; } }
+#endif
+    const char *ac = getenv("SEDI_AUTO_COMM");
+    if (!via_mpi && ac && atoi(ac) != 0) {
+      static const char *const ws[] = {"SEDI_WORLD_SIZE", "WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "SLURM_NTASKS", 0};
+      static const char *const rk[] = {"SEDI_RANK", "RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK", "SLURM_PROCID", 0};
+      world = env_int(ws, 1); rank = env_int(rk, 0);
+    }
+    if (world <= 1) return;
+    static int instance = 0;
+    const int inst = instance++;
+    char id[256];
+    int nb = 0;
+    if (rank == 0) { nb = Comm::unique_id(id, sizeof(id)); if (nb <= 0) fatal("multi-GPU bootstrap: NCCL is not available (libnccl.so.2)"); }
+    if (via_mpi) {
+#ifdef SEDI_HAVE_MPI
+      MPI_Bcast(&nb, 1, MPI_INT, 0, mpi_world);
+      MPI_Bcast(id, nb, MPI_BYTE, 0, mpi_world);
+#endif
+    } else {
+      static const char *const job[] = {"SEDI_BOOTSTRAP_TOKEN", "MASTER_PORT", "SLURM_JOB_ID", "OMPI_MCA_ess_base_jobid", 0};
+      const char *dir = getenv("SEDI_BOOTSTRAP_DIR");
+      char path[1024], tmp[1100];
+      snprintf(path, sizeof(path), "%s/sedi_nccl_%d_%d", dir ? dir : "/tmp", env_int(job, 0), inst);
+      if (rank == 0) {
+        snprintf(tmp, sizeof(tmp), "%s.tmp", path);
+        FILE *fp = fopen(tmp, "wb");
+        if (!fp) fatal("multi-GPU bootstrap: cannot write the rendezvous file", tmp);
+        fwrite(&nb, sizeof(int), 1, fp); fwrite(id, 1, nb, fp); fclose(fp);
+        if (rename(tmp, path) != 0) fatal("multi-GPU bootstrap: cannot publish the rendezvous file", path);
+      } else {
+        FILE *fp = 0;
+        for (int k = 0; k < 12000 && !fp; k++) { fp = fopen(path, "rb"); if (!fp) usleep(10000); }
+        if (!fp) fatal("multi-GPU bootstrap: rank 0 never published the NCCL id", path);
+        if (fread(&nb, sizeof(int), 1, fp) != 1 || nb <= 0 || nb > (int)sizeof(id) || fread(id, 1, nb, fp) != (size_t)nb) fatal("multi-GPU bootstrap: bad rendezvous file", path);
+        fclose(fp);
+      }
+      comm.init(*this, rank, world, id, nb, 0);
+      comm.barrier();
+      if (rank == 0) unlink(path);
+      return;
+    }
+    comm.init(*this, rank, world, id, nb, 0);
+  }
+
   // ---- Verlet::setup (first `run` of the session, even with `pre no`; softParticleCloud.C:189 lammps_step(0)) -----
   void setup(bool evaluate_forces = true) {
+    auto_comm();
     if (restart_pending) { setup_from_restart(); return; }
     if (!loaded) load_atoms();
     need_device();
@@ -1975,7 +2041,9 @@ using sedi::Engine;
 // The handle that crosses the boundary is a LAMMPS_NS::LAMMPS* exactly as in the reference (softParticleCloud.H:71
 // holds `LAMMPS* lmp_` and passes it as the `void *` of library.h): include/lammps_shim/lammps.h.
 namespace LAMMPS_NS {
-LAMMPS::LAMMPS(int, char **, MPI_Comm communicator) : input(new Input(this)), engine(new Engine()), world(communicator) {}
+LAMMPS::LAMMPS(int, char **, MPI_Comm communicator) : input(new Input(this)), engine(new Engine()), world(communicator) {
+  ((Engine *)engine)->mpi_world = communicator;
+}
 LAMMPS::~LAMMPS() { delete (Engine *)engine; delete input; }
 char *Input::one(const char *line) { ((Engine *)lmp->engine)->command(line); return NULL; }
 void Input::file(const char *path) { ((Engine *)lmp->engine)->file(path); }
@@ -1985,6 +2053,14 @@ static inline Engine *E(void *p) {
   if (!p) sedi::fatal("NULL LAMMPS handle passed to libsedi_b200");
   return (Engine *)((LAMMPS_NS::LAMMPS *)p)->engine;
 }
+// the pre-run queries of softParticleCloud::initLammps (softParticleCloud.C:119-163) are per-rank in the reference: on
+// several ranks the bricks must exist (and own their atoms) before they are answered
+static inline Engine *EQ(void *p) {
+  Engine *e = E(p);
+  e->auto_comm();
+  if (e->comm.nranks > 1 && !e->loaded) e->load_atoms();
+  return e;
+}
 
 extern "C" {
 
@@ -1993,15 +2069,15 @@ void lammps_close(void *ptr) { delete (LAMMPS_NS::LAMMPS *)ptr; }
 void lammps_file(void *ptr, char *path) { E(ptr)->file(path); }
 char *lammps_command(void *ptr, char *line) { E(ptr)->command(line); return NULL; }
 void lammps_sync(void *ptr) { Engine *e = E(ptr); if (e->dev_ready) { CK(cudaSetDevice(e->device)); CK(cudaStreamSynchronize(e->stream)); } e->comm.barrier(); }
-int lammps_get_global_n(void *ptr) { Engine *e = E(ptr); long long m = e->loaded ? e->nlocal : (long long)e->script.atoms.size(); return (int)e->comm.allreduce_sum_ll(m); }
+int lammps_get_global_n(void *ptr) { Engine *e = EQ(ptr); long long m = e->loaded ? e->nlocal : (long long)e->script.atoms.size(); return (int)e->comm.allreduce_sum_ll(m); }
 void lammps_get_initial_np(void *ptr, int *np) {
-  Engine *e = E(ptr);
+  Engine *e = EQ(ptr);
   const int m = e->loaded ? e->nlocal : (int)e->script.atoms.size();
   e->comm.allgather_int(m, np);
 }
 void lammps_get_initial_info(void *ptr, double *coords, double *velos, double *diam, double *rho, int *tag, int *lmpCpuId,
                              int *type) {
-  Engine *e = E(ptr);
+  Engine *e = EQ(ptr);
   if (!e->loaded) {  // before the first run the atoms still live in the script (read_data order)
     const sedi::AtomData &a = e->script.atoms;
     for (size_t i = 0; i < a.size(); i++) {
@@ -2022,9 +2098,9 @@ void lammps_get_initial_info(void *ptr, double *coords, double *velos, double *d
     lmpCpuId[i] = e->comm.rank;
   }
 }
-int lammps_get_local_n(void *ptr) { Engine *e = E(ptr); return e->loaded ? e->nlocal : (int)e->script.atoms.size(); }
+int lammps_get_local_n(void *ptr) { Engine *e = EQ(ptr); return e->loaded ? e->nlocal : (int)e->script.atoms.size(); }
 void lammps_get_local_domain(void *ptr, double *dom) {
-  Engine *e = E(ptr);
+  Engine *e = EQ(ptr);
   for (int d = 0; d < 3; d++) { dom[2 * d] = e->comm.sublo(e->cfg(), d, 0.0); dom[2 * d + 1] = e->comm.subhi(e->cfg(), d, 0.0); }
 }
 void lammps_get_local_info(void *ptr, double *coords, double *velos, int *foamCpuId, int *lmpCpuId, int *tag) {

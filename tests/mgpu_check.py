@@ -46,6 +46,10 @@ def _close(a, b, tol=1e-8):
     return all(v <= tol for v in e)
 
 
+def fd_bed(case):
+    return cases.bench_fluid_force(case)
+
+
 def features(rank, world, lr):
     """multi-GPU features without a CPU oracle of their own: the several-GPU engine against the SAME engine on one GPU
     (which the single-GPU suite checks against the reference objects): restart written as per-rank parts and read back,
@@ -172,6 +176,34 @@ def features(rank, world, lr):
     del ERRS[:]
     ok = ok and good
     m.close(); s1.close()
+
+    # ---- bootstrap without a host call: lammps_open + script + the pre-run queries + lammps_step, as softParticleCloud::initLammps
+    # drives the reference (softParticleCloud.C:57-206); the bricks and the NCCL communicator come up by themselves
+    case = cases.settled_bed(columns=(3, 2), column="column_256x4.npz")
+    os.environ["SEDI_AUTO_COMM"] = "1"
+    a = sb.Lammps(device=lr)
+    cases.apply(case, a)
+    nglobal = a.get_global_n()
+    npr = a.get_initial_np(world)
+    info = a.get_initial_info()
+    dom = a.get_local_domain()
+    a.step(0)
+    os.environ.pop("SEDI_AUTO_COMM")
+    loc = a.get_local_info(); a.put_local_info(fd_bed(case)[loc["tag"] - 1], loc["tag"])
+    a.step(150)
+    ref = sb.Lammps(device=lr)
+    cases.apply(case, ref)
+    ref.step(0); ref.put_local_info(fd_bed(case), case["tag"]); ref.step(150)
+    inside = np.all((info["x"][:, 0] >= dom[0] - 1e-12) & (info["x"][:, 0] < dom[1] + 1e-12))
+    good = nglobal == len(case["tag"]) and int(npr.sum()) == nglobal and npr[rank] == len(info["tag"]) and a.comm_stat("links") > 0 and bool(inside)
+    good = _close(_gather(a, world), ref.atoms()) and good
+    flag = torch.tensor([1 if good else 0], device="cuda"); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    good = int(flag.item()) == 1
+    if rank == 0:
+        print("[mgpu bootstrap] lammps_open + script + initLammps queries on %d ranks, no sedi_comm_init: np = %s (%s) -> %s" % (world, npr.tolist(), "; ".join(ERRS), "OK" if good else "FAIL"), flush=True)
+    del ERRS[:]
+    ok = ok and good
+    a.close(); ref.close()
     return ok
 
 

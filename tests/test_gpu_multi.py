@@ -33,4 +33,4 @@ def test_two_gpu_parity_against_whole_box_oracle(halo):
                        timeout=900)
     sys.stdout.write(r.stdout[-4000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("-> OK") >= 8 and "FAIL" not in r.stdout
+    assert r.stdout.count("-> OK") >= 9 and "FAIL" not in r.stdout
