@@ -76,6 +76,7 @@ struct StepParams {
   int nve_groupbit;  // 0 = no integrator
   int freeze_groupbit;
   int periodic_any;
+  int equal_spheres;  // all spheres of the system have one radius and one mass: meff = m / 2, reff = r / 2 (host-checked, same on every rank)
   long long ntimestep;
   const D4 *posr_in, *velm_in, *omgt_in;
   D4 *posr_out, *velm_out, *omgt_out;
@@ -98,8 +99,10 @@ struct StepParams {
   int *ctrl;                  // [0] rebuild-needed flag, [1] steps completed, [2] error flags
   unsigned long long *counters;  // [0] directed pair visits, [1] directed touching pairs
   double dtv, dtf, dt_live, trigger_sq;
+  double c_dtfm, c_dtirot;   // equal_spheres: dtf / m and (dtf / 0.4) / (r r m) of the one particle class
   double kn, kt, gamman, gammat, xmu, beta;
   double prd[3];
+  double imglo[3], imghi[3];   // a row outside [imglo, imghi) in some dimension may have periodic-image list entries (+-inf where the GPU's box does not wrap)
   double lub_mu, lub_cutsq, lub_cut_inner, lub_R0, lub_RT0;
   // host-folded constants of the Hertz-Mindlin "Fix" law (pair_gran_hertzFix_history.cpp:192-236)
   double c_sn;     // 2/1.82 * kn              : sn = c_sn * polyhertz

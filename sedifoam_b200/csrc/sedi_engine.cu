@@ -25,6 +25,7 @@
 #include <chrono>
 #include <string>
 #include <vector>
+#include <limits>
 
 #include "../../include/sedi_b200.h"
 #include "../../include/lammps_shim/lammps.h"
@@ -213,6 +214,8 @@ class Engine {
   Pinned<unsigned long long> h_counters;
   BinParams bin;
   double cutneighmax;
+  double eq_radius, eq_mass;
+  int equal_spheres;   // every atom of the system has the same radius and mass (launch-uniform fast path of the pair law)
   double cutneighsq[(MAX_TYPES + 1) * (MAX_TYPES + 1)];
   double dt_init;
   double lub_R0, lub_RT0, lub_RS0;
@@ -265,7 +268,7 @@ class Engine {
 
   Engine()
       : device(0), dev_ready(false), loaded(false), setup_done(false), params_dirty(true), cell_valid(false), stream(0), n(0),
-        nlocal(0), nghost(0), npad(0), maxtag(0), cur(0), icur(0), ecur(0), cutneighmax(0), dt_init(0), lub_R0(0), lub_RT0(0), lub_RS0(0),
+        nlocal(0), nghost(0), npad(0), maxtag(0), cur(0), icur(0), ecur(0), cutneighmax(0), eq_radius(0), eq_mass(0), equal_spheres(0), dt_init(0), lub_R0(0), lub_RT0(0), lub_RS0(0),
         beta_pair(0), pair_evals_unique(0), nbuilds(0), pair_evals(0), steps_done(0), launches(0), list_gran_dir(0), list_type_dir(0), list_gran_img(0),
         list_type_img(0), chunk(50), last_step_ms(0), count_in_kernel(false), have_mesh(false), ncells(0), have_DDtU(false),
         have_curlU(false), have_gradp(false), have_Uf(false), drag_model(0), force_flags(SEDI_FORCE_DRAG | SEDI_FORCE_PGRAD), nub(1e-6), rhob(1000.0),
@@ -487,6 +490,19 @@ class Engine {
       }
     cutneighmax = cutmax + cfg().skin;
     if (!(cutneighmax > 0.0)) cutneighmax = std::max(cfg().skin, 1e-30);
+    // monodisperse system?  (same decision on every rank: the pair law's equal-sphere branch must be taken by both owners of a pair)
+    {
+      const double inf = std::numeric_limits<double>::infinity();
+      double mm[4] = {-inf, -inf, -inf, -inf};   // max r, max -r, max m, max -m
+      for (size_t i = 0; i < a.size(); i++) {
+        mm[0] = std::max(mm[0], a.radius[i]); mm[1] = std::max(mm[1], -a.radius[i]);
+        mm[2] = std::max(mm[2], a.rmass[i]); mm[3] = std::max(mm[3], -a.rmass[i]);
+      }
+      comm.allreduce_max_host(mm, 4);
+      equal_spheres = (mm[0] == -mm[1] && mm[2] == -mm[3] && mm[0] > 0.0 && mm[2] > 0.0) ? 1 : 0;
+      if (getenv("SEDI_NO_EQUAL_SPHERES")) equal_spheres = 0;
+      eq_radius = mm[0]; eq_mass = mm[2];
+    }
   }
 
   bool want_type_list() const {
@@ -540,9 +556,14 @@ class Engine {
     P.n = n; P.npad = ell[ecur].npad; P.nfix = (int)c.fixes.size(); P.pair = c.pair;
     P.lub_enabled = c.lub.enabled; P.lub_flaglog = c.lub.flaglog; P.lub_flagfld = c.lub.flagfld; P.lub_flagHI = c.lub.flagHI;
     P.freeze_groupbit = c.freeze_group_bit;
+    P.equal_spheres = equal_spheres;
     P.periodic_any = c.periodic[0] | c.periodic[1] | c.periodic[2];
     P.dtv = dt_init; P.dtf = 0.5 * dt_init; P.dt_live = c.dt;
     P.trigger_sq = 0.25 * c.skin * c.skin;
+    if (equal_spheres) {   // nve/sphere factors of the one particle class, with the reference's own expressions (EXTERNAL FixNVESphere)
+      P.c_dtfm = P.dtf / eq_mass;
+      P.c_dtirot = (P.dtf / 0.4) / (eq_radius * eq_radius * eq_mass);
+    }
     P.kn = c.gran.kn; P.kt = c.gran.kt; P.gamman = c.gran.gamman; P.gammat = c.gran.gammat; P.xmu = c.gran.xmu;
     P.beta = (c.pair == PAIR_HERTZFIX_HISTORY) ? fix_beta(c.gran.gamman) : 0.0;
     {  // loop invariants of the Hertz-Mindlin "Fix" law, folded once (see hertzfix_fast)
@@ -555,6 +576,12 @@ class Engine {
       P.c_ekt = (P.kt != 0.0) ? 8.0 / (8.84 * P.kt) : 0.0;
     }
     for (int d = 0; d < 3; d++) P.prd[d] = c.boxhi[d] - c.boxlo[d];
+    for (int d = 0; d < 3; d++) {
+      const double inf = std::numeric_limits<double>::infinity();
+      const double band = cutneighmax + c.skin;   // list cut-off + the most a particle moves between two list builds
+      P.imglo[d] = comm.wraps(c, d) ? c.boxlo[d] + band : -inf;
+      P.imghi[d] = comm.wraps(c, d) ? c.boxhi[d] - band : inf;
+    }
     for (int img = 0; img < 27; img++) {
       const int ix = img % 3 - 1, iy = (img / 3) % 3 - 1, iz = img / 9 - 1;
       P.imgshift[img][0] = ix * P.prd[0]; P.imgshift[img][1] = iy * P.prd[1]; P.imgshift[img][2] = iz * P.prd[2];
@@ -634,11 +661,16 @@ class Engine {
 #else
       const int sb = std::max(1, cdiv(nlocal, ST));
 #endif
+      // 32-bit row masks when no row has more than 32 granular slots (SEDI_SELL_M32=0 forces the 64-bit form)
+      static const bool allow32 = !(getenv("SEDI_SELL_M32") && atoi(getenv("SEDI_SELL_M32")) == 0);
+      const bool m32 = allow32 && P.hcap <= 32;
+#define SEDI_LAUNCH_SELL3(PK, PB, TL)                                                                         \
+  do { if (m32) k_step_sell<PK, PB, TL, true><<<sb, ST, 0, stream>>>(P, seq); else k_step_sell<PK, PB, TL, false><<<sb, ST, 0, stream>>>(P, seq); } while (0)
 #define SEDI_LAUNCH_SELL(PK)                                                                                  \
   do {                                                                                                        \
-    if (P.lub_enabled) { if (pbc) k_step_sell<PK, true, 2><<<sb, ST, 0, stream>>>(P, seq); else k_step_sell<PK, false, 2><<<sb, ST, 0, stream>>>(P, seq); } \
-    else if (tl) { if (pbc) k_step_sell<PK, true, 1><<<sb, ST, 0, stream>>>(P, seq); else k_step_sell<PK, false, 1><<<sb, ST, 0, stream>>>(P, seq); } \
-    else { if (pbc) k_step_sell<PK, true, 0><<<sb, ST, 0, stream>>>(P, seq); else k_step_sell<PK, false, 0><<<sb, ST, 0, stream>>>(P, seq); } \
+    if (P.lub_enabled) { if (pbc) SEDI_LAUNCH_SELL3(PK, true, 2); else SEDI_LAUNCH_SELL3(PK, false, 2); }    \
+    else if (tl) { if (pbc) SEDI_LAUNCH_SELL3(PK, true, 1); else SEDI_LAUNCH_SELL3(PK, false, 1); }          \
+    else { if (pbc) SEDI_LAUNCH_SELL3(PK, true, 0); else SEDI_LAUNCH_SELL3(PK, false, 0); }                  \
   } while (0)
       switch (cfg().pair) {
         case PAIR_HERTZFIX_HISTORY: SEDI_LAUNCH_SELL(PAIR_HERTZFIX_HISTORY); break;
@@ -646,6 +678,7 @@ class Engine {
         default: SEDI_LAUNCH_SELL(PAIR_HOOKE); break;
       }
 #undef SEDI_LAUNCH_SELL
+#undef SEDI_LAUNCH_SELL3
       launches++;
       return;
     }
@@ -735,9 +768,15 @@ class Engine {
     if (sorted_rows) {
       order2.ensure(npad); crow.ensure(npad);
       Ell &Lprev = ell[ecur];
+      ImgBand band;
+      for (int d = 0; d < 3; d++) {
+        const double inf = std::numeric_limits<double>::infinity(), bw = cutneighmax + cfg().skin;
+        band.lo[d] = comm.wraps(cfg(), d) ? cfg().boxlo[d] + bw : -inf;
+        band.hi[d] = comm.wraps(cfg(), d) ? cfg().boxhi[d] - bw : inf;
+      }
       k_window_sort<<<cdiv(nlocal_new, SELL_WINDOW), SELL_WINDOW, 0, stream>>>(nlocal_new, order.p, Lprev.valid ? Lprev.tmask.p : (const unsigned long long *)0,
                                                                                Lprev.valid ? Lprev.nn.p : (const int *)0,
-                                                                               (Lprev.valid && want_type_list()) ? Lprev.nt.p : (const int *)0, nlocal, order2.p, crow.p);
+                                                                               (Lprev.valid && want_type_list()) ? Lprev.nt.p : (const int *)0, nlocal, order2.p, crow.p, posr[cur].p, band);
       launches++;
       ord = order2.p;
     }
