@@ -102,7 +102,6 @@ struct StepParams {
   double c_dtfm, c_dtirot;   // equal_spheres: dtf / m and (dtf / 0.4) / (r r m) of the one particle class
   double kn, kt, gamman, gammat, xmu, beta;
   double prd[3];
-  double imglo[3], imghi[3];   // a row outside [imglo, imghi) in some dimension may have periodic-image list entries (+-inf where the GPU's box does not wrap)
   double lub_mu, lub_cutsq, lub_cut_inner, lub_R0, lub_RT0;
   // host-folded constants of the Hertz-Mindlin "Fix" law (pair_gran_hertzFix_history.cpp:192-236)
   double c_sn;     // 2/1.82 * kn              : sn = c_sn * polyhertz

@@ -576,12 +576,6 @@ class Engine {
       P.c_ekt = (P.kt != 0.0) ? 8.0 / (8.84 * P.kt) : 0.0;
     }
     for (int d = 0; d < 3; d++) P.prd[d] = c.boxhi[d] - c.boxlo[d];
-    for (int d = 0; d < 3; d++) {
-      const double inf = std::numeric_limits<double>::infinity();
-      const double band = cutneighmax + c.skin;   // list cut-off + the most a particle moves between two list builds
-      P.imglo[d] = comm.wraps(c, d) ? c.boxlo[d] + band : -inf;
-      P.imghi[d] = comm.wraps(c, d) ? c.boxhi[d] - band : inf;
-    }
     for (int img = 0; img < 27; img++) {
       const int ix = img % 3 - 1, iy = (img / 3) % 3 - 1, iz = img / 9 - 1;
       P.imgshift[img][0] = ix * P.prd[0]; P.imgshift[img][1] = iy * P.prd[1]; P.imgshift[img][2] = iz * P.prd[2];
@@ -768,15 +762,9 @@ class Engine {
     if (sorted_rows) {
       order2.ensure(npad); crow.ensure(npad);
       Ell &Lprev = ell[ecur];
-      ImgBand band;
-      for (int d = 0; d < 3; d++) {
-        const double inf = std::numeric_limits<double>::infinity(), bw = cutneighmax + cfg().skin;
-        band.lo[d] = comm.wraps(cfg(), d) ? cfg().boxlo[d] + bw : -inf;
-        band.hi[d] = comm.wraps(cfg(), d) ? cfg().boxhi[d] - bw : inf;
-      }
       k_window_sort<<<cdiv(nlocal_new, SELL_WINDOW), SELL_WINDOW, 0, stream>>>(nlocal_new, order.p, Lprev.valid ? Lprev.tmask.p : (const unsigned long long *)0,
                                                                                Lprev.valid ? Lprev.nn.p : (const int *)0,
-                                                                               (Lprev.valid && want_type_list()) ? Lprev.nt.p : (const int *)0, nlocal, order2.p, crow.p, posr[cur].p, band);
+                                                                               (Lprev.valid && want_type_list()) ? Lprev.nt.p : (const int *)0, nlocal, order2.p, crow.p);
       launches++;
       ord = order2.p;
     }

@@ -24,7 +24,6 @@
 //             warp busy, force / torque accumulate in registers.  No shared memory, no atomics, bitwise deterministic;
 //   epilogue  step_epilogue<> (fixes in script order, final + initial integrate, skin/2 trigger).
 #pragma once
-#include <type_traits>
 #include "sedi_step.cuh"
 
 namespace sedi {
@@ -42,9 +41,6 @@ namespace sedi {
 #define SEDI_SELL_SPEC 1   // 1 (history styles): phase 1 tests only the entries that did NOT overlap one sub-step ago; the entries that did go straight
                            // to phase 2, which repeats the overlap test with the operands it gathers anyway.  Halves the position gathers of phase 1,
                            // removes its second round trip, and the first contact's operands are requested together with the phase-1 positions
-#endif
-#ifndef SEDI_SELL_PP
-#define SEDI_SELL_PP 0     // 1: phase 2 alternates between two operand sets instead of copying next -> current after every contact
 #endif
 #ifndef SEDI_SELL_MONO
 #define SEDI_SELL_MONO 1   // 1: equal-sphere pairs take meff = m / 2, reff = r / 2 directly
@@ -64,10 +60,8 @@ static const int SELL_WINDOW = SEDI_SELL_WINDOW;   // sigma of SELL-C-sigma: row
 // order[k]  : canonical (bin-ordered) position k -> old row            (input, from the counting sort)
 // order2[r] : physical new row r -> old row                             (what the permutation kernels and the history re-attachment use)
 // crow[k]   : canonical position k -> physical new row                  (how the list build reaches the rows of a bin)
-struct ImgBand { double lo[3], hi[3]; };   // rows outside [lo, hi) in some dimension can have periodic-image entries (StepParams::imglo / imghi)
 __global__ void __launch_bounds__(SELL_WINDOW) k_window_sort(int n, const int *order, const unsigned long long *tmask_old, const int *nn_old,
-                                                             const int *nt_old, int nrows_old, int *order2, int *crow, const D4 *posr_old,
-                                                             const ImgBand band) {
+                                                             const int *nt_old, int nrows_old, int *order2, int *crow) {
   __shared__ unsigned s[SELL_WINDOW];
   const int t = threadIdx.x;
   const int k = blockIdx.x * SELL_WINDOW + t;
@@ -86,10 +80,6 @@ __global__ void __launch_bounds__(SELL_WINDOW) k_window_sort(int n, const int *o
       }
     }
     comp = ((4095u - key) << 10) | (unsigned)t;   // heavy rows first; ties keep the bin order (the composite is unique)
-    if (posr_old) {   // rows near a periodic face of this GPU's box go to the end of the window: warps of their own (see sell_row)
-      const D4 p = posr_old[o];
-      if (p.x < band.lo[0] || p.x >= band.hi[0] || p.y < band.lo[1] || p.y >= band.hi[1] || p.z < band.lo[2] || p.z >= band.hi[2]) comp |= (1u << 22);
-    }
   }
   s[t] = comp;
   __syncthreads();
@@ -126,14 +116,6 @@ __device__ __forceinline__ void apply_image(const StepParams &P, const int img, 
 #else
   pj.x = pj.x + P.imgshift[img][0]; pj.y = pj.y + P.imgshift[img][1]; pj.z = pj.z + P.imgshift[img][2];
 #endif
-}
-
-#ifndef SEDI_SELL_IMGSPLIT
-#define SEDI_SELL_IMGSPLIT 1
-#endif
-// can this row have periodic-image list entries?  (conservative, geometric; the same test keys the window sort)
-__device__ __forceinline__ bool near_periodic_face(const StepParams &P, const D4 &p) {
-  return p.x < P.imglo[0] || p.x >= P.imghi[0] || p.y < P.imglo[1] || p.y >= P.imghi[1] || p.z < P.imglo[2] || p.z >= P.imghi[2];
 }
 
 // contact / candidate masks of a row: 32-bit when every row of the list has at most 32 granular slots (launch-uniform, the usual case:
@@ -198,234 +180,202 @@ __device__ __forceinline__ void sell_row(const StepParams &P, const int seq, con
     for (int k = 8; k < 16; k++) if (k < nni) prefetch_l1(&P.posr_in[e16[k] & NB_IDX_MASK]);   // second gather batch: lines on their way while the first is tested
   }
 
-  // ---- periodic-image handling is compiled in only for the warps that can have image entries: the rows within one neighbour cut-off
-  // (+ skin, the most a particle moves between two list builds) of a periodic face of this GPU's box.  The window sort puts those rows
-  // into warps of their own, so the other warps run the sweep without the image decode / shift (SEDI_SELL_IMGSPLIT)
-  bool rowimg = PBC;
-#if SEDI_SELL_IMGSPLIT
-  if (PBC) rowimg = near_periodic_face(P, pi);
-#endif
-  auto body = [&](auto IMGC) {
-    constexpr bool IMG = decltype(IMGC)::value;
-    // ---- the pieces of the pair sweep
-    mask_t touch = 0;
-    // distance test of one list entry (pair :131 `rsq >= radsum*radsum` -> no contact)
-    auto test_entry = [&](const unsigned e, const D4 &pj_in, const int s, mask_t &mask) {
-      if (!(e & NB_FLAG_GRAN)) return;
-      D4 pj = pj_in;
-      const int img = (int)((e >> NB_IMG_SHIFT) & 31u);
-      if (IMG && img != NB_IMG_NONE) apply_image(P, img, pj);
-      const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
-      const double rsq = delx * delx + dely * dely + delz * delz;
-      const double radsum = radi + pj.w;
-      if (rsq < radsum * radsum) mask |= (ONE << s);
-    };
-    const bool shearupdate = (P.mode != MODE_SETUP);
-    HzCoef hc; hc.c_sn = P.c_sn; hc.c_ccel = P.c_ccel; hc.c_damp = P.c_damp; hc.c_kts = P.c_kts; hc.c_ctd = P.c_ctd; hc.c_ekt = P.c_ekt; hc.xmu = P.xmu;
-    GranCoef gc; gc.kn = P.kn; gc.kt = P.kt; gc.gamman = P.gamman; gc.gammat = P.gammat; gc.xmu = P.xmu; gc.beta = P.beta;
-    double fx = 0.0, fy = 0.0, fz = 0.0, tx = 0.0, ty = 0.0, tz = 0.0;   // pair accumulators (force_clear)
-    auto list_word = [&](const int sl) -> unsigned { return sl < 16 ? s_e[sl][tid] : ld_nc_u32(&P.nbr[(size_t)sl * P.npad + i]); };
-    // gathers of one overlapping entry: partner position / velocity / spin and the history quad of the slot
-    struct Opnd { D4 pj, vj, wj; double h0, h1, h2; };
-    auto gather = [&](const unsigned ew, const int sl, Opnd &o) {
-      const int j = (int)(ew & NB_IDX_MASK);
-      o.pj = ldg_d4(&P.posr_in[j]);
-      o.vj = ldg_d4(&P.velm_in[j]);
-      o.wj = ldg_d4(&P.omgt_in[j]);
-      o.h0 = o.h1 = o.h2 = 0.0;
-      if (HIST && ((tm_old >> sl) & ONE)) { const D4 h = ld_d4(&P.shear[(size_t)sl * P.npad + i]); o.h0 = h.x; o.h1 = h.y; o.h2 = h.z; }
-    };
-    // overlap test (the reference's own, pair :131), contact law, history write-back, accumulation for one entry whose operands
-    // have been gathered; false: the spheres do not overlap (an entry that did one sub-step ago: its history is dropped with the bit)
-    auto evaluate = [&](const unsigned ew, const int sl, const Opnd &o) -> bool {
-      D4 pj = o.pj;
-      const int img = (int)((ew >> NB_IMG_SHIFT) & 31u);
-      if (IMG && img != NB_IMG_NONE) apply_image(P, img, pj);
-      const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
-      const double rsq = delx * delx + dely * dely + delz * delz;
-      const double radj = pj.w, mj = o.vj.w;
-      const double radsum = radi + radj;
-      if (!(rsq < radsum * radsum)) return false;
-      const int maskj = bits_mask((unsigned long long)__double_as_longlong(o.wj.w));
-      double meff, reff = 0.0;
-      if (PAIR == PAIR_HERTZFIX_HISTORY) {
-        // monodisperse system (launch-uniform, decided on the host for the whole system, so both directed evaluations of every
-        // pair take the same branch): m m / (2 m) and r r / (2 r) without the two divisions
-        if (SEDI_SELL_MONO && P.equal_spheres) { meff = 0.5 * mi; reff = 0.5 * radi; }
-        else { meff = div_nr(mi * mj, mi + mj); reff = div_nr(radi * radj, radsum); }
-      } else meff = (mi * mj) / (mi + mj);
-      if (maski & P.freeze_groupbit) meff = mj;
-      if (maskj & P.freeze_groupbit) meff = mi;
-      const double vrx = vi.x - o.vj.x, vry = vi.y - o.vj.y, vrz = vi.z - o.vj.z;
-      const double wsx = radi * wi.x + radj * o.wj.x, wsy = radi * wi.y + radj * o.wj.y, wsz = radi * wi.z + radj * o.wj.z;
-      double s0 = o.h0, s1 = o.h1, s2 = o.h2, fox, foy, foz, tox, toy, toz;
-      if (PAIR == PAIR_HERTZFIX_HISTORY) {
-        hertzfix_fast(delx, dely, delz, rsq, vrx, vry, vrz, wsx, wsy, wsz, meff, radsum, reff, hc, P.dtv, shearupdate,
-                      s0, s1, s2, fox, foy, foz, tox, toy, toz);
-      } else {
-        V3 vr = {vrx, vry, vrz}, ws = {wsx, wsy, wsz}, sh = {s0, s1, s2}, fo, to;
-        if (PAIR == PAIR_HOOKE_HISTORY) hooke_history_contact(delx, dely, delz, rsq, vr, ws, meff, radsum, gc, P.dtv, shearupdate, sh, fo, to);
-        else hooke_contact(delx, dely, delz, rsq, vr, ws, meff, radsum, gc, fo, to);
-        s0 = sh.x; s1 = sh.y; s2 = sh.z; fox = fo.x; foy = fo.y; foz = fo.z; tox = to.x; toy = to.y; toz = to.z;
-      }
-      if (HIST) { D4 h; h.x = s0; h.y = s1; h.z = s2; h.w = 0.0; st_d4(&P.shear[(size_t)sl * P.npad + i], h); }
-      // reference: f[i] += F ; torque[i] -= radi * tor   (pair :259-271)
-      fx += fox; fy += foy; fz += foz;
-      tx -= radi * tox; ty -= radi * toy; tz -= radi * toz;
-      return true;
-    };
-
-    mask_t m;   // entries handed to phase 2
-    int s = 0;
-    unsigned e = 0u;
-    Opnd cur;
-    bool have_cur = false;
-    if (HIST && SEDI_SELL_SPEC) {
-      // ---- phase 1, history styles: an entry that overlapped one sub-step ago (bit of tm_old) almost surely still does -- it goes to phase 2
-      // untested (evaluate() repeats the reference's test on the operands it gathers anyway, so the result is the same set); only the other
-      // entries of the row are tested here, four partner positions in flight at a time, and the operands of the first old contact are
-      // requested in the same round trip.
-      const mask_t valid = nni >= MBITS ? ~(mask_t)0 : ((ONE << nni) - ONE);
-      const mask_t m_old = tm_old & valid;
-      if (m_old) { s = mask_ffs(m_old); e = list_word(s); gather(e, s, cur); have_cur = true; }
-      mask_t cand = valid & ~tm_old, m_new = 0;
-      while (cand) {
-        int sl[SEDI_SELL_P1B];
-        unsigned ew[SEDI_SELL_P1B];
-        D4 pp[SEDI_SELL_P1B];
-  #pragma unroll
-        for (int k = 0; k < SEDI_SELL_P1B; k++) {
-          sl[k] = 0; ew[k] = 0u;
-          if (cand) { sl[k] = mask_ffs(cand); cand &= cand - 1; ew[k] = list_word(sl[k]); }
-        }
-  #pragma unroll
-        for (int k = 0; k < SEDI_SELL_P1B; k++) pp[k] = ldg_d4(&P.posr_in[ew[k] & NB_IDX_MASK]);
-  #pragma unroll
-        for (int k = 0; k < SEDI_SELL_P1B; k++) test_entry(ew[k], pp[k], sl[k], m_new);
-      }
-      m = m_old | m_new;
-      if (m) {
-        const int sf = mask_ffs(m);
-        if (!have_cur || sf != s) { s = sf; e = list_word(s); gather(e, s, cur); have_cur = true; }   // a new contact in front of the first old one (rare)
-      }
-    } else {
-      // ---- phase 1: which list entries overlap
-  #pragma unroll
-      for (int b = 0; b < 16; b += 8) {
-        if (b < nni) {
-          D4 p8[8];
-  #pragma unroll
-          for (int k = 0; k < 8; k++) p8[k] = ldg_d4(&P.posr_in[e16[b + k] & NB_IDX_MASK]);
-  #pragma unroll
-          for (int k = 0; k < 8; k++) test_entry(e16[b + k], p8[k], b + k, touch);
-        }
-      }
-      for (int sb = 16; sb < nni; sb += 4) {   // long rows (large skin)
-        unsigned e4[4];
-        D4 p4[4];
-  #pragma unroll
-        for (int k = 0; k < 4; k++) e4[k] = (sb + k < nni) ? ld_nc_u32(&P.nbr[(size_t)(sb + k) * P.npad + i]) : 0u;
-  #pragma unroll
-        for (int k = 0; k < 4; k++) p4[k] = ldg_d4(&P.posr_in[e4[k] & NB_IDX_MASK]);
-  #pragma unroll
-        for (int k = 0; k < 4; k++) test_entry(e4[k], p4[k], sb + k, touch);
-      }
-      m = touch; touch = 0;
-      if (m) { s = mask_ffs(m); e = list_word(s); gather(e, s, cur); }
-    }
-
-    // ---- phase 2: the (presumably) overlapping entries, in slot order; the rows of a warp have (nearly) the same number of them.
-    // Register double buffer: the operands of the next entry are gathered while this one is evaluated.
-  #if SEDI_SELL_PP
-    // two operand sets used alternately (no register-to-register copy of the 30-register set per contact)
-    if (m) {
-      Opnd alt;
-      int sa = 0;
-      unsigned ea = 0u;
-      while (true) {
-        m &= m - 1;
-        if (m) { sa = mask_ffs(m); ea = list_word(sa); gather(ea, sa, alt); }
-        if (evaluate(e, s, cur)) touch |= (ONE << s);
-        if (!m) break;
-        m &= m - 1;
-        if (m) { s = mask_ffs(m); e = list_word(s); gather(e, s, cur); }
-        if (evaluate(ea, sa, alt)) touch |= (ONE << sa);
-        if (!m) break;
-      }
-    }
-  #else
-    if (m) {
-      while (true) {
-        m &= m - 1;
-        if (!m) { if (evaluate(e, s, cur)) touch |= (ONE << s); break; }
-        const int sn = mask_ffs(m);
-        const unsigned en = list_word(sn);
-        Opnd nxt;
-        gather(en, sn, nxt);
-        if (evaluate(e, s, cur)) touch |= (ONE << s);
-        cur = nxt; s = sn; e = en;
-      }
-    }
-  #endif
-    if (HIST && touch != tm_old) P.tmask[i] = (unsigned long long)touch;
-
-    // ---- phase T (TYPELIST): fix cohesive / pair lubricate/poly over the entries of the type-cut-off list -- the granular segment
-    // [0, nni) and the type-only segment [hcap, hcap + nti) --, four partner positions in flight at a time.  Rows of a warp have
-    // (nearly) the same length, so the per-lane walk keeps the lanes busy.
-    double lfx = 0.0, lfy = 0.0, lfz = 0.0, ltx = 0.0, lty = 0.0, ltz = 0.0;  // lubricate/poly
-    double cfx = 0.0, cfy = 0.0, cfz = 0.0;                               // fix cohesive
-    if (TYPELIST) {
-      const CoheCoef co = cohesive_coef<(TYPELIST != 0)>(P);
-      const int tagi = bits_tag((unsigned long long)__double_as_longlong(wi.w));
-      const int ntot = nni + nti;
-      const double inv_radi = 1.0 / radi;
-      for (int sb = 0; sb < ntot; sb += 4) {
-        unsigned e4[4];
-        D4 p4[4];
-  #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int q = sb + k;
-          e4[k] = (q < ntot) ? (q < nni ? list_word(q) : ld_nc_u32(&P.nbr[(size_t)(P.hcap + (q - nni)) * P.npad + i])) : 0u;
-        }
-  #pragma unroll
-        for (int k = 0; k < 4; k++) p4[k] = ldg_d4(&P.posr_in[e4[k] & NB_IDX_MASK]);
-  #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const unsigned ew = e4[k];
-          if (!(ew & NB_FLAG_TYPE)) continue;
-          D4 pj = p4[k];
-          const int img = (int)((ew >> NB_IMG_SHIFT) & 31u);
-          if (IMG && img != NB_IMG_NONE) apply_image(P, img, pj);
-          const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
-          const double rsq = delx * delx + dely * dely + delz * delz;
-          const double radj = pj.w;
-          const double radsum = radi + radj;
-          const int j = (int)(ew & NB_IDX_MASK);
-          if (P.has_cohesive) cohesive_entry_fast(P, co, j, img, tagi, maski, radsum, rsq, delx, dely, delz, cfx, cfy, cfz);
-          if (TYPELIST == 2 && P.lub_enabled && P.lub_flagHI && rsq < P.lub_cutsq) lubricate_entry_fast(P, j, pi, vi, wi, inv_radi, radj, rsq, delx, dely, delz, lfx, lfy, lfz, ltx, lty, ltz);
-        }
-      }
-      if (TYPELIST == 2 && P.lub_enabled) {  // isotropic FLD terms (:213-221) are applied before the pair terms in the reference
-        double ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
-        if (P.lub_flagfld) {
-          ax -= P.lub_R0 * radi * vi.x; ay -= P.lub_R0 * radi * vi.y; az -= P.lub_R0 * radi * vi.z;
-          const double radi3 = radi * radi * radi;
-          bx -= P.lub_RT0 * radi3 * wi.x; by -= P.lub_RT0 * radi3 * wi.y; bz -= P.lub_RT0 * radi3 * wi.z;
-        }
-        fx += ax + lfx; fy += ay + lfy; fz += az + lfz;
-        tx += bx + ltx; ty += by + lty; tz += bz + ltz;
-      }
-    }
-    double fd0 = 0.0, fd1 = 0.0, fd2 = 0.0, xh0 = 0.0, xh1 = 0.0, xh2 = 0.0;
-    if (P.has_fdrag) { fd0 = ld_nc_f64(&P.fdrag[0][i]); fd1 = ld_nc_f64(&P.fdrag[1][i]); fd2 = ld_nc_f64(&P.fdrag[2][i]); }
-    if (P.mode == MODE_FUSED) { xh0 = ld_nc_f64(&P.xhold[0][i]); xh1 = ld_nc_f64(&P.xhold[1][i]); xh2 = ld_nc_f64(&P.xhold[2][i]); }
-    step_epilogue<PAIR, (TYPELIST != 0)>(P, i, seq, pi, vi, wi, fx, fy, fz, tx, ty, tz, cfx, cfy, cfz, fd0, fd1, fd2, xh0, xh1, xh2, (unsigned long long)touch);
+  // ---- the pieces of the pair sweep
+  mask_t touch = 0;
+  // distance test of one list entry (pair :131 `rsq >= radsum*radsum` -> no contact)
+  auto test_entry = [&](const unsigned e, const D4 &pj_in, const int s, mask_t &mask) {
+    if (!(e & NB_FLAG_GRAN)) return;
+    D4 pj = pj_in;
+    const int img = (int)((e >> NB_IMG_SHIFT) & 31u);
+    if (PBC && img != NB_IMG_NONE) apply_image(P, img, pj);
+    const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
+    const double rsq = delx * delx + dely * dely + delz * delz;
+    const double radsum = radi + pj.w;
+    if (rsq < radsum * radsum) mask |= (ONE << s);
   };
-#if SEDI_SELL_IMGSPLIT
-  if (PBC && __any_sync(__activemask(), rowimg)) body(std::true_type()); else body(std::false_type());
-#else
-  if (PBC) body(std::true_type()); else body(std::false_type());
-#endif
+  const bool shearupdate = (P.mode != MODE_SETUP);
+  HzCoef hc; hc.c_sn = P.c_sn; hc.c_ccel = P.c_ccel; hc.c_damp = P.c_damp; hc.c_kts = P.c_kts; hc.c_ctd = P.c_ctd; hc.c_ekt = P.c_ekt; hc.xmu = P.xmu;
+  GranCoef gc; gc.kn = P.kn; gc.kt = P.kt; gc.gamman = P.gamman; gc.gammat = P.gammat; gc.xmu = P.xmu; gc.beta = P.beta;
+  double fx = 0.0, fy = 0.0, fz = 0.0, tx = 0.0, ty = 0.0, tz = 0.0;   // pair accumulators (force_clear)
+  auto list_word = [&](const int sl) -> unsigned { return sl < 16 ? s_e[sl][tid] : ld_nc_u32(&P.nbr[(size_t)sl * P.npad + i]); };
+  // gathers of one overlapping entry: partner position / velocity / spin and the history quad of the slot
+  struct Opnd { D4 pj, vj, wj; double h0, h1, h2; };
+  auto gather = [&](const unsigned ew, const int sl, Opnd &o) {
+    const int j = (int)(ew & NB_IDX_MASK);
+    o.pj = ldg_d4(&P.posr_in[j]);
+    o.vj = ldg_d4(&P.velm_in[j]);
+    o.wj = ldg_d4(&P.omgt_in[j]);
+    o.h0 = o.h1 = o.h2 = 0.0;
+    if (HIST && ((tm_old >> sl) & ONE)) { const D4 h = ld_d4(&P.shear[(size_t)sl * P.npad + i]); o.h0 = h.x; o.h1 = h.y; o.h2 = h.z; }
+  };
+  // one entry in two stages.  prep(): everything that reads the gathered operands -- the reference's own overlap test (pair :131), relative
+  // velocity, summed spin, effective mass / radius, old history -- into a set of derived values; false: the spheres do not overlap (an
+  // entry that did one sub-step ago: its history is dropped with the bit).  contact(): contact law, history write-back, accumulation.
+  // Between the two the operand registers are free, so the next entry's gathers are issued straight into them (phase 2 below).
+  struct Drv { double delx, dely, delz, rsq, radsum, meff, reff, vrx, vry, vrz, wsx, wsy, wsz, s0, s1, s2; };
+  auto prep = [&](const unsigned ew, const Opnd &o, Drv &d) -> bool {
+    D4 pj = o.pj;
+    const int img = (int)((ew >> NB_IMG_SHIFT) & 31u);
+    if (PBC && img != NB_IMG_NONE) apply_image(P, img, pj);
+    d.delx = pi.x - pj.x; d.dely = pi.y - pj.y; d.delz = pi.z - pj.z;
+    d.rsq = d.delx * d.delx + d.dely * d.dely + d.delz * d.delz;
+    const double radj = pj.w, mj = o.vj.w;
+    d.radsum = radi + radj;
+    const int maskj = bits_mask((unsigned long long)__double_as_longlong(o.wj.w));
+    d.reff = 0.0;
+    if (PAIR == PAIR_HERTZFIX_HISTORY) {
+      // monodisperse system (launch-uniform, decided on the host for the whole system, so both directed evaluations of every
+      // pair take the same branch): m m / (2 m) and r r / (2 r) without the two divisions
+      if (SEDI_SELL_MONO && P.equal_spheres) { d.meff = 0.5 * mi; d.reff = 0.5 * radi; }
+      else { d.meff = div_nr(mi * mj, mi + mj); d.reff = div_nr(radi * radj, d.radsum); }
+    } else d.meff = (mi * mj) / (mi + mj);
+    if (maski & P.freeze_groupbit) d.meff = mj;
+    if (maskj & P.freeze_groupbit) d.meff = mi;
+    d.vrx = vi.x - o.vj.x; d.vry = vi.y - o.vj.y; d.vrz = vi.z - o.vj.z;
+    d.wsx = radi * wi.x + radj * o.wj.x; d.wsy = radi * wi.y + radj * o.wj.y; d.wsz = radi * wi.z + radj * o.wj.z;
+    d.s0 = o.h0; d.s1 = o.h1; d.s2 = o.h2;
+    return d.rsq < d.radsum * d.radsum;
+  };
+  auto contact = [&](const int sl, const Drv &d) {
+    double s0 = d.s0, s1 = d.s1, s2 = d.s2, fox, foy, foz, tox, toy, toz;
+    if (PAIR == PAIR_HERTZFIX_HISTORY) {
+      hertzfix_fast(d.delx, d.dely, d.delz, d.rsq, d.vrx, d.vry, d.vrz, d.wsx, d.wsy, d.wsz, d.meff, d.radsum, d.reff, hc, P.dtv, shearupdate,
+                    s0, s1, s2, fox, foy, foz, tox, toy, toz);
+    } else {
+      V3 vr = {d.vrx, d.vry, d.vrz}, ws = {d.wsx, d.wsy, d.wsz}, sh = {s0, s1, s2}, fo, to;
+      if (PAIR == PAIR_HOOKE_HISTORY) hooke_history_contact(d.delx, d.dely, d.delz, d.rsq, vr, ws, d.meff, d.radsum, gc, P.dtv, shearupdate, sh, fo, to);
+      else hooke_contact(d.delx, d.dely, d.delz, d.rsq, vr, ws, d.meff, d.radsum, gc, fo, to);
+      s0 = sh.x; s1 = sh.y; s2 = sh.z; fox = fo.x; foy = fo.y; foz = fo.z; tox = to.x; toy = to.y; toz = to.z;
+    }
+    if (HIST) { D4 h; h.x = s0; h.y = s1; h.z = s2; h.w = 0.0; st_d4(&P.shear[(size_t)sl * P.npad + i], h); }
+    // reference: f[i] += F ; torque[i] -= radi * tor   (pair :259-271)
+    fx += fox; fy += foy; fz += foz;
+    tx -= radi * tox; ty -= radi * toy; tz -= radi * toz;
+  };
+
+  mask_t m;   // entries handed to phase 2
+  int s = 0;
+  unsigned e = 0u;
+  Opnd cur;
+  bool have_cur = false;
+  if (HIST && SEDI_SELL_SPEC) {
+    // ---- phase 1, history styles: an entry that overlapped one sub-step ago (bit of tm_old) almost surely still does -- it goes to phase 2
+    // untested (prep() repeats the reference's test on the operands it gathers anyway, so the result is the same set); only the other
+    // entries of the row are tested here, four partner positions in flight at a time, and the operands of the first old contact are
+    // requested in the same round trip.
+    const mask_t valid = nni >= MBITS ? ~(mask_t)0 : ((ONE << nni) - ONE);
+    const mask_t m_old = tm_old & valid;
+    if (m_old) { s = mask_ffs(m_old); e = list_word(s); gather(e, s, cur); have_cur = true; }
+    mask_t cand = valid & ~tm_old, m_new = 0;
+    while (cand) {
+      int sl[SEDI_SELL_P1B];
+      unsigned ew[SEDI_SELL_P1B];
+      D4 pp[SEDI_SELL_P1B];
+#pragma unroll
+      for (int k = 0; k < SEDI_SELL_P1B; k++) {
+        sl[k] = 0; ew[k] = 0u;
+        if (cand) { sl[k] = mask_ffs(cand); cand &= cand - 1; ew[k] = list_word(sl[k]); }
+      }
+#pragma unroll
+      for (int k = 0; k < SEDI_SELL_P1B; k++) pp[k] = ldg_d4(&P.posr_in[ew[k] & NB_IDX_MASK]);
+#pragma unroll
+      for (int k = 0; k < SEDI_SELL_P1B; k++) test_entry(ew[k], pp[k], sl[k], m_new);
+    }
+    m = m_old | m_new;
+    if (m) {
+      const int sf = mask_ffs(m);
+      if (!have_cur || sf != s) { s = sf; e = list_word(s); gather(e, s, cur); have_cur = true; }   // a new contact in front of the first old one (rare)
+    }
+  } else {
+    // ---- phase 1: which list entries overlap
+#pragma unroll
+    for (int b = 0; b < 16; b += 8) {
+      if (b < nni) {
+        D4 p8[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) p8[k] = ldg_d4(&P.posr_in[e16[b + k] & NB_IDX_MASK]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) test_entry(e16[b + k], p8[k], b + k, touch);
+      }
+    }
+    for (int sb = 16; sb < nni; sb += 4) {   // long rows (large skin)
+      unsigned e4[4];
+      D4 p4[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) e4[k] = (sb + k < nni) ? ld_nc_u32(&P.nbr[(size_t)(sb + k) * P.npad + i]) : 0u;
+#pragma unroll
+      for (int k = 0; k < 4; k++) p4[k] = ldg_d4(&P.posr_in[e4[k] & NB_IDX_MASK]);
+#pragma unroll
+      for (int k = 0; k < 4; k++) test_entry(e4[k], p4[k], sb + k, touch);
+    }
+    m = touch; touch = 0;
+    if (m) { s = mask_ffs(m); e = list_word(s); gather(e, s, cur); }
+  }
+
+  // ---- phase 2: the (presumably) overlapping entries, in slot order; the rows of a warp have (nearly) the same number of them.
+  // `cur` holds the gathered operands of entry (e, s).  They are consumed by prep(), the next entry's gathers are issued into the same
+  // registers, and the contact law runs on the derived values while those loads are in flight (no second operand set, no copies).
+  while (m) {
+    Drv d;
+    const bool ok = prep(e, cur, d);
+    const int sc = s;
+    m &= m - 1;
+    if (m) { s = mask_ffs(m); e = list_word(s); gather(e, s, cur); }
+    if (ok) { contact(sc, d); touch |= (ONE << sc); }
+  }
+  if (HIST && touch != tm_old) P.tmask[i] = (unsigned long long)touch;
+
+  // ---- phase T (TYPELIST): fix cohesive / pair lubricate/poly over the entries of the type-cut-off list -- the granular segment
+  // [0, nni) and the type-only segment [hcap, hcap + nti) --, four partner positions in flight at a time.  Rows of a warp have
+  // (nearly) the same length, so the per-lane walk keeps the lanes busy.
+  double lfx = 0.0, lfy = 0.0, lfz = 0.0, ltx = 0.0, lty = 0.0, ltz = 0.0;  // lubricate/poly
+  double cfx = 0.0, cfy = 0.0, cfz = 0.0;                               // fix cohesive
+  if (TYPELIST) {
+    const CoheCoef co = cohesive_coef<(TYPELIST != 0)>(P);
+    const int tagi = bits_tag((unsigned long long)__double_as_longlong(wi.w));
+    const int ntot = nni + nti;
+    const double inv_radi = 1.0 / radi;
+    for (int sb = 0; sb < ntot; sb += 4) {
+      unsigned e4[4];
+      D4 p4[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int q = sb + k;
+        e4[k] = (q < ntot) ? (q < nni ? list_word(q) : ld_nc_u32(&P.nbr[(size_t)(P.hcap + (q - nni)) * P.npad + i])) : 0u;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) p4[k] = ldg_d4(&P.posr_in[e4[k] & NB_IDX_MASK]);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const unsigned ew = e4[k];
+        if (!(ew & NB_FLAG_TYPE)) continue;
+        D4 pj = p4[k];
+        const int img = (int)((ew >> NB_IMG_SHIFT) & 31u);
+        if (PBC && img != NB_IMG_NONE) apply_image(P, img, pj);
+        const double delx = pi.x - pj.x, dely = pi.y - pj.y, delz = pi.z - pj.z;
+        const double rsq = delx * delx + dely * dely + delz * delz;
+        const double radj = pj.w;
+        const double radsum = radi + radj;
+        const int j = (int)(ew & NB_IDX_MASK);
+        if (P.has_cohesive) cohesive_entry_fast(P, co, j, img, tagi, maski, radsum, rsq, delx, dely, delz, cfx, cfy, cfz);
+        if (TYPELIST == 2 && P.lub_enabled && P.lub_flagHI && rsq < P.lub_cutsq) lubricate_entry_fast(P, j, pi, vi, wi, inv_radi, radj, rsq, delx, dely, delz, lfx, lfy, lfz, ltx, lty, ltz);
+      }
+    }
+    if (TYPELIST == 2 && P.lub_enabled) {  // isotropic FLD terms (:213-221) are applied before the pair terms in the reference
+      double ax = 0.0, ay = 0.0, az = 0.0, bx = 0.0, by = 0.0, bz = 0.0;
+      if (P.lub_flagfld) {
+        ax -= P.lub_R0 * radi * vi.x; ay -= P.lub_R0 * radi * vi.y; az -= P.lub_R0 * radi * vi.z;
+        const double radi3 = radi * radi * radi;
+        bx -= P.lub_RT0 * radi3 * wi.x; by -= P.lub_RT0 * radi3 * wi.y; bz -= P.lub_RT0 * radi3 * wi.z;
+      }
+      fx += ax + lfx; fy += ay + lfy; fz += az + lfz;
+      tx += bx + ltx; ty += by + lty; tz += bz + ltz;
+    }
+  }
+  double fd0 = 0.0, fd1 = 0.0, fd2 = 0.0, xh0 = 0.0, xh1 = 0.0, xh2 = 0.0;
+  if (P.has_fdrag) { fd0 = ld_nc_f64(&P.fdrag[0][i]); fd1 = ld_nc_f64(&P.fdrag[1][i]); fd2 = ld_nc_f64(&P.fdrag[2][i]); }
+  if (P.mode == MODE_FUSED) { xh0 = ld_nc_f64(&P.xhold[0][i]); xh1 = ld_nc_f64(&P.xhold[1][i]); xh2 = ld_nc_f64(&P.xhold[2][i]); }
+  step_epilogue<PAIR, (TYPELIST != 0)>(P, i, seq, pi, vi, wi, fx, fy, fz, tx, ty, tz, cfx, cfy, cfz, fd0, fd1, fd2, xh0, xh1, xh2, (unsigned long long)touch);
 }
 
 
