@@ -211,40 +211,50 @@ __global__ void k_save_uold(const D4 *velm, int n, double *u0, double *u1, doubl
   u0[i] = v.x; u1[i] = v.y; u2[i] = v.z;
 }
 
-// Segmented warp reduction keyed by cell id: runs of equal adjacent keys are summed with shuffles, one FP64 atomic
-// per run head.  Particles are stored in DEM-bin order, so neighbouring lanes usually share a fluid cell.
-__device__ __forceinline__ void warp_cell_add4(int key, double a, double b, double c, double d, double *dsta, double *dstv) {
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const int kprev = __shfl_up_sync(full, key, 1);
-  const bool head = (lane == 0) || (kprev != key);
-  const unsigned heads = __ballot_sync(full, head);
-  const unsigned above = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));  // run heads strictly above this lane
-  const int end = above ? (__ffs(above) - 1) : 32;                            // first lane of the next run
-  for (int o = 1; o < 32; o <<= 1) {
-    const double a2 = __shfl_down_sync(full, a, o), b2 = __shfl_down_sync(full, b, o), c2 = __shfl_down_sync(full, c, o), d2 = __shfl_down_sync(full, d, o);
-    if (lane + o < end) { a += a2; b += b2; c += c2; d += d2; }
-  }
-  if (key >= 0 && head) {
-    if (dsta) atomicAdd(&dsta[key], a);
-    atomicAdd(&dstv[3 * (size_t)key], b); atomicAdd(&dstv[3 * (size_t)key + 1], c); atomicAdd(&dstv[3 * (size_t)key + 2], d);
+// ---- particle -> cell accumulation with a FIXED summation order (bitwise reproducible run to run, no floating-point atomics).
+// After every cell-owner location the rows of each fluid cell are listed in ascending row order (count -> scan -> fill -> per-cell
+// sort: integer work only); a warp then sums one cell: lane l adds the entries l, l + 32, ... of the cell's list in that order and the
+// 32 partial sums are combined by a fixed shuffle tree.
+__global__ void k_fcell_count(const int *cell, int n, int *count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const int c = cell[i]; if (c >= 0) atomicAdd(&count[c], 1); }
+}
+__global__ void k_fcell_fill(const int *cell, int n, const int *start, int *fill, int *rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const int c = cell[i]; if (c >= 0) rows[start[c] + atomicAdd(&fill[c], 1)] = i; }
+}
+// ascending row index inside every cell: one thread per cell, insertion sort (the fill order is nearly sorted already)
+__global__ void k_fcell_sort(const int *start, int C, int *rows) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int s = start[c], e = start[c + 1];
+  for (int a = s + 1; a < e; a++) {
+    const int ra = rows[a];
+    int b = a - 1;
+    while (b >= s && rows[b] > ra) { rows[b + 1] = rows[b]; b--; }
+    rows[b + 1] = ra;
   }
 }
+__device__ __forceinline__ double warp_tree_sum(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;   // lane 0 holds the sum
+}
 
-// scatter 1: gamma += Vp, Ue += Vp Up   (enhancedCloud.C:918-930)
-__global__ void __launch_bounds__(256) k_scatter_alpha_u(const D4 *posr, const D4 *velm, const int *cell, int n, double *gamma, double *Ue) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int key = -1; double vol = 0.0, m0 = 0.0, m1 = 0.0, m2 = 0.0;
-  if (i < n) {
-    key = cell[i];
-    if (key >= 0) {
-      const double d = posr[i].w * 2.0;
-      vol = 3.14159265358979323846 * d * d * d / 6.0;
-      const D4 v = velm[i];
-      m0 = vol * v.x; m1 = vol * v.y; m2 = vol * v.z;
-    }
+// scatter 1: gamma = sum Vp, Ue = sum Vp Up over the cell's particles   (enhancedCloud.C:918-930)
+__global__ void __launch_bounds__(256) k_scatter_alpha_u(const D4 *posr, const D4 *velm, const int *start, const int *rows, int C, double *gamma, double *Ue) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double vol = 0.0, m0 = 0.0, m1 = 0.0, m2 = 0.0;
+  const int e = start[c + 1];
+  for (int k = start[c] + lane; k < e; k += 32) {
+    const int i = rows[k];
+    const double d = posr[i].w * 2.0;
+    const double vp = 3.14159265358979323846 * d * d * d / 6.0;
+    const D4 v = velm[i];
+    vol += vp; m0 += vp * v.x; m1 += vp * v.y; m2 += vp * v.z;
   }
-  warp_cell_add4(key, vol, m0, m1, m2, gamma, Ue);
+  vol = warp_tree_sum(vol); m0 = warp_tree_sum(m0); m1 = warp_tree_sum(m1); m2 = warp_tree_sum(m2);
+  if (lane == 0) { gamma[c] = vol; Ue[3 * (size_t)c] = m0; Ue[3 * (size_t)c + 1] = m1; Ue[3 * (size_t)c + 2] = m2; }
 }
 // gamma /= V ; Ue /= V ; Ue /= gamma where gamma > ROOTVSMALL   (:932-962, smoothing flags off)
 __global__ void k_finalize_alpha_u(int C, const double *cellV, double *gamma, double *Ue) {
@@ -258,27 +268,31 @@ __global__ void k_finalize_alpha_u(int C, const double *cellV, double *gamma, do
   Ue[3 * (size_t)c] = u0; Ue[3 * (size_t)c + 1] = u1; Ue[3 * (size_t)c + 2] = u2;
 }
 
-// scatter 2: Asrc[c] += Vp Jd / Vc (Up - Uf[c])   (enhancedCloud.C:356-386); Omega stays 0 (:391)
-__global__ void __launch_bounds__(256) k_scatter_asrc(const D4 *posr, const D4 *velm, const int *cell, int n, const double *Uf,
+// scatter 2: Asrc[c] = sum Vp Jd / Vc (Up - Uf[c])   (enhancedCloud.C:356-386); Omega stays 0 (:391)
+__global__ void __launch_bounds__(256) k_scatter_asrc(const D4 *posr, const D4 *velm, const int *start, const int *rows, int C, const double *Uf,
                                                       const double *gamma, const double *cellV, int model, double nub, double rhob,
                                                       double *Asrc) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int key = -1; double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-  if (i < n) {
-    key = cell[i];
-    if (key >= 0) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  const int e = start[c + 1], b = start[c];
+  if (b < e) {
+    const double f0 = Uf[3 * (size_t)c], f1 = Uf[3 * (size_t)c + 1], f2 = Uf[3 * (size_t)c + 2];
+    const double gam = gamma[c], Vc = cellV[c];
+    for (int k = b + lane; k < e; k += 32) {
+      const int i = rows[k];
       const D4 v = velm[i];
       const double d = posr[i].w * 2.0;
-      const double f0 = Uf[3 * (size_t)key], f1 = Uf[3 * (size_t)key + 1], f2 = Uf[3 * (size_t)key + 2];
       const double u0 = f0 - v.x, u1 = f1 - v.y, u2 = f2 - v.z;
       const double mag = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
-      const double jd = jd_closure(model, mag, gamma[key], d, nub, rhob);
+      const double jd = jd_closure(model, mag, gam, d, nub, rhob);
       const double Vol = 3.14159265358979323846 * d * d * d / 6.0;
-      const double omg = Vol * jd / cellV[key];
-      s0 = omg * (v.x - f0); s1 = omg * (v.y - f1); s2 = omg * (v.z - f2);
+      const double omg = Vol * jd / Vc;
+      s0 += omg * (v.x - f0); s1 += omg * (v.y - f1); s2 += omg * (v.z - f2);
     }
   }
-  warp_cell_add4(key, 0.0, s0, s1, s2, (double *)0, Asrc);
+  s0 = warp_tree_sum(s0); s1 = warp_tree_sum(s1); s2 = warp_tree_sum(s2);
+  if (lane == 0) { Asrc[3 * (size_t)c] = s0; Asrc[3 * (size_t)c + 1] = s1; Asrc[3 * (size_t)c + 2] = s2; }
 }
 // Asrc *= (1-gamma) ; [smooth] ; Asrc /= (1-gamma)   (:407-416)
 __global__ void k_finalize_asrc(int C, const double *gamma, double *Asrc) {

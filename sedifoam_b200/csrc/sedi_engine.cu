@@ -245,6 +245,7 @@ class Engine {
   bool have_mesh;
   int ncells;
   Buf<int> cell;
+  Buf<int> fc_count, fc_start, fc_fill, fc_rows, fc_blocksum;   // rows of every fluid cell, ascending (fixed-order scatter sums)
   Buf<double> Uf, gamma, gradp, DDtU, curlU, cellV, Ue, Asrc;
   bool have_DDtU, have_curlU, have_gradp, have_Uf;
   int drag_model, force_flags;
@@ -650,14 +651,10 @@ class Engine {
     const bool pbc = P.periodic_any != 0;
     if (use_sell && cfg().pair != PAIR_NONE) {   // sorted-row kernel: one lane per particle, rows of a warp carry equal work (sedi_sell.cuh)
       const int ST = SEDI_SELL_THREADS;
-#if SEDI_SELL_PERSIST
-      const int sb = std::max(1, std::min(cdiv(nlocal, ST), sm_count * (P.lub_enabled ? 6 : SEDI_SELL_MINB)));   // one resident wave, grid-stride loop
-#else
       const int sb = std::max(1, cdiv(nlocal, ST));
-#endif
-      // 32-bit row masks when no row has more than 32 granular slots (SEDI_SELL_M32=0 forces the 64-bit form)
+      // 32-bit row masks / all list words staged in shared memory when no row has more than 16 granular slots (SEDI_SELL_M32=0 forces the general form)
       static const bool allow32 = !(getenv("SEDI_SELL_M32") && atoi(getenv("SEDI_SELL_M32")) == 0);
-      const bool m32 = allow32 && P.hcap <= 32;
+      const bool m32 = allow32 && P.hcap <= 16;
 #define SEDI_LAUNCH_SELL3(PK, PB, TL)                                                                         \
   do { if (m32) k_step_sell<PK, PB, TL, true><<<sb, ST, 0, stream>>>(P, seq); else k_step_sell<PK, PB, TL, false><<<sb, ST, 0, stream>>>(P, seq); } while (0)
 #define SEDI_LAUNCH_SELL(PK)                                                                                  \
@@ -1456,6 +1453,22 @@ class Engine {
     const double t0 = now_s();
     if (nlocal) k_locate_cells<<<cdiv(nlocal, 256), 256, 0, stream>>>(posr[cur].p, nlocal, mesh, cell.p);
     launches++;
+    {  // rows of every fluid cell in ascending order: the scatter kernels sum a cell's particles in this fixed order
+      const int C = (int)ncells, nscan = C + 1, nblk = cdiv(nscan, SCAN_ITEMS);
+      fc_count.ensure((size_t)C + 2); fc_start.ensure((size_t)C + 2); fc_fill.ensure((size_t)C + 2); fc_rows.ensure(npad);
+      fc_blocksum.ensure((size_t)nblk + 1);
+      CK(cudaMemsetAsync(fc_count.p, 0, ((size_t)C + 2) * sizeof(int), stream));
+      CK(cudaMemsetAsync(fc_fill.p, 0, ((size_t)C + 2) * sizeof(int), stream));
+      if (nlocal) k_fcell_count<<<cdiv(nlocal, 256), 256, 0, stream>>>(cell.p, nlocal, fc_count.p);
+      k_scan_local<<<nblk, 1024, 0, stream>>>(fc_count.p, fc_start.p, nscan, fc_blocksum.p);
+      k_scan_sums<<<1, 1024, 0, stream>>>(fc_blocksum.p, nblk);
+      k_scan_add<<<cdiv(nscan, 256), 256, 0, stream>>>(fc_start.p, nscan, fc_blocksum.p, 0);
+      if (nlocal) {
+        k_fcell_fill<<<cdiv(nlocal, 256), 256, 0, stream>>>(cell.p, nlocal, fc_start.p, fc_fill.p, fc_rows.p);
+        k_fcell_sort<<<cdiv(C, 128), 128, 0, stream>>>(fc_start.p, C, fc_rows.p);
+      }
+      launches += 6;
+    }
     cell_valid = true;
     if (want_sums) { CK(cudaStreamSynchronize(stream)); }   // timing mode: the host's log attributes the time to this call
     timers[2] += now_s() - t0;
@@ -1615,9 +1628,7 @@ class Engine {
     if (!setup_done) setup();
     if (!cell_valid) locate();
     const size_t C = ncells;
-    CK(cudaMemsetAsync(gamma.p, 0, C * sizeof(double), stream));
-    CK(cudaMemsetAsync(Ue.p, 0, 3 * C * sizeof(double), stream));
-    if (nlocal) k_scatter_alpha_u<<<cdiv(nlocal, 256), 256, 0, stream>>>(posr[cur].p, velm[cur].p, cell.p, nlocal, gamma.p, Ue.p);
+    k_scatter_alpha_u<<<cdiv(32 * C, 256), 256, 0, stream>>>(posr[cur].p, velm[cur].p, fc_start.p, fc_rows.p, (int)C, gamma.p, Ue.p);
     if (comm.nranks > 1) { comm.allreduce_sum_dev(gamma.p, C, stream); comm.allreduce_sum_dev(Ue.p, 3 * C, stream); }
     if (want_sums) field_sum(Ue.p, 0, sums + 6);   // Utotal1 = sum of Vp Up per cell, before the division by V (:936-941)
     if (smoothing_on(8) || smoothing_on(2)) {  // enhancedCloud.C:932-962 with alphaSmooth / UpSmooth
@@ -1639,9 +1650,7 @@ class Engine {
     if (!setup_done) setup();
     if (!cell_valid) locate();
     const size_t C = ncells;
-    CK(cudaMemsetAsync(Asrc.p, 0, 3 * C * sizeof(double), stream));
-    if (nlocal)
-      k_scatter_asrc<<<cdiv(nlocal, 256), 256, 0, stream>>>(posr[cur].p, velm[cur].p, cell.p, nlocal, Uf.p, gamma.p, cellV.p, drag_model, nub, rhob, Asrc.p);
+    k_scatter_asrc<<<cdiv(32 * C, 256), 256, 0, stream>>>(posr[cur].p, velm[cur].p, fc_start.p, fc_rows.p, (int)C, Uf.p, gamma.p, cellV.p, drag_model, nub, rhob, Asrc.p);
     if (comm.nranks > 1) comm.allreduce_sum_dev(Asrc.p, 3 * C, stream);
     if (want_sums) field_sum(Asrc.p, 1, sums + 0);   // Ftotal1 = sum Asrc V (1 - gamma) before smoothing (:395-403)
     if (smoothing_on(4)) {  // Asrc (1-gamma) -> smooth -> / (1-gamma)   (enhancedCloud.C:407-416, dragSmooth)

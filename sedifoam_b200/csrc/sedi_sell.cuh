@@ -118,8 +118,9 @@ __device__ __forceinline__ void apply_image(const StepParams &P, const int img, 
 #endif
 }
 
-// contact / candidate masks of a row: 32-bit when every row of the list has at most 32 granular slots (launch-uniform, the usual case:
-// a monodisperse row has <= 16), 64-bit otherwise -- half the bit-manipulation instructions of the pair sweep
+// contact / candidate masks of a row: 32-bit (M32) when every row of the list has at most 16 granular slots (launch-uniform; the usual
+// case: a monodisperse row has <= 14 entries) -- all its list words are then the sixteen staged in shared memory --, 64-bit otherwise:
+// half the bit-manipulation instructions of the pair sweep
 template <bool M32> struct RowMask { typedef unsigned long long type; };
 template <> struct RowMask<true> { typedef unsigned type; };
 __device__ __forceinline__ int mask_ffs(unsigned m) { return __ffs((int)m) - 1; }
@@ -133,7 +134,7 @@ __device__ __forceinline__ int mask_ffs(unsigned long long m) { return __ffsll((
 // one DEM sub-step of row i (one lane)
 // TYPELIST: 0 none, 1 fix cohesive only, 2 pair lubricate/poly (and fix cohesive if present)
 template <int PAIR, bool PBC, int TYPELIST, bool M32>
-__device__ __forceinline__ void sell_row(const StepParams &P, const int seq, const int i, unsigned (*s_e)[SEDI_SELL_THREADS]) {
+__device__ __forceinline__ void sell_row(const StepParams &P, const int seq, const int i, unsigned (*s_e)[SEDI_SELL_THREADS], const bool skip) {
   constexpr bool HIST = (PAIR == PAIR_HERTZFIX_HISTORY || PAIR == PAIR_HOOKE_HISTORY);
   typedef typename RowMask<M32>::type mask_t;
   constexpr int MBITS = M32 ? 32 : 64;
@@ -169,6 +170,7 @@ __device__ __forceinline__ void sell_row(const StepParams &P, const int seq, con
     for (mask_t hm = tm_old >> 16; hm; hm &= hm - 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.shear[(size_t)(mask_ffs(hm) + 16) * P.npad + i]));
   }
 #endif
+  if (skip) return;   // (tested here, behind the row's own loads, so that the flag's round trip is not exposed at the top of every warp)
   if (bits_flags((unsigned long long)__double_as_longlong(wi.w)) & PFLAG_GHOST) return;  // ghost rows are refreshed by the halo exchange
   const double radi = pi.w, mi = vi.w;
   const int maski = bits_mask((unsigned long long)__double_as_longlong(wi.w));
@@ -197,7 +199,7 @@ __device__ __forceinline__ void sell_row(const StepParams &P, const int seq, con
   HzCoef hc; hc.c_sn = P.c_sn; hc.c_ccel = P.c_ccel; hc.c_damp = P.c_damp; hc.c_kts = P.c_kts; hc.c_ctd = P.c_ctd; hc.c_ekt = P.c_ekt; hc.xmu = P.xmu;
   GranCoef gc; gc.kn = P.kn; gc.kt = P.kt; gc.gamman = P.gamman; gc.gammat = P.gammat; gc.xmu = P.xmu; gc.beta = P.beta;
   double fx = 0.0, fy = 0.0, fz = 0.0, tx = 0.0, ty = 0.0, tz = 0.0;   // pair accumulators (force_clear)
-  auto list_word = [&](const int sl) -> unsigned { return sl < 16 ? s_e[sl][tid] : ld_nc_u32(&P.nbr[(size_t)sl * P.npad + i]); };
+  auto list_word = [&](const int sl) -> unsigned { return (M32 || sl < 16) ? s_e[sl][tid] : ld_nc_u32(&P.nbr[(size_t)sl * P.npad + i]); };   // M32: every row fits the staged sixteen
   // gathers of one overlapping entry: partner position / velocity / spin and the history quad of the slot
   struct Opnd { D4 pj, vj, wj; double h0, h1, h2; };
   auto gather = [&](const unsigned ew, const int sl, Opnd &o) {
@@ -379,39 +381,17 @@ __device__ __forceinline__ void sell_row(const StepParams &P, const int seq, con
 }
 
 
-#ifndef SEDI_SELL_PERSIST
-#define SEDI_SELL_PERSIST 0   // 1: persistent grid (one wave of CTAs), grid-stride loop over the rows, next row's lines prefetched to L2
-#endif
 template <int PAIR, bool PBC, int TYPELIST, bool M32>
 __global__ void __launch_bounds__(SEDI_SELL_THREADS, TYPELIST == 2 ? 6 : SEDI_SELL_MINB) k_step_sell(const __grid_constant__ StepParams P, const int seq) {
-  if (P.mode != MODE_SETUP) {
-    const int fl = *(volatile int *)&P.ctrl[0];
-    if (fl != 0 && fl < seq) return;  // an earlier step of this chunk asked for a neighbour rebuild: become a no-op
-  }
+  // an earlier step of this chunk asked for a neighbour rebuild: this launch is a no-op (the flag is requested here, tested in sell_row)
+  int fl = 0;
+  if (P.mode != MODE_SETUP) fl = *(volatile int *)&P.ctrl[0];
   __shared__ unsigned s_e[16][SEDI_SELL_THREADS];   // the row's list words, kept for phase 2 (one column per lane: conflict-free)
   const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i0 == 0 && P.mode != MODE_SETUP) atomicAdd(&P.ctrl[1], 1);
-#if SEDI_SELL_PERSIST
-  const int stride = gridDim.x * blockDim.x;
-  for (int i = i0; i < P.n; i += stride) {
-    const int in = i + stride;
-    if (in < P.n) {   // the next row of this lane: its lines start towards L2 while this row is processed
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.posr_in[in]));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.velm_in[in]));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.omgt_in[in]));
-      if ((threadIdx.x & 7) == 0) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.nn[in]));
-#pragma unroll
-        for (int k = 0; k < 12; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.nbr[(size_t)k * P.npad + in]));
-      }
-      if ((threadIdx.x & 3) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.tmask[in]));
-    }
-    sell_row<PAIR, PBC, TYPELIST, M32>(P, seq, i, s_e);
-  }
-#else
+  const bool skip = (fl != 0 && fl < seq);
+  if (i0 == 0 && P.mode != MODE_SETUP && !skip) atomicAdd(&P.ctrl[1], 1);   // executed sub-steps (an empty brick counts them too)
   if (i0 >= P.n) return;
-  sell_row<PAIR, PBC, TYPELIST, M32>(P, seq, i0, s_e);
-#endif
+  sell_row<PAIR, PBC, TYPELIST, M32>(P, seq, i0, s_e, skip);
 }
 
 }  // namespace sedi

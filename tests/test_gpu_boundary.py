@@ -623,3 +623,36 @@ def test_reference_printouts_and_timers(oracle_mod):
     t = e.timers()
     assert t["cpuTimeSplit"][4] > 0.0 and t["particleMoveTime"] > 0.0 and t["diffusionTimeCount"][1] > 0.0
     assert np.all(t["cpuTimeSplit"][:3] == 0.0)                                 # no all-to-alls here
+
+
+def test_scatter_is_bitwise_reproducible_and_order_independent():
+    """gamma / Ue / Asrc are summed per cell in a fixed order (no floating-point atomics): two runs give identical bits, through
+    neighbour rebuilds that re-order the rows, and a whole coupled loop (force -> sub-steps -> scatter) is reproducible"""
+    case = cases.settled_bed(columns=(2, 2), column="column_256x4.npz")
+    Uf0, gamma0, gradp0 = cases.uniform_fields(case)
+    out = []
+    for rep in range(2):
+        e = make_engine(case)
+        e.mesh_box(case["mesh_lo"], case["mesh_hi"], case["mesh_n"])
+        e.coupling_config(DRAG_ERGUN_WENYU, FORCE_DRAG | FORCE_PGRAD, case["nub"], case["rhob"], case["g"], 2.0e-4)
+        e.put_cell_fields(Uf0, gamma0, gradp0)
+        e.setup()
+        res = []
+        for k in range(3):
+            g, Ue = e.scatter_alpha_u()
+            e.put_cell_fields(Uf0, g, gradp0)
+            e.compute_fluid_force()
+            e.sedi_step(40)
+            if k == 1:
+                e.force_rebuild()
+            A, _ = e.calc_tc()
+            res.append((g.copy(), Ue.copy(), A.copy()))
+        st = e.atoms()
+        o = np.argsort(st["tag"])
+        res.append((st["x"][o].copy(), st["v"][o].copy(), st["omega"][o].copy()))
+        out.append(res)
+        e.close()
+    for a, b in zip(out[0], out[1]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    assert np.abs(out[0][0][2]).max() > 0
