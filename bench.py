@@ -454,7 +454,7 @@ def main():
     kname = {1: "gran/hertzFix/history", 2: "gran/hertzFix/history", 3: "gran/hertzFix/history + fix cohesive",
              4: "gran/hertzFix/history + lubricate/poly"}[cfg]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": ("k_step_sell<%s>" if cfg in (1, 2) and not os.environ.get("SEDI_KSTEP_PATH") else "k_step<%s>") % kname,
+                "kernel": ("k_step_sell<%s>" if not os.environ.get("SEDI_KSTEP_PATH") else "k_step<%s>") % kname,
                 "avg_launch_us": k_avg_ms * 1e3, "launches_timed": ksteps,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_share_of_step": kms / ms_dev if ms_dev > 0 else None}
