@@ -218,6 +218,7 @@ class Engine {
   int equal_spheres;   // every atom of the system has the same radius and mass (launch-uniform fast path of the pair law)
   double cutneighsq[(MAX_TYPES + 1) * (MAX_TYPES + 1)];
   double dt_init;
+  bool setup_done_once;   // a full setup() has run at least once (init-time constants exist)
   double lub_R0, lub_RT0, lub_RS0;
   double beta_pair;
   StepParams base;
@@ -269,7 +270,7 @@ class Engine {
 
   Engine()
       : device(0), dev_ready(false), loaded(false), setup_done(false), params_dirty(true), cell_valid(false), stream(0), n(0),
-        nlocal(0), nghost(0), npad(0), maxtag(0), cur(0), icur(0), ecur(0), cutneighmax(0), eq_radius(0), eq_mass(0), equal_spheres(0), dt_init(0), lub_R0(0), lub_RT0(0), lub_RS0(0),
+        nlocal(0), nghost(0), npad(0), maxtag(0), cur(0), icur(0), ecur(0), cutneighmax(0), eq_radius(0), eq_mass(0), equal_spheres(0), dt_init(0), setup_done_once(false), lub_R0(0), lub_RT0(0), lub_RS0(0),
         beta_pair(0), pair_evals_unique(0), nbuilds(0), pair_evals(0), steps_done(0), launches(0), list_gran_dir(0), list_type_dir(0), list_gran_img(0),
         list_type_img(0), chunk(50), last_step_ms(0), count_in_kernel(false), have_mesh(false), ncells(0), have_DDtU(false),
         have_curlU(false), have_gradp(false), have_Uf(false), drag_model(0), force_flags(SEDI_FORCE_DRAG | SEDI_FORCE_PGRAD), nub(1e-6), rhob(1000.0),
@@ -966,6 +967,7 @@ class Engine {
       inject_pending = ip;
     }
     setup_done = true;
+    if (evaluate_forces) setup_done_once = true;
     if (!cfg().dumps.empty()) write_dumps();   // Output::setup writes the initial snapshot
   }
 
@@ -1806,7 +1808,11 @@ class Engine {
     // here (`run N pre no`), the next half-kick uses the stored f(n) -- which does not know the injected particles
     // yet -- and an extra evaluation would apply the Coulomb rescale of the shear springs once more
     // (pair_gran_hertzFix_history.cpp:244-252 is not guarded by shearupdate).
+    const bool had_setup = setup_done_once;
+    const double dt0 = dt_init, r0 = lub_R0, rt0 = lub_RT0, rs0 = lub_RS0;
     setup(false);
+    // the reference never re-initialises at an edit (library.cpp:406-621): init-time constants keep their values
+    if (had_setup) { dt_init = dt0; lub_R0 = r0; lub_RT0 = rt0; lub_RS0 = rs0; build_base_params(); }
     inject_pending = false;
     cfg().ntimestep = step;
     CK(cudaStreamSynchronize(stream));

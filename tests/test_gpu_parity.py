@@ -30,6 +30,8 @@ SCENARIOS = {
     "cohesive_opt1": (lambda: cases.cohesive_shear_bed(dims=(10, 8, 10), opt=1), 300),
     "cohesive_opt0": (lambda: cases.cohesive_shear_bed(dims=(10, 8, 10), opt=0), 300),
     "lubricate_poly": (lambda: cases.poly_lubricated(dims=(10, 10, 10)), 200),
+    # the dense polydisperse packing of configs[4] (phi 0.55, full list of ~50 entries per row, two row segments)
+    "lubricate_poly_dense": (lambda: cases.random_poly_lubricated(tiles=(1, 1, 1), tile_n=1500), 200),
     "frozen_floor": (lambda: _frozen(cases.sediment_column(dims=(8, 12, 8), phi=0.50, jitter_frac=0.02)), 300),
     # skin = d: rows of ~32 neighbours, mostly not touching (the skin of cases/example-cases/transport-bedload/in.lammps:12);
     # exercises the look-ahead ring refill of k_step and the growth of the ELL capacity
