@@ -486,16 +486,16 @@ inline void Comm::build_row_table(Engine &e) {
 inline void Comm::forward(Engine &e, int buf, bool with_flag, bool pushed) {
   const int T = 256, NL = dev.nlinks;
   if (p2p) {
+    halo_calls++;
     PushTable H;
     make_push_table(H, buf);
-    if (total_send && !pushed) k_halo_push<<<cdiv(total_send, T), T, 0, e.stream>>>(e.posr[buf].p, e.velm[buf].p, e.omgt[buf].p, d_sendrows, H);
+    if (total_send && !pushed) { k_halo_push<<<cdiv(total_send, T), T, 0, e.stream>>>(e.posr[buf].p, e.velm[buf].p, e.omgt[buf].p, d_sendrows, H); e.launches++; }
     SignalTable S;
     memset(&S, 0, sizeof(S));
     S.nranks = nranks; S.me = rank;
     for (int r = 0; r < nranks; r++) S.rsig[r] = (unsigned long long *)peer_base[r][6];
     k_halo_signal_wait<<<1, 64, 0, e.stream>>>(S, d_sig, e.ctrl.p, with_flag ? 1 : 0);
-    e.launches += 2;
-    halo_calls++;
+    e.launches++;
     return;
   }
   HaloTable H;

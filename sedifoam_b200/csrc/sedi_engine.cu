@@ -185,6 +185,9 @@ class Engine {
   cudaStream_t stream;
   cudaEvent_t ev0, ev1, evk0, evk1, evt0, evt1;
   bool prof_on;
+  bool prof_split;                       // SEDI_PROF_SPLIT=1 (diagnostic, no graph): events around every sub-step kernel and every ghost exchange
+  std::vector<cudaEvent_t> split_ev;
+  double split_step_ms, split_halo_ms; long long split_n;
   double prof_ms;
   long long prof_steps;
   // particle rows
@@ -274,7 +277,7 @@ class Engine {
         beta_pair(0), pair_evals_unique(0), nbuilds(0), pair_evals(0), steps_done(0), launches(0), list_gran_dir(0), list_type_dir(0), list_gran_img(0),
         list_type_img(0), chunk(50), last_step_ms(0), count_in_kernel(false), have_mesh(false), ncells(0), have_DDtU(false),
         have_curlU(false), have_gradp(false), have_Uf(false), drag_model(0), force_flags(SEDI_FORCE_DRAG | SEDI_FORCE_PGRAD), nub(1e-6), rhob(1000.0),
-        deltaT(1.0), restart_every(0), restart_toggle(0), restart_pending(false), restart_carry(0), inject_pending(false), hist_alloc(false), have_UfOld(false), time_index(0), inlet_option(0), want_diag(false), smooth_b(0.0), smooth_steps(0), smooth_flags(0), smooth_iters_last(0), prof_on(false), prof_ms(0), prof_steps(0) {
+        deltaT(1.0), restart_every(0), restart_toggle(0), restart_pending(false), restart_carry(0), inject_pending(false), hist_alloc(false), have_UfOld(false), time_index(0), inlet_option(0), want_diag(false), smooth_b(0.0), smooth_steps(0), smooth_flags(0), smooth_iters_last(0), prof_on(false), prof_split(false), split_step_ms(0), split_halo_ms(0), split_n(0), prof_ms(0), prof_steps(0) {
     gvec[0] = gvec[1] = gvec[2] = 0.0;
     memset(timers, 0, sizeof(timers)); memset(sums, 0, sizeof(sums)); want_sums = false;
     memset(inlet_force, 0, sizeof(inlet_force)); memset(inlet_box, 0, sizeof(inlet_box)); memset(inlet_ecc, 0, sizeof(inlet_ecc));
@@ -287,6 +290,8 @@ class Engine {
     graph_on = true;
     e = getenv("SEDI_GRAPH");
     if (e && atoi(e) == 0) graph_on = false;
+    e = getenv("SEDI_PROF_SPLIT");
+    prof_split = (e && atoi(e) != 0);
     e = getenv("SEDI_KSTEP_PATH");
     warned_neigh = false; sm_count = 148; mpi_world = (MPI_Comm)0; comm_tried = false;
     use_wq = (e && !strcmp(e, "wq"));
@@ -303,6 +308,8 @@ class Engine {
     for (size_t k = 0; k < script.cfg.dumps.size(); k++) if (script.cfg.dumps[k].fp) { fclose(script.cfg.dumps[k].fp); script.cfg.dumps[k].fp = 0; }
     if (!dev_ready) return;
     cudaSetDevice(device);
+    if (prof_split && split_n) fprintf(stderr, "[sedi prof split] rank %d: %lld sub-steps, sub-step kernel %.2f us, ghost exchange / barrier %.2f us per sub-step\n", comm.rank, split_n, 1e3 * split_step_ms / split_n, 1e3 * split_halo_ms / split_n);
+    for (size_t k = 0; k < split_ev.size(); k++) cudaEventDestroy(split_ev[k]);
     g_comm_engine_set(this);
     cudaStreamSynchronize(stream);
     // device memory is released with the process; explicit frees keep long-lived hosts clean
@@ -610,6 +617,9 @@ class Engine {
     drop_graphs();
   }
 
+  // several GPUs, peer-memory halo: the sub-step kernel writes the neighbours' ghost rows itself
+  bool step_pushes() { return comm.nranks > 1 && comm.p2p && comm.fused_push; }
+
   // per-launch part of the parameter block
   void fill_launch(StepParams &P, int mode, int in, long long ntimestep) {
     P = base;
@@ -760,9 +770,17 @@ class Engine {
     if (sorted_rows) {
       order2.ensure(npad); crow.ensure(npad);
       Ell &Lprev = ell[ecur];
+      BorderBand band;
+      for (int d = 0; d < 3; d++) {
+        const double inf = std::numeric_limits<double>::infinity();
+        const bool split = comm.nranks > 1 && comm.grid[d] > 1;
+        band.lo[d] = split ? comm.sublo(cfg(), d, 0.0) + cutneighmax : -inf;
+        band.hi[d] = split ? comm.subhi(cfg(), d, 0.0) - cutneighmax : inf;
+      }
       k_window_sort<<<cdiv(nlocal_new, SELL_WINDOW), SELL_WINDOW, 0, stream>>>(nlocal_new, order.p, Lprev.valid ? Lprev.tmask.p : (const unsigned long long *)0,
                                                                                Lprev.valid ? Lprev.nn.p : (const int *)0,
-                                                                               (Lprev.valid && want_type_list()) ? Lprev.nt.p : (const int *)0, nlocal, order2.p, crow.p);
+                                                                               (Lprev.valid && want_type_list()) ? Lprev.nt.p : (const int *)0, nlocal, order2.p, crow.p,
+                                                                               (step_pushes() && !getenv("SEDI_BORDER_CLUSTER_OFF")) ? posr[cur].p : (const D4 *)0, band);
       launches++;
       ord = order2.p;
     }
@@ -1077,7 +1095,7 @@ class Engine {
       for (size_t k = 0; k < cfg().fixes.size(); k++) if (cfg().fixes[k].kind == FIX_WALL_GRAN && cfg().fixes[k].wiggle) wiggle = true;
       // one CUDA graph per chunk; on several GPUs it includes the halo push / signal kernels of every sub-step (peer-memory
       // path only: their launches carry no per-call argument).  Odd-sized remainders after a rebuild are launched directly.
-      if (graph_on && (!mg || comm.p2p) && !wiggle && K == chunk && K > 1) {
+      if (graph_on && !prof_split && (!mg || comm.p2p) && !wiggle && K == chunk && K > 1) {
         const int lastflag = (remaining == K) ? 1 : 0;
         StepGraph *g = 0;
         for (size_t k = 0; k < graphs.size(); k++) if (graphs[k].in == in && graphs[k].K == K && graphs[k].last == lastflag && graphs[k].seq0 == seq) g = &graphs[k];
@@ -1090,7 +1108,7 @@ class Engine {
             const bool lastk = (lastflag && s == K - 1);
             launch_step(lastk ? MODE_LAST : MODE_FUSED, cin, cfg().ntimestep + s + 1, ++cseq);
             cin ^= 1;
-            if (mg && !lastk) comm.forward(*this, cin, true, comm.p2p && comm.fused_push);
+            if (mg && !lastk) comm.forward(*this, cin, true, step_pushes());
           }
           CK(cudaStreamEndCapture(stream, &gr));
           launches = l0; comm.halo_calls = h0;
@@ -1113,19 +1131,30 @@ class Engine {
         }
         CK(cudaGraphLaunch(g->exec, stream));
         launches += K; seq += K; in ^= (K & 1);
-        if (mg) { const int nfw = K - (lastflag ? 1 : 0); launches += 2 * nfw; comm.halo_calls += nfw; }
+        if (mg) { const int nfw = K - (lastflag ? 1 : 0); launches += (step_pushes() ? 1 : 2) * nfw; comm.halo_calls += nfw; }
       } else
       for (int s = 0; s < K; s++) {
         const bool last = (remaining - s == 1);
+        if (prof_split) { while ((int)split_ev.size() < 3 * chunk + 3) { cudaEvent_t ev; CK(cudaEventCreate(&ev)); split_ev.push_back(ev); } CK(cudaEventRecord(split_ev[3 * s], stream)); }
         launch_step(last ? MODE_LAST : MODE_FUSED, in, cfg().ntimestep + s + 1, ++seq);
+        if (prof_split) CK(cudaEventRecord(split_ev[3 * s + 1], stream));
         in ^= 1;
-        if (mg && !last) comm.forward(*this, in, true, comm.p2p && comm.fused_push);  // ghost x, v, omega of the new positions (written by the step kernel itself on the peer-memory path) + rebuild consensus
+        if (mg && !last) comm.forward(*this, in, true, step_pushes());  // ghost x, v, omega of the new positions (written by the step kernel itself on the peer-memory path) + rebuild consensus
+        if (prof_split) CK(cudaEventRecord(split_ev[3 * s + 2], stream));
       }
       if (prof_on) CK(cudaEventRecord(evk1, stream));
       CK(cudaMemcpyAsync(h_ctrl.p, ctrl.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, stream));
       CK(cudaStreamSynchronize(stream));
       CK(cudaGetLastError());
       const int flag = h_ctrl.p[0], done = h_ctrl.p[1];
+      if (prof_split) {
+        for (int s = 0; s < K && 3 * s + 2 < (int)split_ev.size(); s++) {
+          float a = 0.f, b = 0.f;
+          if (cudaEventElapsedTime(&a, split_ev[3 * s], split_ev[3 * s + 1]) == cudaSuccess && cudaEventElapsedTime(&b, split_ev[3 * s + 1], split_ev[3 * s + 2]) == cudaSuccess) {
+            split_step_ms += a; split_halo_ms += b; split_n++;
+          } else cudaGetLastError();
+        }
+      }
       if (prof_on) {  // the K k_step launches are back to back on the stream: their summed duration / executed count
         float kms = 0.f;
         CK(cudaEventElapsedTime(&kms, evk0, evk1));

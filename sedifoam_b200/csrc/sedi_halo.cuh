@@ -245,9 +245,9 @@ __global__ void k_halo_signal_wait(const __grid_constant__ SignalTable S, volati
   const unsigned epoch = (unsigned)mysig[64] + 1u;
   if (r < S.nranks) {
     const unsigned fl = with_flag ? (unsigned)ctrl[0] : 0u;
-    __threadfence_system();
+    // (no fence in front of the store: everything this rank wrote into its neighbours' memory was written by earlier kernels of
+    // this stream, and a grid's completion makes its writes visible system-wide before the next grid starts)
     *((volatile unsigned long long *)&S.rsig[r][S.me]) = ((unsigned long long)epoch << 32) | fl;
-    __threadfence_system();
     unsigned long long v;
     do { v = mysig[r]; } while ((unsigned)(v >> 32) < epoch);
     sflag[r] = (int)(unsigned)(v & 0xffffffffull);

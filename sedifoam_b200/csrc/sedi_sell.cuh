@@ -60,8 +60,13 @@ static const int SELL_WINDOW = SEDI_SELL_WINDOW;   // sigma of SELL-C-sigma: row
 // order[k]  : canonical (bin-ordered) position k -> old row            (input, from the counting sort)
 // order2[r] : physical new row r -> old row                             (what the permutation kernels and the history re-attachment use)
 // crow[k]   : canonical position k -> physical new row                  (how the list build reaches the rows of a bin)
+// several GPUs: rows whose particle lies within the ghost cut-off of a face shared with a neighbour brick (outside [lo, hi) in a split
+// dimension; +-inf elsewhere) are the ones the sub-step kernel writes into the neighbour's memory.  They are sorted to the end of their
+// window, i.e. into warps of their own, so that the other warps do not diverge into the push code of the epilogue
+struct BorderBand { double lo[3], hi[3]; };
 __global__ void __launch_bounds__(SELL_WINDOW) k_window_sort(int n, const int *order, const unsigned long long *tmask_old, const int *nn_old,
-                                                             const int *nt_old, int nrows_old, int *order2, int *crow) {
+                                                             const int *nt_old, int nrows_old, int *order2, int *crow, const D4 *posr_old,
+                                                             const BorderBand band) {
   __shared__ unsigned s[SELL_WINDOW];
   const int t = threadIdx.x;
   const int k = blockIdx.x * SELL_WINDOW + t;
@@ -80,6 +85,10 @@ __global__ void __launch_bounds__(SELL_WINDOW) k_window_sort(int n, const int *o
       }
     }
     comp = ((4095u - key) << 10) | (unsigned)t;   // heavy rows first; ties keep the bin order (the composite is unique)
+    if (posr_old) {
+      const D4 p = posr_old[o];
+      if (p.x < band.lo[0] || p.x >= band.hi[0] || p.y < band.lo[1] || p.y >= band.hi[1] || p.z < band.lo[2] || p.z >= band.hi[2]) comp |= (1u << 22);
+    }
   }
   s[t] = comp;
   __syncthreads();
@@ -133,8 +142,8 @@ __device__ __forceinline__ int mask_ffs(unsigned long long m) { return __ffsll((
 // granular instantiation carries none of it.
 // one DEM sub-step of row i (one lane)
 // TYPELIST: 0 none, 1 fix cohesive only, 2 pair lubricate/poly (and fix cohesive if present)
-template <int PAIR, bool PBC, int TYPELIST, bool M32>
-__device__ __forceinline__ void sell_row(const StepParams &P, const int seq, const int i, unsigned (*s_e)[SEDI_SELL_THREADS], const bool skip) {
+template <int PAIR, bool PBC, int TYPELIST, bool M32, class SkipF>
+__device__ __forceinline__ void sell_row(const StepParams &P, const int seq, const int i, unsigned (*s_e)[SEDI_SELL_THREADS], SkipF skipf) {
   constexpr bool HIST = (PAIR == PAIR_HERTZFIX_HISTORY || PAIR == PAIR_HOOKE_HISTORY);
   typedef typename RowMask<M32>::type mask_t;
   constexpr int MBITS = M32 ? 32 : 64;
@@ -158,6 +167,7 @@ __device__ __forceinline__ void sell_row(const StepParams &P, const int seq, con
     if (P.mode == MODE_FUSED) { prefetch_l1(&P.xhold[0][i]); prefetch_l1(&P.xhold[1][i]); prefetch_l1(&P.xhold[2][i]); }
   }
   if ((tid & 7) == 0 && P.wmask) prefetch_l1(&P.wmask[i]);
+  if ((tid & 31) == 0 && P.bcnt) prefetch_l1(&P.bcnt[i]);   // several GPUs: border-entry count of the row, read at the very end of the epilogue
 #if SEDI_SELL_PFH == 1
   if (HIST) for (mask_t hm = tm_old; hm; hm &= hm - 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.shear[(size_t)mask_ffs(hm) * P.npad + i]));
 #elif SEDI_SELL_PFH == 2
@@ -170,7 +180,7 @@ __device__ __forceinline__ void sell_row(const StepParams &P, const int seq, con
     for (mask_t hm = tm_old >> 16; hm; hm &= hm - 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.shear[(size_t)(mask_ffs(hm) + 16) * P.npad + i]));
   }
 #endif
-  if (skip) return;   // (tested here, behind the row's own loads, so that the flag's round trip is not exposed at the top of every warp)
+  if (skipf()) return;   // no-op launch?  (decided here, behind the row's own loads, so that the flag's round trip is not exposed at the top of every warp)
   if (bits_flags((unsigned long long)__double_as_longlong(wi.w)) & PFLAG_GHOST) return;  // ghost rows are refreshed by the halo exchange
   const double radi = pi.w, mi = vi.w;
   const int maski = bits_mask((unsigned long long)__double_as_longlong(wi.w));
@@ -383,15 +393,18 @@ __device__ __forceinline__ void sell_row(const StepParams &P, const int seq, con
 
 template <int PAIR, bool PBC, int TYPELIST, bool M32>
 __global__ void __launch_bounds__(SEDI_SELL_THREADS, TYPELIST == 2 ? 6 : SEDI_SELL_MINB) k_step_sell(const __grid_constant__ StepParams P, const int seq) {
+  __shared__ unsigned s_e[16][SEDI_SELL_THREADS];   // the row's list words, kept for phase 2 (one column per lane: conflict-free)
+  const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
   // an earlier step of this chunk asked for a neighbour rebuild: this launch is a no-op (the flag is requested here, tested in sell_row)
   int fl = 0;
   if (P.mode != MODE_SETUP) fl = *(volatile int *)&P.ctrl[0];
-  __shared__ unsigned s_e[16][SEDI_SELL_THREADS];   // the row's list words, kept for phase 2 (one column per lane: conflict-free)
-  const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool skip = (fl != 0 && fl < seq);
-  if (i0 == 0 && P.mode != MODE_SETUP && !skip) atomicAdd(&P.ctrl[1], 1);   // executed sub-steps (an empty brick counts them too)
-  if (i0 >= P.n) return;
-  sell_row<PAIR, PBC, TYPELIST, M32>(P, seq, i0, s_e, skip);
+  auto skipf = [&]() -> bool {
+    const bool skip = (fl != 0 && fl < seq);
+    if (i0 == 0 && P.mode != MODE_SETUP && !skip) atomicAdd(&P.ctrl[1], 1);   // executed sub-steps (an empty brick counts them too)
+    return skip;
+  };
+  if (i0 < P.n) sell_row<PAIR, PBC, TYPELIST, M32>(P, seq, i0, s_e, skipf);
+  else if (i0 == 0) skipf();
 }
 
 }  // namespace sedi

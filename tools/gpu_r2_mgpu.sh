@@ -16,6 +16,7 @@ except Exception as e: print('$1 no json', e)
 "; grep -v "^\*\*\*\|OMP_NUM" gpurun_out/mg${N}_$1.err | tail -2 | cut -c1-300
 }
 run weak "SEDI_X=1" ""
+run weak_ksig "SEDI_HALO_SIGNAL=kernel" ""
 run weak_unfused "SEDI_HALO_FUSED=0" ""
 run weak_nograph "SEDI_GRAPH=0" ""
 run strong "SEDI_X=1" "--scaling strong"
