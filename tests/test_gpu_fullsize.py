@@ -1,7 +1,8 @@
 """-m gpu: BASELINE.json's full sizes (1e5 / 1e6 particles).
 
 Parity against the reference's own compiled objects at size (configs[1]: 1e5 particles x 1000 sub-steps, configs[2]:
-1e6 particles x 100 sub-steps; about 20-40 s of single-core CPU each), then size-independent properties of the hot path:
+1e6 particles x 100 sub-steps, configs[3]: 1e6 cohesive x 30, configs[4]: 1.25e6 lubricated x 12; about 20-60 s of single-core CPU
+each), then size-independent properties of the hot path:
 
   * the directed neighbour list is symmetric (every pair sits in both partners' rows) and agrees with the
     brute-force count of overlapping lattice neighbours;
@@ -63,6 +64,23 @@ def test_config2_1e6_settled_bed_parity_with_reference_objects(oracle_mod):
     assert len(case["tag"]) == 1000000
     kind, touching = _fullsize_parity(oracle_mod, case, 100)
     assert touching > 2 * 2.0e6      # directed touching entries: more than two touching pairs per particle
+
+
+def test_config3_1e6_cohesive_bed_parity_with_reference_objects(oracle_mod):
+    """configs[3]: the 1e6-particle cohesive settled bed under the sheared lid (gran/hertzFix/history + fix cohesive over its own
+    half list), 30 DEM sub-steps, against the reference objects (fix_cohesive.cpp:138-263)"""
+    case = cases.settled_cohesive_bed()
+    assert len(case["tag"]) == 1000000
+    _fullsize_parity(oracle_mod, case, 30)
+
+
+def test_config4_1p25e6_polydisperse_lubricated_parity_with_reference_objects(oracle_mod):
+    """configs[4]: 1.25e6 polydisperse spheres at phi 0.55, hybrid/overlay gran/hertzFix/history + lubricate/poly over the full list
+    (about 50 entries per row in two row segments), 12 DEM sub-steps, against the reference objects
+    (pair_lubricate_poly.cpp:233-403)"""
+    case = cases.random_poly_lubricated()
+    assert len(case["tag"]) == 1250000
+    _fullsize_parity(oracle_mod, case, 12)
 
 
 def _pairs_symmetric(e):
