@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 #include <limits>
 
@@ -183,7 +184,7 @@ class Engine {
   int device;
   bool dev_ready, loaded, setup_done, params_dirty, cell_valid;
   cudaStream_t stream;
-  cudaEvent_t ev0, ev1, evk0, evk1, evt0, evt1;
+  cudaEvent_t ev0, ev1, evk0, evk1, evt0, evt1, ev_get[2];
   bool prof_on;
   bool prof_split;                       // SEDI_PROF_SPLIT=1 (diagnostic, no graph): events around every sub-step kernel and every ghost exchange
   std::vector<cudaEvent_t> split_ev;
@@ -327,7 +328,7 @@ class Engine {
     dg_Uri.release(); dg_mag.release(); dg_alpha.release(); dg_Jd.release();
     cg_r.release(); cg_z.release(); cg_p.release(); cg_Ap.release(); cg_partial.release(); cg_s.release(); cg_tmp.release(); h_cg.release();
     comm.destroy();
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evk0); cudaEventDestroy(evk1);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evk0); cudaEventDestroy(evk1); cudaEventDestroy(ev_get[0]); cudaEventDestroy(ev_get[1]);
     cudaEventDestroy(evt0); cudaEventDestroy(evt1);
     cudaStreamDestroy(stream);
   }
@@ -348,6 +349,7 @@ class Engine {
     { cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, device)); sm_count = pr.multiProcessorCount; }
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1)); CK(cudaEventCreate(&evk0)); CK(cudaEventCreate(&evk1));
+    CK(cudaEventCreateWithFlags(&ev_get[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ev_get[1], cudaEventDisableTiming));
     CK(cudaEventCreate(&evt0)); CK(cudaEventCreate(&evt1));
     ctrl.ensure(8); counters.ensure(8); h_ctrl.ensure(8); h_counters.ensure(8);
     CK(cudaMemsetAsync(ctrl.p, 0, 8 * sizeof(int), stream));
@@ -1183,6 +1185,25 @@ class Engine {
   }
 
   // ---- C-ABI data movement ---------------------------------------------------------------------------------------
+  // The unchanged host (softParticleCloud.C:908-912, 959-963) hands over pageable `new double[]` arrays: they are staged through
+  // page-locked buffers.  The host-side copy between the two is split over a few threads (one core moves ~10 GB/s, the DMA 25+),
+  // and on the way back every array is copied out while the next one is still arriving.
+  static void par_memcpy(void *dst, const void *src, size_t bytes) {
+    const size_t MINB = (size_t)4 << 20;
+    int nt = (int)std::min<size_t>(4, bytes / MINB);
+    if (const char *e = getenv("SEDI_COPY_THREADS")) nt = std::max(1, std::min(16, atoi(e)));
+    if (nt <= 1) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> th;
+    const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
+    for (int t = 1; t < nt; t++) {
+      const size_t o = per * t;
+      if (o >= bytes) break;
+      const size_t len = std::min(per, bytes - o);
+      th.emplace_back([=]() { memcpy((char *)dst + o, (const char *)src + o, len); });
+    }
+    memcpy(dst, src, std::min(per, bytes));
+    for (size_t t = 0; t < th.size(); t++) th[t].join();
+  }
   static bool is_pinned(const void *p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -1200,7 +1221,7 @@ class Engine {
     d_stage_a.ensure(3 * (size_t)nin); d_stage_i.ensure(nin); d_stage_j.ensure(nin);
     // caller arrays that are already page-locked go straight to the copy engine; pageable ones are staged
     const void *src_a = fd, *src_i = tagin, *src_j = foamin;
-    if (!is_pinned(fd)) { h_stage_a.ensure(3 * (size_t)nin); memcpy(h_stage_a.p, fd, 3 * (size_t)nin * sizeof(double)); src_a = h_stage_a.p; }
+    if (!is_pinned(fd)) { h_stage_a.ensure(3 * (size_t)nin); par_memcpy(h_stage_a.p, fd, 3 * (size_t)nin * sizeof(double)); src_a = h_stage_a.p; }
     if (!is_pinned(tagin)) { h_stage_i.ensure(nin); memcpy(h_stage_i.p, tagin, nin * sizeof(int)); src_i = h_stage_i.p; }
     if (foamin && !is_pinned(foamin)) { h_stage_j.ensure(nin); memcpy(h_stage_j.p, foamin, nin * sizeof(int)); src_j = h_stage_j.p; }
     CK(cudaMemcpyAsync(d_stage_a.p, src_a, 3 * (size_t)nin * sizeof(double), cudaMemcpyHostToDevice, stream));
@@ -1229,16 +1250,16 @@ class Engine {
     if (v && !pv) h_stage_b.ensure(3 * (size_t)m);
     if (tag && !pt) h_stage_i.ensure(m);
     if (foamid && !pf) h_stage_j.ensure(m);
-    if (x) CK(cudaMemcpyAsync(px ? (void *)x : (void *)h_stage_a.p, d_stage_a.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
-    if (v) CK(cudaMemcpyAsync(pv ? (void *)v : (void *)h_stage_b.p, d_stage_b.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (x) { CK(cudaMemcpyAsync(px ? (void *)x : (void *)h_stage_a.p, d_stage_a.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream)); CK(cudaEventRecord(ev_get[0], stream)); }
+    if (v) { CK(cudaMemcpyAsync(pv ? (void *)v : (void *)h_stage_b.p, d_stage_b.p, 3 * (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, stream)); CK(cudaEventRecord(ev_get[1], stream)); }
     if (tag) CK(cudaMemcpyAsync(pt ? (void *)tag : (void *)h_stage_i.p, d_stage_i.p, m * sizeof(int), cudaMemcpyDeviceToHost, stream));
     if (foamid) CK(cudaMemcpyAsync(pf ? (void *)foamid : (void *)h_stage_j.p, d_stage_j.p, m * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (lmpid) for (int i = 0; i < m; i++) lmpid[i] = comm.rank;   // (while the first array arrives)
+    if (x && !px) { CK(cudaEventSynchronize(ev_get[0])); par_memcpy(x, h_stage_a.p, 3 * (size_t)m * sizeof(double)); }   // v is still arriving
+    if (v && !pv) { CK(cudaEventSynchronize(ev_get[1])); par_memcpy(v, h_stage_b.p, 3 * (size_t)m * sizeof(double)); }
     CK(cudaStreamSynchronize(stream));
-    if (x && !px) memcpy(x, h_stage_a.p, 3 * (size_t)m * sizeof(double));
-    if (v && !pv) memcpy(v, h_stage_b.p, 3 * (size_t)m * sizeof(double));
     if (tag && !pt) memcpy(tag, h_stage_i.p, m * sizeof(int));
     if (foamid && !pf) memcpy(foamid, h_stage_j.p, m * sizeof(int));
-    if (lmpid) for (int i = 0; i < m; i++) lmpid[i] = comm.rank;
   }
 
   // full state in device row order (owned rows first `nlocal` rows are owned; ghosts follow)

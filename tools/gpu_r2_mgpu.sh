@@ -3,7 +3,7 @@
 N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/mgpu_check.py > gpurun_out/mg_check.log 2>&1; echo "mgpu_check rc=$?"; grep "mgpu" gpurun_out/mg_check.log | cut -c1-330
+timeout 1200 python -m pytest tests/test_gpu_multi.py -m gpu -q --timeout 900 > gpurun_out/mg_pytest.log 2>&1; echo "pytest multi rc=$?"; tail -3 gpurun_out/mg_pytest.log | cut -c1-200
 P=29600
 run() {  # name, extra env, extra args
   P=$((P+1))
@@ -16,7 +16,6 @@ except Exception as e: print('$1 no json', e)
 "; grep -v "^\*\*\*\|OMP_NUM" gpurun_out/mg${N}_$1.err | tail -2 | cut -c1-300
 }
 run weak "SEDI_X=1" ""
-run weak_ksig "SEDI_HALO_SIGNAL=kernel" ""
 run weak_unfused "SEDI_HALO_FUSED=0" ""
 run weak_nograph "SEDI_GRAPH=0" ""
 run strong "SEDI_X=1" "--scaling strong"
