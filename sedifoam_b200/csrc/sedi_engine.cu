@@ -980,7 +980,7 @@ class Engine {
     }
     // the rows are sorted by the work they had under the previous list; the first list has no predecessor, so the same
     // list is built once more now that its touch masks are known (same positions, same pair set: not a LAMMPS re-neighbouring)
-    if (sell_sort && nlocal + nghost > 0) {
+    if (sell_sort && (comm.nranks > 1 || nlocal + nghost > 0)) {   // (a rebuild is collective on several GPUs: an empty brick takes part)
       const bool ip = inject_pending;   // the list just built carries the injected history: re-attach from it, not from the arrival lists again
       inject_pending = false;
       rebuild(false);
