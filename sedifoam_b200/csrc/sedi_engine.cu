@@ -2075,7 +2075,7 @@ class Engine {
     script.mask = mk;
   }
   void create_particles(int np, const double *pos, const double *tagd, double diameter, double rho, int type, const double *vel) {
-    const bool carry = carry_enabled() && nlocal > 0;
+    const bool carry = carry_enabled() && (comm.nranks > 1 || nlocal > 0);   // (collective on several GPUs: an empty brick takes part in the re-upload)
     RowCarry R;
     if (carry) save_rows(R);
     sync_host_atoms();
@@ -2097,7 +2097,7 @@ class Engine {
     if (carry) reinject(R, keep);
   }
   void delete_particles(const int *list, int nd) {  // list holds atom tags (library.cpp:507-621)
-    const bool carry = carry_enabled() && nlocal > 0;
+    const bool carry = carry_enabled() && (comm.nranks > 1 || nlocal > 0);   // (collective on several GPUs: an empty brick takes part in the re-upload)
     RowCarry R;
     if (carry) save_rows(R);
     sync_host_atoms();
