@@ -245,8 +245,9 @@ __global__ void k_halo_signal_wait(const __grid_constant__ SignalTable S, volati
   const unsigned epoch = (unsigned)mysig[64] + 1u;
   if (r < S.nranks) {
     const unsigned fl = with_flag ? (unsigned)ctrl[0] : 0u;
-    // (no fence in front of the store: everything this rank wrote into its neighbours' memory was written by earlier kernels of
-    // this stream, and a grid's completion makes its writes visible system-wide before the next grid starts)
+    // release: the border rows this rank wrote into its neighbours' memory (earlier kernels of this stream, ordered before this
+    // thread by the grid boundary) become visible system-wide before the signal does -- fence cumulativity, PTX memory model
+    __threadfence_system();
     *((volatile unsigned long long *)&S.rsig[r][S.me]) = ((unsigned long long)epoch << 32) | fl;
     unsigned long long v;
     do { v = mysig[r]; } while ((unsigned)(v >> 32) < epoch);
