@@ -34,3 +34,17 @@ def test_two_gpu_parity_against_whole_box_oracle(halo):
     sys.stdout.write(r.stdout[-4000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("-> OK") >= 9 and "FAIL" not in r.stdout
+
+
+def test_four_gpu_parity_incl_an_empty_brick():
+    """4 ranks: 2x1x2 / 1x4x1 bricks, up to 8 links per brick, and -- settled_random -- a decomposition whose top brick owns no particle
+    (every rebuild is collective: the empty rank must take part; it once skipped the second list build of setup() and dead-locked)"""
+    import torch
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "4", "--master-addr", "127.0.0.1",
+                        "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "mgpu_check.py")], env=dict(os.environ), capture_output=True,
+                       text=True, timeout=600)
+    sys.stdout.write(r.stdout[-4000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("-> OK") >= 5 and "FAIL" not in r.stdout
