@@ -17,12 +17,16 @@
 //             the bed, so the locality of the gathers is kept; the bins are reached through an index list (crow) during
 //             the list build, so cells stay contiguous in the canonical order.  On the benchmark bed the longest lane of
 //             a warp then has 5.2 overlapping entries against a mean of 4.96 (unsorted: 7.6);
-//   phase 1   one lane per particle: list words requested with the particle's own state, partner positions gathered
-//             eight at a time, distance TESTED only -> touch mask of the row;
-//   phase 2   the lane walks its own overlapping entries in slot order: partner position / velocity / spin and the
-//             history quad are gathered (prefetched one contact ahead), the contact law runs with every lane of the
-//             warp busy, force / torque accumulate in registers.  No shared memory, no atomics, bitwise deterministic;
-//   epilogue  step_epilogue<> (fixes in script order, final + initial integrate, skin/2 trigger).
+//   phase 1   one lane per particle: the row's sixteen list words are requested with the particle's own state and parked in shared
+//             memory (one column per lane).  History styles: an entry that overlapped one sub-step ago goes to phase 2 UNTESTED (phase 2
+//             repeats the reference's own test on the operands it gathers anyway); only the other entries are distance-tested here, four
+//             partner positions in flight, and the first old contact's operands are requested in the same round trip;
+//   phase 2   the lane walks its (presumably) overlapping entries in slot order.  prep() consumes the gathered partner position /
+//             velocity / spin / history quad into 16 derived values, the NEXT entry's gathers are issued into the registers just
+//             consumed, contact() runs the contact law on the derived values while those loads fly; force / torque accumulate in
+//             registers.  No atomics, no inter-lane exchange, bitwise deterministic;
+//   epilogue  step_epilogue<> (fixes in script order, final + initial integrate, skin/2 trigger, ghost refresh on several GPUs).
+// Launch-uniform specialisations: M32 (rows of at most 16 granular slots) and StepParams::equal_spheres (one radius, one mass).
 #pragma once
 #include "sedi_step.cuh"
 
