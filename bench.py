@@ -244,7 +244,26 @@ def log(msg):
 T_START = time.perf_counter()
 
 
+def _watchdog(seconds):
+    """A multi-GPU run whose ranks wait for each other inside kernels (peer-memory barrier) or inside NCCL cannot be interrupted from
+    Python if a peer dies: leave the process -- and with it the CUDA context and the spinning kernel -- after `seconds` of wall clock
+    instead of hanging until somebody else's limit (SEDI_BENCH_WATCHDOG=0 disables)."""
+    import threading
+
+    def bark():
+        sys.stderr.write("bench.py: watchdog: no result after %d s, leaving (rank %s)\n" % (seconds, os.environ.get("RANK", "0")))
+        sys.stderr.flush()
+        os._exit(3)
+    t = threading.Timer(seconds, bark)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def main():
+    wd = float(os.environ.get("SEDI_BENCH_WATCHDOG", "1500"))
+    if wd > 0:
+        _watchdog(wd)
     if os.environ.get("SEDI_BENCH_TRACE"):
         import faulthandler
         faulthandler.dump_traceback_later(float(os.environ["SEDI_BENCH_TRACE"]), repeat=True, file=sys.stderr)
