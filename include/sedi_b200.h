@@ -111,7 +111,7 @@ int sedi_mesh_ncells(void *ptr);
 #define SEDI_FORCE_BUOY_BIT 4
 #define SEDI_FORCE_ADDEDMASS_BIT 8
 #define SEDI_FORCE_LIFT_BIT 16
-#define SEDI_FORCE_HISTORY_BIT 32   /* particleHistoryForce, enhancedCloud.C:197-234 (single GPU) */
+#define SEDI_FORCE_HISTORY_BIT 32   /* particleHistoryForce, enhancedCloud.C:197-234 (the state migrates with its particle) */
 #define SEDI_FORCE_WALL_LUB_BIT 64  /* lubricationForce against the y = 0 wall, enhancedCloud.C:235-248 */
 #define SEDI_FORCE_INLET_BIT 128    /* inletForce inside inletBox, enhancedCloud.C:249-257 */
 void sedi_coupling_config(void *ptr, int drag_model, int force_flags, double nub, double rhob, const double *g,
