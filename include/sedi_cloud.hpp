@@ -25,7 +25,7 @@ struct CloudProperties {          // constant/cloudProperties + transportPropert
   int subCycles;
   double g[3];
   bool particleDrag, particlePressureGrad, particleBuoyancy, particleAddedMass, particleLift;
-  bool particleHistoryForce, lubricationForce;        // enhancedCloud.C:595-598 (single GPU for the history force)
+  bool particleHistoryForce, lubricationForce;        // enhancedCloud.C:595-598
   double inletForce[3];           // enhancedCloud.C:600-608; active inside inletBox when |inletForce| > 0
   double inletBox[9];             // x1 x2 y1 y2 z1 z2 r1 r2 - (softParticleCloud.C:471, pointInRegion :1354-1415)
   int addParticleOption;          // 1 box, 2 hollow cylinder
