@@ -173,8 +173,11 @@ void sedi_average_info(void *ptr, double *totalVolume, double *totalVel, double 
 void sedi_get_timers(void *ptr, double *diffusionTimeCount, double *particleMoveTime, double *cpuTimeSplit);
 
 /* --- multi-GPU: one process per GPU, brick decomposition of the particle box (LAMMPS `processors Px Py Pz`).
- * The NCCL unique id is produced by rank 0 (sedi_comm_unique_id) and distributed by the host (MPI_Bcast in a real
- * lammpsFoam run, torch.distributed in bench.py); procgrid may be NULL (taken from the script / factorised). */
+ * A host that links with -DSEDI_HAVE_MPI needs none of these calls: the library bootstraps NCCL from the MPI_Comm handed to
+ * lammps_open / new LAMMPS (rank 0 creates the id, MPI_Bcast distributes it); SEDI_AUTO_COMM=1 does the same from the launcher
+ * environment (RANK / WORLD_SIZE, OMPI_*, PMI_*, SLURM_*) through a rendezvous file.  A host that bootstraps itself: the NCCL
+ * unique id is produced by rank 0 (sedi_comm_unique_id) and distributed by the host (torch.distributed in bench.py);
+ * procgrid may be NULL (taken from the script / factorised). */
 int sedi_comm_unique_id(void *out, int cap); /* returns the id size in bytes, 0 when NCCL is unavailable */
 int sedi_comm_init(void *ptr, int rank, int nranks, const void *nccl_unique_id, int id_bytes, const int *procgrid);
 int sedi_comm_rank(void *ptr);
